@@ -1,0 +1,87 @@
+"""ctypes binding of libfreehunch_b200.so (C ABI: include/free_hunch_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing the import fails loudly.  The only other
+library this loader will accept is the CPU *emulation* build used by the CPU test-suite
+(tests/emu/build_emu.sh), and only when the test harness asks for it explicitly through
+FREE_HUNCH_B200_EMU_LIB -- it is never selected automatically and never on a machine's product path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfreehunch_b200.so")
+
+c_void_p, c_int, c_double, c_long = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong
+
+_SIGNATURES = {
+    "fh_last_error": (ctypes.c_char_p, []),
+    "fh_version": (c_int, []),
+    "fh_launch_count": (c_long, [c_int]),
+    "fh_ctx_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]),
+    "fh_ctx_destroy": (c_int, [c_void_p]),
+    "fh_dct2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fh_state_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int]),
+    "fh_state_destroy": (c_int, [c_void_p]),
+    "fh_state_init": (c_int, [c_void_p, c_void_p, c_double, c_void_p]),
+    "fh_state_rank": (c_int, [c_void_p]),
+    "fh_state_var2": (c_double, [c_void_p]),
+    "fh_cov_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fh_time_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "fh_space_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
+    "fh_state_set_cov_vectors": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),
+    "fh_state_drop_all": (c_int, [c_void_p, c_double, c_void_p]),
+    "fh_state_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fh_op_create_conv": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int, c_int]),
+    "fh_op_create_inpaint": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int]),
+    "fh_op_destroy": (c_int, [c_void_p]),
+    "fh_op_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fh_cg_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class FreeHunchLibraryError(RuntimeError):
+    pass
+
+
+def _bind(path):
+    if not os.path.exists(path):
+        raise FreeHunchLibraryError(
+            f"{path} not found: build the sm_100a extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "free_hunch_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+_is_emu = False
+
+
+def lib():
+    """The loaded library (loads on first use)."""
+    global _lib, _is_emu
+    if _lib is None:
+        emu = os.environ.get("FREE_HUNCH_B200_EMU_LIB")
+        if emu:
+            _lib = _bind(emu)
+            _is_emu = True
+        else:
+            _lib = _bind(_LIB_PATH)
+    return _lib
+
+
+def is_emulated():
+    lib()
+    return _is_emu
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().fh_last_error()
+        raise FreeHunchLibraryError(f"libfreehunch_b200 error {rc}: {msg.decode() if msg else '?'}")

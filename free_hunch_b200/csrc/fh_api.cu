@@ -1,0 +1,612 @@
+// Host side of libfreehunch_b200: C ABI (include/free_hunch_b200.h) over the kernels in fh_dct.cuh and
+// fh_kernels.cuh.  No torch types, no hidden host<->device copies on the hot path except the CG
+// convergence poll (one 4-byte flag per image every few iterations).
+#include "fh_common.cuh"
+#include "fh_dct.cuh"
+#include "fh_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/free_hunch_b200.h"
+
+long long fh_g_launches = 0;
+static thread_local std::string g_err;
+
+#define FH_FAIL(code, ...)                         \
+  do {                                             \
+    char _b[512];                                  \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);         \
+    g_err = _b;                                    \
+    return (code);                                 \
+  } while (0)
+#define FH_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) FH_FAIL(FH_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+#define FH_KCHECK()                                                                            \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) FH_FAIL(FH_ECUDA, "kernel launch failed: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+struct fh_ctx {
+  int device, max_batch, C, H, W, max_rank;
+  long d;
+  float2 *tw256, *post, *cw;          // DCT tables
+  float* plane_tmp;                   // (max_batch, d) scratch for the 2-pass DCT
+  float* scratch[6];                  // (max_batch, d) general scratch vectors
+  double* dot_partial;                // (max_batch, nchunk, FH_MAXM+2)
+  double* csum;                       // (max_batch, FH_MAXM+2)
+  double* coef;                       // (max_batch, FH_MAXM)
+  double* gram_partial;               // (max_batch, FH_GRAM_CTAS, LD*LD)
+  double* gramK;                      // (max_batch, LD*LD)
+  double *part_a, *part_b;            // (max_batch, nchunk) scalar-dot partials
+  FhCgScalars* cg_sc;                 // (max_batch)
+  FhCgScalars* cg_sc_host;            // pinned
+  int* status;                        // device error counter (singular small matrices)
+  float* cgv[6];                      // CG vectors b,x,r,p,q,t  (max_batch, d)
+};
+
+struct fh_state {
+  fh_ctx* ctx;
+  int B, basis, m;
+  long d;
+  double var2;                        // effective sigma^2 of the state
+  float *pi, *delta, *Z;              // (B,d), (B,d), (B,FH_MAXM,d)
+  double *Gz, *Gs;                    // (B,FH_MAXM,FH_MAXM)
+};
+
+struct fh_op {
+  fh_ctx* ctx;
+  int kind, sf;
+  const float* mask; int mask_batch;
+  bool separable;
+  int* t_dy; int* t_dx; float* t_w; int nt, ymin, ymax, xmin, xmax;
+  float *kr, *kc; int nr, nc, cr, cc;
+};
+
+static inline dim3 ew_grid(long d, int B) { return dim3((unsigned)fh_nchunks(d), (unsigned)B, 1); }
+static inline int vec_ok(long d) { return (d % 4 == 0) ? 1 : 0; }
+
+extern "C" const char* fh_last_error(void) { return g_err.c_str(); }
+extern "C" int fh_version(void) { return 100; }
+extern "C" long long fh_launch_count(int reset) {
+  long long v = fh_g_launches;
+  if (reset) fh_g_launches = 0;
+  return v;
+}
+
+// --------------------------------------------------------------------------------------------- ctx
+extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channels, int height, int width, int max_rank) {
+  if (!out || max_batch < 1 || channels < 1 || height < 1 || width < 1) FH_FAIL(FH_EINVAL, "bad ctx arguments");
+  if (max_rank > FH_MAXM) FH_FAIL(FH_EINVAL, "max_rank %d > compiled limit %d", max_rank, FH_MAXM);
+  FH_CUDA(cudaSetDevice(device));
+  fh_ctx* c = (fh_ctx*)calloc(1, sizeof(fh_ctx));
+  c->device = device; c->max_batch = max_batch; c->C = channels; c->H = height; c->W = width; c->max_rank = max_rank;
+  c->d = (long)channels * height * width;
+  std::vector<float2> tw(FH_N), post(FH_N), cw(FH_N);
+  for (int j = 0; j < FH_N; ++j) {
+    const double a = -2.0 * M_PI * j / FH_N;
+    tw[j] = make_float2((float)cos(a), (float)sin(a));
+    const double th = -M_PI * j / (2.0 * FH_N);
+    const double f = (j == 0) ? sqrt(1.0 / FH_N) : sqrt(2.0 / FH_N);
+    post[j] = make_float2((float)(f * cos(th)), (float)(f * sin(th)));
+    cw[j] = make_float2((float)cos(-th), (float)sin(-th));
+  }
+  FH_CUDA(cudaMalloc((void**)&c->tw256, FH_N * sizeof(float2)));
+  FH_CUDA(cudaMalloc((void**)&c->post, FH_N * sizeof(float2)));
+  FH_CUDA(cudaMalloc((void**)&c->cw, FH_N * sizeof(float2)));
+  FH_CUDA(cudaMemcpy(c->tw256, tw.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
+  FH_CUDA(cudaMemcpy(c->post, post.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
+  FH_CUDA(cudaMemcpy(c->cw, cw.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
+  const size_t vec = (size_t)max_batch * c->d * sizeof(float);
+  FH_CUDA(cudaMalloc((void**)&c->plane_tmp, vec));
+  for (int i = 0; i < 6; ++i) FH_CUDA(cudaMalloc((void**)&c->scratch[i], vec));
+  for (int i = 0; i < 6; ++i) FH_CUDA(cudaMalloc((void**)&c->cgv[i], vec));
+  const int nch = fh_nchunks(c->d);
+  FH_CUDA(cudaMalloc((void**)&c->dot_partial, (size_t)max_batch * nch * (FH_MAXM + 2) * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->csum, (size_t)max_batch * (FH_MAXM + 2) * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->coef, (size_t)max_batch * FH_MAXM * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->gram_partial, (size_t)max_batch * FH_GRAM_CTAS * FH_GRAM_LD * FH_GRAM_LD * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->gramK, (size_t)max_batch * FH_GRAM_LD * FH_GRAM_LD * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->part_a, (size_t)max_batch * nch * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->part_b, (size_t)max_batch * nch * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->cg_sc, (size_t)max_batch * sizeof(FhCgScalars)));
+  FH_CUDA(cudaMallocHost((void**)&c->cg_sc_host, (size_t)max_batch * sizeof(FhCgScalars)));
+  FH_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
+  FH_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+#ifndef FH_EMU
+  const int core_smem = (2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * (int)sizeof(double);
+  FH_CUDA(cudaFuncSetAttribute(fh_k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, core_smem));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_core_from_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, core_smem));
+#endif
+  *out = c;
+  return FH_OK;
+}
+
+extern "C" int fh_ctx_destroy(fh_ctx* c) {
+  if (!c) return FH_OK;
+  cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
+  for (int i = 0; i < 6; ++i) { cudaFree(c->scratch[i]); cudaFree(c->cgv[i]); }
+  cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
+  cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFree(c->status);
+  free(c);
+  return FH_OK;
+}
+
+// --------------------------------------------------------------------------------------------- DCT
+static int dct2_planes(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, void* stream) {
+  if (c->H != FH_N || c->W != FH_N) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 planes (got %dx%d)", c->H, c->W);
+  if ((size_t)nplanes * FH_N * FH_N > (size_t)c->max_batch * c->d) FH_FAIL(FH_EINVAL, "too many planes for the scratch buffer");
+  FhDctTables tab{c->tw256, c->post, c->cw};
+  dim3 grid(FH_N / FH_DCT_ROWS, nplanes), block(FH_DCT_THREADS);
+  if (inverse) {
+    FH_LAUNCH(fh_k_dct_rows_t<true>, grid, block, 0, stream, in, c->plane_tmp, tab);
+    FH_LAUNCH(fh_k_dct_rows_t<true>, grid, block, 0, stream, c->plane_tmp, out, tab);
+  } else {
+    FH_LAUNCH(fh_k_dct_rows_t<false>, grid, block, 0, stream, in, c->plane_tmp, tab);
+    FH_LAUNCH(fh_k_dct_rows_t<false>, grid, block, 0, stream, c->plane_tmp, out, tab);
+  }
+  FH_KCHECK();
+  return FH_OK;
+}
+extern "C" int fh_dct2(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, void* stream) {
+  if (!c || !in || !out || nplanes < 1) FH_FAIL(FH_EINVAL, "bad fh_dct2 arguments");
+  return dct2_planes(c, in, out, nplanes, inverse, stream);
+}
+
+// ------------------------------------------------------------------------------------------- state
+extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) {
+  if (!c || !out || batch < 1 || batch > c->max_batch) FH_FAIL(FH_EINVAL, "bad fh_state_create arguments");
+  if (basis == FH_BASIS_DCT && (c->H != FH_N || c->W != FH_N)) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 images");
+  fh_state* s = (fh_state*)calloc(1, sizeof(fh_state));
+  s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0;
+  const size_t vec = (size_t)batch * s->d * sizeof(float);
+  FH_CUDA(cudaMalloc((void**)&s->pi, vec));
+  FH_CUDA(cudaMalloc((void**)&s->delta, vec));
+  FH_CUDA(cudaMalloc((void**)&s->Z, (size_t)batch * c->max_rank * s->d * sizeof(float) + 16));
+  FH_CUDA(cudaMalloc((void**)&s->Gz, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&s->Gs, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  *out = s;
+  return FH_OK;
+}
+extern "C" int fh_state_destroy(fh_state* s) {
+  if (!s) return FH_OK;
+  cudaFree(s->pi); cudaFree(s->delta); cudaFree(s->Z); cudaFree(s->Gz); cudaFree(s->Gs);
+  free(s);
+  return FH_OK;
+}
+extern "C" int fh_state_rank(const fh_state* s) { return s ? s->m : -1; }
+extern "C" double fh_state_var2(const fh_state* s) { return s ? s->var2 : -1.0; }
+
+// Z is allocated with row capacity ctx->max_rank but indexed with stride FH_MAXM in the kernels: keep them equal.
+static int check_rank_layout(fh_state* s) {
+  if (s->ctx->max_rank != FH_MAXM) FH_FAIL(FH_EINVAL, "ctx max_rank must equal %d in this build", FH_MAXM);
+  return FH_OK;
+}
+
+static int refresh_delta(fh_state* s, void* stream) {
+  FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->pi, s->delta, (float)(1.0 / s->var2), s->d, vec_ok(s->d));
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// K = Z diag(w) Z^T (+ extra rows) into ctx->gramK
+static int gram(fh_state* s, int m, FhRowPtrs xr, int nx, const float* w, void* stream) {
+  fh_ctx* c = s->ctx;
+  const size_t smem = (size_t)(FH_GRAM_MAXR * (FH_GRAM_TILE + 1) + FH_GRAM_TILE) * sizeof(float);
+  FH_LAUNCH(fh_k_gram, dim3(FH_GRAM_CTAS, s->B), dim3(256), smem, stream, s->Z, m, xr, nx, w, c->gram_partial, s->d);
+  FH_KCHECK();
+  FH_LAUNCH(fh_k_gram_reduce, dim3(s->B), dim3(256), 0, stream, c->gram_partial, FH_GRAM_CTAS, m + nx, c->gramK);
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// Recompute Gs for the current (pi, Z, Gz, var2).  If tu_s != null (score in the state's basis) also leaves the
+// time-update coefficient vector in ctx->coef.
+static int refresh_core(fh_state* s, const float* tu_s, double var2_old, void* stream) {
+  fh_ctx* c = s->ctx;
+  int rc = refresh_delta(s, stream);
+  if (rc) return rc;
+  if (s->m == 0) return FH_OK;
+  FhRowPtrs xr{};
+  int nx = 0;
+  if (tu_s) {
+    FH_LAUNCH(fh_k_tu_rows, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, tu_s, s->pi, s->delta, c->scratch[4], c->scratch[5], s->d, vec_ok(s->d));
+    FH_KCHECK();
+    xr.p[0] = tu_s; xr.p[1] = c->scratch[4]; xr.p[2] = c->scratch[5];
+    nx = 3;
+  }
+  rc = gram(s, s->m, xr, nx, s->delta, stream);
+  if (rc) return rc;
+  const size_t smem = (size_t)(2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * sizeof(double);
+  FH_LAUNCH(fh_k_core, dim3(s->B), dim3(256), smem, stream, c->gramK, s->Gz, s->m, s->Gs, tu_s ? 1 : 0, var2_old, c->coef, c->status);
+  FH_KCHECK();
+  return FH_OK;
+}
+
+extern "C" int fh_state_init(fh_state* s, const float* var_dev, double init_noise_variance, void* stream) {
+  if (!s || !var_dev || !(init_noise_variance > 0)) FH_FAIL(FH_EINVAL, "bad fh_state_init arguments");
+  int rc = check_rank_layout(s);
+  if (rc) return rc;
+  s->m = 0;
+  s->var2 = init_noise_variance;
+  FH_LAUNCH(fh_k_init_pi, dim3((unsigned)((s->d + 255) / 256), s->B), dim3(256), 0, stream, var_dev, s->pi, 1.0 / init_noise_variance, s->d);
+  FH_KCHECK();
+  FH_CUDA(cudaMemsetAsync(s->Gz, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  FH_CUDA(cudaMemsetAsync(s->Gs, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  return refresh_delta(s, stream);
+}
+
+// to / from the state's basis
+static int to_basis(fh_state* s, const float* in, float* out, void* stream) {
+  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 0, stream);
+  FH_CUDA(cudaMemcpyAsync(out, in, (size_t)s->B * s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return FH_OK;
+}
+static int from_basis(fh_state* s, const float* in, float* out, void* stream) {
+  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 1, stream);
+  FH_CUDA(cudaMemcpyAsync(out, in, (size_t)s->B * s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return FH_OK;
+}
+
+// out = Sigma v with v, out in the state's basis (out may alias v)
+static int cov_dot_basis(fh_state* s, const float* v, float* out, void* stream) {
+  fh_ctx* c = s->ctx;
+  const int vec = vec_ok(s->d);
+  if (s->m > 0) {
+    FH_LAUNCH(fh_k_dots, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, v, s->delta, (const float*)nullptr, (const float*)nullptr, c->dot_partial, s->d, vec);
+    FH_KCHECK();
+    FH_LAUNCH(fh_k_dots_finalize, dim3(s->B), dim3(128), 0, stream, c->dot_partial, fh_nchunks(s->d), s->m, 0, s->Gs, c->csum, c->coef);
+    FH_KCHECK();
+  }
+  // out = delta .* (v + Z^T coef)
+  FH_LAUNCH(fh_k_lowrank_apply, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, c->coef, s->delta, v, 1.0f, out, s->d, vec);
+  FH_KCHECK();
+  return FH_OK;
+}
+
+extern "C" int fh_cov_dot(fh_state* s, const float* v, float* out, void* stream) {
+  if (!s || !v || !out) FH_FAIL(FH_EINVAL, "bad fh_cov_dot arguments");
+  fh_ctx* c = s->ctx;
+  if (s->basis == FH_BASIS_IDENTITY) return cov_dot_basis(s, v, out, stream);
+  int rc = to_basis(s, v, c->scratch[0], stream);
+  if (rc) return rc;
+  rc = cov_dot_basis(s, c->scratch[0], c->scratch[0], stream);
+  if (rc) return rc;
+  return from_basis(s, c->scratch[0], out, stream);
+}
+
+extern "C" int fh_time_update(fh_state* s, const float* x, const float* score, double sigma_t, double sigma_tnext,
+                              int only_cov, float* mean_out, float* score_out, void* stream) {
+  if (!s || !(sigma_t > 0) || !(sigma_tnext > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update arguments");
+  if (!only_cov && (!x || !score || !mean_out || !score_out)) FH_FAIL(FH_EINVAL, "fh_time_update needs x, score and outputs");
+  fh_ctx* c = s->ctx;
+  const double var2_old = s->var2;
+  // the reference shifts the inverse-Hessian diagonal by a float32-rounded amount (online_update_bfgs.py:172)
+  s->var2 = var2_old + (double)(float)(sigma_tnext * sigma_tnext - sigma_t * sigma_t);
+  if (!(s->var2 > 0)) FH_FAIL(FH_ESTATE, "non-positive effective variance after time update");
+  if (only_cov) return refresh_core(s, nullptr, var2_old, stream);
+  int rc;
+  float* xh = c->scratch[0];
+  float* sh = c->scratch[1];
+  if ((rc = to_basis(s, x, xh, stream))) return rc;
+  if ((rc = to_basis(s, score, sh, stream))) return rc;
+  if ((rc = refresh_core(s, sh, var2_old, stream))) return rc;
+  FH_LAUNCH(fh_k_tu_apply, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, c->coef, sh, s->pi, s->delta, xh,
+            (float)var2_old, (float)(1.0 / s->var2), (float)(sigma_tnext * sigma_tnext), c->scratch[2], c->scratch[3], s->d, vec_ok(s->d));
+  FH_KCHECK();
+  if ((rc = from_basis(s, c->scratch[2], score_out, stream))) return rc;
+  return from_basis(s, c->scratch[3], mean_out, stream);
+}
+
+extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float* mean_at_xnext, double sigma_t,
+                               const float* x, const float* xnext, int project_to_diagonal, void* stream) {
+  if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update arguments");
+  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
+  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  fh_ctx* c = s->ctx;
+  const int vec = vec_ok(s->d);
+  int rc;
+  // H is rebuilt from Sigma at the true sigma (online_update_bfgs.py:294): drop the float32 drift of var2
+  if (s->var2 != sigma_t * sigma_t) {
+    s->var2 = sigma_t * sigma_t;
+    if ((rc = refresh_delta(s, stream))) return rc;
+  }
+  float* dxp = c->scratch[0];
+  float* dep = c->scratch[1];
+  FH_LAUNCH(fh_k_su_diffs, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, x, xnext, mean_at_x, mean_at_xnext,
+            (float)(sigma_t * sigma_t), dxp, dep, s->d, vec);
+  FH_KCHECK();
+  float* dx = c->scratch[2];
+  float* de = c->scratch[3];
+  if ((rc = to_basis(s, dxp, dx, stream))) return rc;
+  if ((rc = to_basis(s, dep, de, stream))) return rc;
+  // dots:  Z.de (rows 0..m-1) and dx.de (extra row dx)
+  FH_LAUNCH(fh_k_dots, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, de, (const float*)nullptr, dx, (const float*)nullptr, c->dot_partial, s->d, vec);
+  FH_KCHECK();
+  FH_LAUNCH(fh_k_dots_finalize, dim3(s->B), dim3(128), 0, stream, c->dot_partial, fh_nchunks(s->d), s->m, 1, s->Gz, c->csum, c->coef);
+  FH_KCHECK();
+  // rows m (dx) and m+1 (g = Sigma^-1 de = de./delta + Z^T Gz Z de); de.g partials -> part_b
+  FH_LAUNCH(fh_k_su_rows, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, c->coef, de, s->delta, dx, c->part_b, s->d, vec);
+  FH_KCHECK();
+  FH_LAUNCH(fh_k_bfgs_block, dim3((s->B + 63) / 64), dim3(64), 0, stream, s->Gz, s->m, c->csum, c->part_b, fh_nchunks(s->d), s->B);
+  FH_KCHECK();
+  s->m += 2;
+  return refresh_core(s, nullptr, s->var2, stream);
+}
+
+extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, const float* V, int kv, double sigma, void* stream) {
+  if (!s || ku < 0 || kv < 0 || ku + kv > FH_MAXM || !(sigma > 0)) FH_FAIL(FH_EINVAL, "bad fh_state_set_cov_vectors arguments");
+  fh_ctx* c = s->ctx;
+  const int vec = vec_ok(s->d);
+  int rc;
+  // current Sigma diagonal stays (delta at the current var2); Z = W ./ delta, Gz = -J (I + Kp J)^-1, Kp = W P W^T
+  if ((rc = refresh_delta(s, stream))) return rc;
+  const int m = ku + kv;
+  for (int b = 0; b < s->B; ++b)
+    for (int i = 0; i < m; ++i) {
+      const float* src = (i < ku) ? U + (size_t)i * s->d : V + (size_t)(i - ku) * s->d;
+      FH_CUDA(cudaMemcpyAsync(s->Z + ((size_t)b * FH_MAXM + i) * s->d, src, (size_t)s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+  // w = 1/delta = P  -> scratch[0];  Kp = W diag(P) W^T
+  FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->delta, c->scratch[0], 0.0f, s->d, vec);   // 1/(delta+0)
+  FH_KCHECK();
+  s->m = m;
+  FhRowPtrs xr{};
+  if ((rc = gram(s, m, xr, 0, c->scratch[0], stream))) return rc;
+  const size_t smem = (size_t)(2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * sizeof(double);
+  FH_LAUNCH(fh_k_core_from_cov, dim3(s->B), dim3(256), smem, stream, c->gramK, ku, kv, s->Gz, c->status);
+  FH_KCHECK();
+  // Z <- W .* P  (row by row, in place)
+  for (int b = 0; b < s->B; ++b)
+    for (int i = 0; i < m; ++i) {
+      float* row = s->Z + ((size_t)b * FH_MAXM + i) * s->d;
+      FH_LAUNCH(fh_k_lowrank_apply, dim3((unsigned)fh_nchunks(s->d), 1), dim3(FH_EW_THREADS), 0, stream, s->Z, 0, c->coef, c->scratch[0] + (size_t)b * s->d, row, 1.0f, row, s->d, vec);
+      FH_KCHECK();
+    }
+  // the diagonal of Sigma^-1 is P = 1/delta exactly as before: pi unchanged.  sigma fixes the H relation.
+  (void)sigma;         // Sigma's diagonal is defined at the current var2; `sigma` only fixes the H relation
+  return refresh_core(s, nullptr, s->var2, stream);
+}
+
+extern "C" int fh_state_drop_all(fh_state* s, double sigma, void* stream) {
+  if (!s) FH_FAIL(FH_EINVAL, "null state");
+  // Sigma <- its diagonal part delta at the current sigma:  pi = 1/delta - tau = pi (unchanged), Z dropped.
+  (void)sigma;
+  s->m = 0;
+  FH_CUDA(cudaMemsetAsync(s->Gz, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  FH_CUDA(cudaMemsetAsync(s->Gs, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  return FH_OK;
+}
+
+extern "C" int fh_state_export(fh_state* s, float* pi, float* Z, double* Gz, double* Gs, float* delta, void* stream) {
+  if (!s) FH_FAIL(FH_EINVAL, "null state");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t vec = (size_t)s->B * s->d * sizeof(float);
+  if (pi) FH_CUDA(cudaMemcpyAsync(pi, s->pi, vec, cudaMemcpyDeviceToDevice, st));
+  if (delta) FH_CUDA(cudaMemcpyAsync(delta, s->delta, vec, cudaMemcpyDeviceToDevice, st));
+  if (Z)
+    for (int b = 0; b < s->B; ++b)
+      if (s->m) FH_CUDA(cudaMemcpyAsync(Z + (size_t)b * s->m * s->d, s->Z + (size_t)b * FH_MAXM * s->d, (size_t)s->m * s->d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int which = 0; which < 2; ++which) {
+    double* dst = which ? Gs : Gz;
+    const double* src = which ? s->Gs : s->Gz;
+    if (!dst) continue;
+    for (int b = 0; b < s->B; ++b)
+      for (int i = 0; i < s->m; ++i)
+        FH_CUDA(cudaMemcpyAsync(dst + ((size_t)b * s->m + i) * s->m, src + ((size_t)b * FH_MAXM + i) * FH_MAXM, (size_t)s->m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  return FH_OK;
+}
+
+// --------------------------------------------------------------------------------------- operators
+extern "C" int fh_op_create_inpaint(fh_ctx* c, fh_op** out, const float* mask_dev, int mask_batch) {
+  if (!c || !out || !mask_dev || mask_batch < 1) FH_FAIL(FH_EINVAL, "bad fh_op_create_inpaint arguments");
+  fh_op* o = (fh_op*)calloc(1, sizeof(fh_op));
+  o->ctx = c; o->kind = FH_OP_INPAINT; o->sf = 1; o->mask = mask_dev; o->mask_batch = mask_batch;
+  *out = o;
+  return FH_OK;
+}
+
+extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int ks, int sf) {
+  if (!c || !out || !psf || ks < 1 || (ks & 1) == 0 || sf < 1) FH_FAIL(FH_EINVAL, "bad fh_op_create_conv arguments (odd ks required)");
+  if (c->H % sf || c->W % sf) FH_FAIL(FH_EINVAL, "image size not divisible by sf");
+  if (sf > 1 && ((c->H & (c->H - 1)) || (c->W & (c->W - 1)))) FH_FAIL(FH_EINVAL, "SR needs power-of-two image sizes");
+  fh_op* o = (fh_op*)calloc(1, sizeof(fh_op));
+  o->ctx = c; o->kind = sf > 1 ? FH_OP_SR : FH_OP_BLUR; o->sf = sf;
+  const int cen = ks / 2;                       // utils_sisr.py:37  roll by -int(ks/2)
+  std::vector<int> dy, dx; std::vector<float> w;
+  int ymin = 1 << 30, ymax = -(1 << 30), xmin = 1 << 30, xmax = -(1 << 30);
+  for (int a = 0; a < ks; ++a)
+    for (int b = 0; b < ks; ++b) {
+      const float v = psf[a * ks + b];
+      if (v != 0.f) {
+        dy.push_back(a - cen); dx.push_back(b - cen); w.push_back(v);
+        ymin = std::min(ymin, a - cen); ymax = std::max(ymax, a - cen);
+        xmin = std::min(xmin, b - cen); xmax = std::max(xmax, b - cen);
+      }
+    }
+  if (w.empty()) { free(o); FH_FAIL(FH_EINVAL, "PSF is all zeros"); }
+  if (ymax - ymin >= c->H || xmax - xmin >= c->W) { free(o); FH_FAIL(FH_EINVAL, "PSF support larger than the image"); }
+  o->nt = (int)w.size(); o->ymin = ymin; o->ymax = ymax; o->xmin = xmin; o->xmax = xmax;
+  FH_CUDA(cudaMalloc((void**)&o->t_dy, w.size() * sizeof(int)));
+  FH_CUDA(cudaMalloc((void**)&o->t_dx, w.size() * sizeof(int)));
+  FH_CUDA(cudaMalloc((void**)&o->t_w, w.size() * sizeof(float)));
+  FH_CUDA(cudaMemcpy(o->t_dy, dy.data(), w.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FH_CUDA(cudaMemcpy(o->t_dx, dx.data(), w.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FH_CUDA(cudaMemcpy(o->t_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // rank-1 test on the support box: psf == col (x) row exactly (to 1e-7 of the peak) -> separable path
+  o->separable = false;
+  if (sf == 1) {
+    const int hh = ymax - ymin + 1, ww = xmax - xmin + 1;
+    int pa = 0, pb = 0; double peak = 0;
+    for (int a = 0; a < hh; ++a) for (int b = 0; b < ww; ++b) {
+      const double v = fabs((double)psf[(a + ymin + cen) * ks + (b + xmin + cen)]);
+      if (v > peak) { peak = v; pa = a; pb = b; }
+    }
+    std::vector<double> col(hh), row(ww);
+    for (int a = 0; a < hh; ++a) col[a] = psf[(a + ymin + cen) * ks + (pb + xmin + cen)];
+    for (int b = 0; b < ww; ++b) row[b] = (double)psf[(pa + ymin + cen) * ks + (b + xmin + cen)] / col[pa];
+    double err = 0;
+    for (int a = 0; a < hh; ++a) for (int b = 0; b < ww; ++b)
+      err = std::max(err, fabs(col[a] * row[b] - (double)psf[(a + ymin + cen) * ks + (b + xmin + cen)]));
+    if (err <= 2e-7 * peak) {
+      o->separable = true;
+      std::vector<float> kc(hh), kr(ww);
+      for (int a = 0; a < hh; ++a) kc[a] = (float)col[a];
+      for (int b = 0; b < ww; ++b) kr[b] = (float)row[b];
+      o->nc = hh; o->nr = ww; o->cc = -ymin; o->cr = -xmin;
+      FH_CUDA(cudaMalloc((void**)&o->kc, hh * sizeof(float)));
+      FH_CUDA(cudaMalloc((void**)&o->kr, ww * sizeof(float)));
+      FH_CUDA(cudaMemcpy(o->kc, kc.data(), hh * sizeof(float), cudaMemcpyHostToDevice));
+      FH_CUDA(cudaMemcpy(o->kr, kr.data(), ww * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
+  *out = o;
+  return FH_OK;
+}
+
+extern "C" int fh_op_destroy(fh_op* o) {
+  if (!o) return FH_OK;
+  cudaFree(o->t_dy); cudaFree(o->t_dx); cudaFree(o->t_w); cudaFree(o->kr); cudaFree(o->kc);
+  free(o);
+  return FH_OK;
+}
+
+static long op_ylen(const fh_op* o) {
+  const fh_ctx* c = o->ctx;
+  return (long)c->C * (c->H / o->sf) * (c->W / o->sf);
+}
+
+extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int transpose, void* stream) {
+  if (!o || !in || !out || batch < 1) FH_FAIL(FH_EINVAL, "bad fh_op_apply arguments");
+  fh_ctx* c = o->ctx;
+  const int planes = batch * c->C;
+  if (o->kind == FH_OP_INPAINT) {
+    const long hw = (long)c->H * c->W;
+    FH_LAUNCH(fh_k_mask_mul, dim3((unsigned)((c->d + 255) / 256), batch), dim3(256), 0, stream, in, o->mask, o->mask_batch, out, c->C, hw);
+  } else if (o->kind == FH_OP_BLUR) {
+    if (c->H % 32 || c->W % 32) FH_FAIL(FH_EINVAL, "blur needs image sizes divisible by 32");
+    dim3 grid(c->W / 32, c->H / 32, planes), block(32, 8);
+    if (o->separable) {
+      FhSepTaps k{o->kr, o->kc, o->nr, o->nc, o->cr, o->cc};
+      const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
+      const size_t smem = (size_t)(th * tw + th * 33) * sizeof(float);
+      FH_LAUNCH(fh_k_conv_sep, grid, block, smem, stream, in, out, k, c->H, c->W, transpose);
+    } else {
+      FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
+      const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;
+      const size_t smem = (size_t)th * tw * sizeof(float);
+      FH_LAUNCH(fh_k_conv_taps, grid, block, smem, stream, in, out, t, c->H, c->W, transpose);
+    }
+  } else {
+    FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
+    const size_t smem = (size_t)o->nt * 3 * sizeof(float);
+    if (!transpose) {
+      const int n = (c->H / o->sf) * (c->W / o->sf);
+      FH_LAUNCH(fh_k_sr_forward, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+    } else {
+      const int n = c->H * c->W;
+      FH_LAUNCH(fh_k_sr_transpose, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+    }
+  }
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// --------------------------------------------------------------------------------------------- CG
+// t = A Sigma A^T p   (y-space in, y-space out); for inpainting the two mask multiplies are folded into the
+// callers (cg_q applies the outer mask; the inner one is applied here).
+static int apply_ASAt(fh_state* s, fh_op* o, const float* p, float* t, void* stream) {
+  fh_ctx* c = s->ctx;
+  int rc;
+  float* img = c->scratch[0];
+  if ((rc = fh_op_apply(o, p, img, s->B, 1, stream))) return rc;            // A^T p   (inpaint: mask.*p)
+  if (s->basis == FH_BASIS_DCT) {
+    if ((rc = to_basis(s, img, c->scratch[1], stream))) return rc;
+    if ((rc = cov_dot_basis(s, c->scratch[1], c->scratch[1], stream))) return rc;
+    if ((rc = from_basis(s, c->scratch[1], img, stream))) return rc;
+  } else {
+    if ((rc = cov_dot_basis(s, img, img, stream))) return rc;
+  }
+  if (o->kind == FH_OP_INPAINT) {
+    // outer mask is applied inside fh_k_cg_q
+    FH_CUDA(cudaMemcpyAsync(t, img, (size_t)s->B * s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FH_OK;
+  }
+  return fh_op_apply(o, img, t, s->B, 0, stream);
+}
+
+extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
+                           int maxiter, int fixed_iters, float* mat_out, int* niter_host, int* optimal_host,
+                           double* resid_host, void* stream) {
+  if (!s || !o || !y || !mu || !mat_out || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve arguments");
+  if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n = op_ylen(o);
+  const int B = s->B;
+  const int nblk = fh_nchunks(n);
+  const long hw = (long)(c->H / o->sf) * (c->W / o->sf);
+  const float* mask = (o->kind == FH_OP_INPAINT) ? o->mask : nullptr;
+  const int mb = o->mask_batch;
+  float *bv = c->cgv[0], *x = c->cgv[1], *r = c->cgv[2], *p = c->cgv[3], *q = c->cgv[4], *t = c->cgv[5];
+  int rc;
+  // rhs and x0 = b
+  const float* amu = mu;
+  if (o->kind != FH_OP_INPAINT) {
+    if ((rc = fh_op_apply(o, mu, t, B, 0, stream))) return rc;
+    amu = t;
+  }
+  FH_LAUNCH(fh_k_cg_rhs, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, amu, mask, mb, hw, bv, x, n);
+  FH_KCHECK();
+  // r0 = b - A_op x0, p0 = r0
+  FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
+  if ((rc = apply_ASAt(s, o, x, t, stream))) return rc;
+  FH_LAUNCH(fh_k_cg_q, dim3(nblk, B), dim3(FH_EW_THREADS), 0, stream, x, t, mask, mb, hw, (float)sigma_y2, q, c->part_a, c->cg_sc, n);
+  FH_KCHECK();
+  FH_LAUNCH(fh_k_cg_init, dim3(nblk, B), dim3(FH_EW_THREADS), 0, stream, bv, q, r, p, c->part_a, c->part_b, n);
+  FH_KCHECK();
+  const int use_stop = fixed_iters > 0 ? 0 : 1;
+  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
+  FH_LAUNCH(fh_k_cg_init_scalars, dim3((B + 63) / 64), dim3(64), 0, stream, c->cg_sc, c->part_a, c->part_b, nblk, rtol, 0.0, use_stop, B);
+  FH_KCHECK();
+  int poll = 4;
+  int since = 0;
+  for (int it = 1; it <= last; ++it) {
+    if ((rc = apply_ASAt(s, o, p, t, stream))) return rc;
+    FH_LAUNCH(fh_k_cg_q, dim3(nblk, B), dim3(FH_EW_THREADS), 0, stream, p, t, mask, mb, hw, (float)sigma_y2, q, c->part_a, c->cg_sc, n);
+    FH_LAUNCH(fh_k_cg_update1, dim3(nblk, B), dim3(FH_EW_THREADS), 0, stream, x, r, p, q, c->part_a, c->part_b, c->cg_sc, it, n);
+    FH_LAUNCH(fh_k_cg_update2, dim3(nblk, B), dim3(FH_EW_THREADS), 0, stream, r, p, c->part_b, c->cg_sc, it, last, n);
+    FH_KCHECK();
+    if (++since >= poll || it == last) {
+      since = 0;
+      FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+      FH_CUDA(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < B; ++b) all = all && c->cg_sc_host[b].done;
+      if (all) break;
+      if (poll < 16) poll *= 2;
+    }
+  }
+  for (int b = 0; b < B; ++b) {
+    if (niter_host) niter_host[b] = c->cg_sc_host[b].niter;
+    if (optimal_host) optimal_host[b] = c->cg_sc_host[b].optimal;
+    if (resid_host) resid_host[b] = sqrt(c->cg_sc_host[b].resid2);
+  }
+  // mat = u (inpainting) or A^T u
+  if (o->kind == FH_OP_INPAINT) {
+    FH_CUDA(cudaMemcpyAsync(mat_out, x, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FH_OK;
+  }
+  return fh_op_apply(o, x, mat_out, B, 1, stream);
+}

@@ -1,0 +1,219 @@
+"""Object layer over the C ABI: device workspace, covariance state, measurement operator, CG solve.
+
+Tensors go in and out as torch tensors on the context's device (float32, contiguous); the C library only
+sees raw pointers and the current CUDA stream.  Nothing here computes on the host.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+BASIS_IDENTITY, BASIS_DCT = 0, 1
+MAX_RANK = 64            # FH_MAXM: rows of Z (two per BFGS space update)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Context:
+    """fh_ctx: twiddle tables, scratch planes and reduction buffers for up to `max_batch` images."""
+
+    def __init__(self, device, max_batch=1, channels=3, height=256, width=256):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and not _lib.is_emulated():
+            raise _lib.FreeHunchLibraryError("free_hunch_b200 needs a CUDA device (no CPU fallback)")
+        self.max_batch, self.C, self.H, self.W = max_batch, channels, height, width
+        self.d = channels * height * width
+        h = ctypes.c_void_p()
+        idx = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
+        if self.device.type == "cuda":
+            torch.cuda.set_device(idx)
+        _lib.check(_lib.lib().fh_ctx_create(ctypes.byref(h), idx, max_batch, channels, height, width, MAX_RANK))
+        self._h = h
+
+    def stream(self):
+        if self.device.type == "cuda":
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def prep(self, t, shape=None):
+        t = torch.as_tensor(t).to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def dct2(self, x, inverse=False):
+        """Orthonormal 2-D DCT-II / DCT-III over the last two axes (256 x 256)."""
+        x = self.prep(x)
+        if x.shape[-2:] != (256, 256):
+            raise ValueError("dct2 needs 256x256 planes")
+        nplanes = x.numel() // (256 * 256)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().fh_dct2(self._h, _ptr(x), _ptr(out), nplanes, 1 if inverse else 0, self.stream()))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fh_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CovState:
+    """fh_state: Sigma(sigma) = (diag(pi) + sigma^-2 I + Z^T Gz Z)^-1 for `batch` images."""
+
+    def __init__(self, ctx, batch=1, basis=BASIS_DCT):
+        self.ctx, self.B, self.basis = ctx, batch, basis
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fh_state_create(ctx._h, ctypes.byref(h), batch, basis))
+        self._h = h
+        self.shape = (batch, ctx.C, ctx.H, ctx.W)
+
+    def init(self, init_variance, init_noise_variance):
+        v = self.ctx.prep(init_variance).reshape(-1)
+        if v.numel() != self.ctx.d:
+            raise ValueError(f"init_variance must have {self.ctx.d} elements")
+        _lib.check(_lib.lib().fh_state_init(self._h, _ptr(v), float(init_noise_variance), self.ctx.stream()))
+        self._keep = v
+
+    @property
+    def rank(self):
+        return _lib.lib().fh_state_rank(self._h)
+
+    @property
+    def var2(self):
+        return _lib.lib().fh_state_var2(self._h)
+
+    def cov_dot(self, v):
+        v = self.ctx.prep(v, self.shape)
+        out = torch.empty_like(v)
+        _lib.check(_lib.lib().fh_cov_dot(self._h, _ptr(v), _ptr(out), self.ctx.stream()))
+        return out
+
+    def time_update(self, x, score, sigma_t, sigma_tnext, only_covariance=False):
+        if only_covariance:
+            _lib.check(_lib.lib().fh_time_update(self._h, None, None, float(sigma_t), float(sigma_tnext), 1, None, None,
+                                                 self.ctx.stream()))
+            return None, None
+        x = self.ctx.prep(x, self.shape)
+        score = self.ctx.prep(score, self.shape)
+        mean, sc = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(_lib.lib().fh_time_update(self._h, _ptr(x), _ptr(score), float(sigma_t), float(sigma_tnext), 0,
+                                             _ptr(mean), _ptr(sc), self.ctx.stream()))
+        return mean, sc
+
+    def space_update(self, mean_at_x, mean_at_xnext, sigma_t, x, xnext, project_to_diagonal=False):
+        a = self.ctx.prep(mean_at_x, self.shape)
+        b = self.ctx.prep(mean_at_xnext, self.shape)
+        c = self.ctx.prep(x, self.shape)
+        d = self.ctx.prep(xnext, self.shape)
+        _lib.check(_lib.lib().fh_space_update(self._h, _ptr(a), _ptr(b), float(sigma_t), _ptr(c), _ptr(d),
+                                              1 if project_to_diagonal else 0, self.ctx.stream()))
+
+    def set_cov_vectors(self, U, V, sigma):
+        """U: (ku, d), V: (kv, d) rows of Sigma = diag + U^T U - V^T V (same for every image of the batch)."""
+        U = self.ctx.prep(U).reshape(-1, self.ctx.d)
+        V = self.ctx.prep(V).reshape(-1, self.ctx.d)
+        _lib.check(_lib.lib().fh_state_set_cov_vectors(self._h, _ptr(U), U.shape[0], _ptr(V), V.shape[0], float(sigma),
+                                                       self.ctx.stream()))
+
+    def drop_all(self, sigma):
+        _lib.check(_lib.lib().fh_state_drop_all(self._h, float(sigma), self.ctx.stream()))
+
+    def export(self):
+        """(pi, Z, Gz, Gs, delta) as tensors; Z is (B, m, d), Gz/Gs are (B, m, m) float64."""
+        m, B, d, dev = self.rank, self.B, self.ctx.d, self.ctx.device
+        pi = torch.empty(B, d, dtype=torch.float32, device=dev)
+        delta = torch.empty_like(pi)
+        Z = torch.empty(B, m, d, dtype=torch.float32, device=dev)
+        Gz = torch.empty(B, m, m, dtype=torch.float64, device=dev)
+        Gs = torch.empty_like(Gz)
+        _lib.check(_lib.lib().fh_state_export(self._h, _ptr(pi), _ptr(Z) if m else None, _ptr(Gz) if m else None,
+                                              _ptr(Gs) if m else None, _ptr(delta), self.ctx.stream()))
+        return pi, Z, Gz, Gs, delta
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fh_state_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Operator:
+    """fh_op: A / A^T of one of the linear measurement operators."""
+
+    def __init__(self, ctx, handle, kind, sf=1, keep=None):
+        self.ctx, self._h, self.kind, self.sf, self._keep = ctx, handle, kind, sf, keep
+
+    @classmethod
+    def conv(cls, ctx, psf, sf=1):
+        psf = np.ascontiguousarray(np.asarray(psf, np.float32))
+        if psf.ndim != 2 or psf.shape[0] != psf.shape[1]:
+            raise ValueError("psf must be square")
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fh_op_create_conv(ctx._h, ctypes.byref(h), psf.ctypes.data_as(ctypes.c_void_p),
+                                                psf.shape[0], sf))
+        return cls(ctx, h, "sr" if sf > 1 else "blur", sf)
+
+    @classmethod
+    def inpaint(cls, ctx, mask):
+        """mask: (H, W) or (B, H, W) of {0,1} (1 = observed)."""
+        m = ctx.prep(mask)
+        m = m.reshape(-1, ctx.H, ctx.W)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fh_op_create_inpaint(ctx._h, ctypes.byref(h), _ptr(m), m.shape[0]))
+        return cls(ctx, h, "inpaint", 1, keep=m)
+
+    def y_shape(self, batch):
+        return (batch, self.ctx.C, self.ctx.H // self.sf, self.ctx.W // self.sf)
+
+    def apply(self, x, transpose=False):
+        x = self.ctx.prep(x)
+        B = x.shape[0]
+        out_shape = (B, self.ctx.C, self.ctx.H, self.ctx.W) if transpose else self.y_shape(B)
+        out = torch.empty(out_shape, dtype=torch.float32, device=self.ctx.device)
+        _lib.check(_lib.lib().fh_op_apply(self._h, _ptr(x), _ptr(out), B, 1 if transpose else 0, self.ctx.stream()))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fh_op_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cg_solve(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
+    """(mat, info): the guidance solve of conditioning_mechanisms.py:384-419/489-527/641-675 for a batch."""
+    ctx = state.ctx
+    y = ctx.prep(y, op.y_shape(state.B))
+    mu = ctx.prep(mu, state.shape)
+    mat = torch.empty_like(mu)
+    niter = (ctypes.c_int * state.B)()
+    optimal = (ctypes.c_int * state.B)()
+    resid = (ctypes.c_double * state.B)()
+    _lib.check(_lib.lib().fh_cg_solve(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
+                                      int(fixed_iters), _ptr(mat), niter, optimal, resid, ctx.stream()))
+    info = {"niter": list(niter), "optimal": [bool(o) for o in optimal], "residual_norm": list(resid)}
+    return mat, info
+
+
+def launch_count(reset=False):
+    return int(_lib.lib().fh_launch_count(1 if reset else 0))

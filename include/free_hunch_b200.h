@@ -1,0 +1,117 @@
+/*
+ * free_hunch_b200 -- C ABI of the B200-native Free Hunch guided-sampling hot path.
+ *
+ * The reference (AaltoML/free-hunch) is pure Python and has no FFI; this header is the boundary a
+ * maintainer would bind (ctypes stub in INTEGRATION.md).  Every entry point names the reference
+ * interface it replaces (file:line relative to the reference root).  All pointers named *_dev are
+ * caller-owned device buffers of float32 unless stated otherwise; `stream` is a cudaStream_t passed as
+ * void*.  Functions return 0 on success and a negative FH_E* code on failure; fh_last_error() gives text.
+ * Nothing in this library falls back to the CPU: without a CUDA device every call fails with FH_ECUDA.
+ *
+ * Layout: an "image vector" is (B, C, H, W) contiguous float32, d = C*H*W per image.  In the DCT basis
+ * (image_base_covariance = dct_diagonal) H = W = 256 is required.
+ */
+#ifndef FREE_HUNCH_B200_H
+#define FREE_HUNCH_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH_OK 0
+#define FH_EINVAL (-1)
+#define FH_ECUDA (-2)
+#define FH_ERANK (-3) /* low-rank capacity exhausted */
+#define FH_ESTATE (-4)
+
+#define FH_BASIS_IDENTITY 0 /* CovarianceHessianBFGS     online_update_bfgs.py:7   */
+#define FH_BASIS_DCT 1      /* CovarianceHessianBFGSDCT  online_update_bfgs.py:339 */
+
+#define FH_OP_INPAINT 0 /* measurements.py:204 + conditioning_mechanisms.py:384 */
+#define FH_OP_BLUR 1    /* measurements.py:126,164 + conditioning_mechanisms.py:489 (gaussian and motion) */
+#define FH_OP_SR 2      /* measurements.py:87 + conditioning_mechanisms.py:641 */
+
+typedef struct fh_ctx fh_ctx;     /* per-device workspace: twiddles, scratch planes, reduction buffers */
+typedef struct fh_state fh_state; /* covariance state of B images: prior precision diag(pi)+Z^T Gz Z   */
+typedef struct fh_op fh_op;       /* measurement operator A / A^T                                       */
+
+const char* fh_last_error(void);
+int fh_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channels, int height, int width, int max_rank);
+int fh_ctx_destroy(fh_ctx* ctx);
+
+/* Orthonormal 2-D DCT-II (inverse=0) / DCT-III (inverse=1) of `nplanes` 256x256 planes.
+ * Replaces torch_dct.dct_2d / idct_2d(norm='ortho'), call sites online_update_bfgs.py:352-374. */
+int fh_dct2(fh_ctx* ctx, const float* in_dev, float* out_dev, int nplanes, int inverse, void* stream);
+
+/* ---- covariance state ------------------------------------------------------------------------
+ * fh_state_create + fh_state_init replace CovarianceHessianBFGS.__init__ (online_update_bfgs.py:12-56)
+ * and CovarianceHessianBFGSDCT.__init__ (:341-349).  init_variance_dev holds d values (shared by all B
+ * images): the initial diagonal of Sigma (dct_variance.pt, or ones). */
+int fh_state_create(fh_ctx* ctx, fh_state** out, int batch, int basis);
+int fh_state_destroy(fh_state* st);
+int fh_state_init(fh_state* st, const float* init_variance_dev, double init_noise_variance, void* stream);
+int fh_state_rank(const fh_state* st); /* m = rows of Z (2 per space update) */
+double fh_state_var2(const fh_state* st);
+
+/* Sigma . v  -- denoiser_cov_vector_dot, online_update_bfgs.py:194-204 (identity) and :370-374 (DCT:
+ * v and the result are in pixel space, DCT -> diag+low-rank -> IDCT happens inside). */
+int fh_cov_dot(fh_state* st, const float* v_dev, float* out_dev, void* stream);
+
+/* update_time_step, online_update_bfgs.py:153-192 (+ DCT wrapper :357-360).  x/score/mean_out/score_out
+ * are (B,d).  only_covariance!=0 skips the score/mean update (outputs untouched, may be NULL). */
+int fh_time_update(fh_state* st, const float* x_dev, const float* score_dev, double sigma_t, double sigma_tnext,
+                   int only_covariance, float* mean_out_dev, float* score_out_dev, void* stream);
+
+/* update_space_step, online_update_bfgs.py:247-312 (+ DCT wrapper :362-368); project_to_diagonal variant
+ * when project_to_diagonal != 0 (:274-277). */
+int fh_space_update(fh_state* st, const float* mean_at_x_dev, const float* mean_at_xnext_dev, double sigma_t,
+                    const float* x_dev, const float* xnext_dev, int project_to_diagonal, void* stream);
+
+/* Test hooks of the reference tests (online_update_tests.py:153-155): load Sigma = diag + U U^T - V V^T
+ * (U: ku x d rows, V: kv x d rows, identical for all B images) and rebuild everything else
+ * (set_others_corresponding_to_current_denoiser_cov, online_update_bfgs.py:327-330). */
+int fh_state_set_cov_vectors(fh_state* st, const float* U_dev, int ku, const float* V_dev, int kv, double sigma,
+                             void* stream);
+/* drop_vectors(0, sigma), online_update_bfgs.py:235-239: forget the low-rank part of Sigma at `sigma`. */
+int fh_state_drop_all(fh_state* st, double sigma, void* stream);
+/* Export for get_dense_matrices (online_update_bfgs.py:320-325): pi (B,d) f32, Z (B,m,d) f32,
+ * Gz (B,m,m) f64, Gs (B,m,m) f64, delta (B,d) f32; any pointer may be NULL. */
+int fh_state_export(fh_state* st, float* pi_dev, float* Z_dev, double* Gz_dev, double* Gs_dev, float* delta_dev,
+                    void* stream);
+
+/* ---- measurement operators ------------------------------------------------------------------- */
+/* Circular convolution with a ks x ks PSF (host pointer, row-major), the FFT operator of
+ * measurements.py:140-157,180-198 / utils_sisr.py:22-41 evaluated directly in pixel space:
+ * (A x)[i,j] = sum_{a,b} psf[a,b] x[(i-(a-ks/2)) mod H, (j-(b-ks/2)) mod W].  sf>1 adds the x`sf`
+ * decimation of utils_sisr.py:44-61 (FH_OP_SR). */
+int fh_op_create_conv(fh_ctx* ctx, fh_op** out, const float* psf_host, int ks, int sf);
+/* Inpainting mask (measurements.py:204-246): mask_dev is (B,H,W) or (1,H,W) float32 of {0,1},
+ * applied to all channels; the pointer is borrowed, not copied. */
+int fh_op_create_inpaint(fh_ctx* ctx, fh_op** out, const float* mask_dev, int mask_batch);
+int fh_op_destroy(fh_op* op);
+/* y = A x (transpose=0; x: (B,C,H,W), y: (B,C,H/sf,W/sf)) or x = A^T y (transpose=1). */
+int fh_op_apply(fh_op* op, const float* in_dev, float* out_dev, int batch, int transpose, void* stream);
+
+/* ---- CG guidance solve ------------------------------------------------------------------------
+ * Replaces conditioning_utils/cg.py:118-292 specialised to the three `*_mat_generic_customcuda_bfgs_tailored`
+ * solvers (conditioning_mechanisms.py:384-419, 489-527, 641-675):
+ *   b = A-side residual (inpaint: m*y - m*mu ; else y - A mu),  x0 = b,
+ *   solve (sigma_y2 I + A Sigma A^T) u = b until |r| <= rtol*|b|  (or p.Ap <= 1e-16, or maxiter),
+ *   mat = u (inpaint) or A^T u.
+ * y_dev: (B, y-shape), mu_dev/mat_out_dev: (B,C,H,W).  niter_host/optimal_host/resid_host: B entries each
+ * (host memory, may be NULL).  fixed_iters>0 disables the residual test and runs exactly that many
+ * iterations (test hook).  Per-image convergence is tracked on the device; the host polls a flag every
+ * few iterations. */
+int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
+                int maxiter, int fixed_iters, float* mat_out_dev, int* niter_host, int* optimal_host,
+                double* resid_host, void* stream);
+/* Counters for bench.py: kernels launched by this library since the last reset. */
+long long fh_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
