@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the Free Hunch guided-sampling hot path on B200 (contract: see DESIGN.md "Measurement").
+
+One *step* = one guided sampling of a micro-batch of B synthetic 256x256 images through the whole
+N-evaluation EDM loop (30-step Heun = 59 mechanism calls by default), every call running the covariance
+time/space updates, the CG guidance solve and the measurement operators in libfreehunch_b200.so.
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                   the CPU restatement of the reference on host cores
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same through host
+buffers (pinned y / noise -> device, final image -> host inside the timed region); `roofline` = the dominant
+kernel's algorithmic bytes / CUDA-event time; `cpu_baseline` = oracle/fh_oracle.py on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "free_hunch_images_per_s_256x256"
+UNIT = "images/s"
+D_VEC_BYTES = 3 * 256 * 256 * 4          # one float32 image vector (786 432 B)
+
+OPERATORS = {"gaussian_blur": "gaussian_ks61_std3", "motion_blur": "motion_ks61_std05",
+             "super_resolution": "bicubic_x4", "inpainting": None}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("FH_BENCH_BATCH", "1")),
+                    help="images sampled concurrently per GPU (independent covariance states)")
+    ap.add_argument("--operator", default="gaussian_blur", choices=list(OPERATORS))
+    ap.add_argument("--num-steps", type=int, default=30, help="EDM sigma steps (30 Heun / 100 Euler in BASELINE)")
+    ap.add_argument("--solver", default="heun", choices=["heun", "euler"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"configs[1]: {a.operator} sigma_y=0.1 ks=61, Free Hunch (dct_diagonal, space updates 1<sigma<10), "
+            f"{a.num_steps}-step {a.solver}, 3x256x256, micro-batch {a.batch}/GPU")
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def synth_inputs(assets, operator, n_images, seed0):
+    """Synthetic clean images drawn from the DCT-diagonal Gaussian prior, measurement noise and
+    initial noise, all seeded by the global image index so results do not depend on the world size."""
+    import scipy.fft as sfft
+    var = assets["dct_variance"].astype(np.float64)
+    xs, noises, ynoise = [], [], []
+    for i in range(n_images):
+        rs = np.random.RandomState(seed0 + i)
+        z = rs.standard_normal(var.shape) * np.sqrt(var)
+        xs.append(np.clip(sfft.idctn(z, type=2, norm="ortho", axes=(-2, -1)), -1, 1))
+        noises.append(rs.standard_normal(var.shape))
+        ynoise.append(rs.standard_normal(var.shape))
+    return np.stack(xs), np.stack(noises), np.stack(ynoise)
+
+
+def random_mask(seed):
+    """measurements.py:287-299 semantics (random p in [0.6, 0.8]), seeded per image."""
+    rs = np.random.RandomState(seed)
+    prob = rs.uniform(0.6, 0.8)
+    m = np.ones(256 * 256, np.float32)
+    m[rs.choice(256 * 256, int(256 * 256 * prob), replace=False)] = 0
+    return m.reshape(256, 256)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_sample(assets, a, budget_s, threads):
+    """The reference algorithm (oracle/fh_oracle.py: float64 CG, complex128 covariance state -- the reference's own
+    precision) on the host cores for a BOUNDED prefix of the same workload: mechanism calls of image 0 are run until
+    `budget_s` seconds are spent.  Returns per-call records so the caller can scale to images/s."""
+    import torch
+    from oracle import fh_oracle as fo
+    torch.set_num_threads(threads)
+    var = assets["dct_variance"]
+    x_clean, noise, ynoise = synth_inputs(assets, a.operator, 1, 1000)
+    if a.operator == "inpainting":
+        mask = np.broadcast_to(random_mask(1000), (1, 3, 256, 256))
+        op = fo.InpaintingOracle(mask, 0.1)
+        y = (x_clean + 0.1 * ynoise) * mask
+    elif a.operator == "super_resolution":
+        op = fo.SuperResolutionOracle(assets["bicubic_x4"], 0.1, 4)
+        y = op.A(x_clean) + 0.1 * ynoise[..., :64, :64]
+    else:
+        cls = fo.GaussianBlurOracle if a.operator == "gaussian_blur" else fo.MotionBlurOracle
+        op = cls(assets[OPERATORS[a.operator]], 0.1)
+        y = op.A(x_clean) + 0.1 * ynoise
+    t_steps = fo.edm_sigma_steps(a.num_steps)
+    mech = fo.FreeHunchOracle(op, fo.CovarianceOracleDCT(var, t_steps[0] ** 2, var.size))
+    model = fo.analytic_dct_gaussian_denoiser(var)
+    calls = []
+    t_begin = time.perf_counter()
+
+    class Budget(Exception):
+        pass
+
+    def timed(x_t, mdl, yy, s):
+        t0 = time.perf_counter()
+        out = mech(x_t, mdl, yy, s)
+        calls.append({"sigma": float(s), "seconds": time.perf_counter() - t0, "niter": mech.log[-1]["niter"]})
+        if time.perf_counter() - t_begin > budget_s:
+            raise Budget()
+        return out
+    try:
+        fo.conditional_sampler(timed, model, y, noise, t_steps, solver=a.solver)
+        complete = True
+    except Budget:
+        complete = False
+    return calls, complete, time.perf_counter() - t_begin
+
+
+def total_calls(a):
+    return 2 * a.num_steps - 1 if a.solver == "heun" else a.num_steps
+
+
+def run_reference_arm(a, assets):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # W warm-up "steps" are skipped for the CPU arm beyond a single short call budget; each step is a bounded sample
+    per_step = max(5.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + min(a.warmup, 1))))
+    if a.warmup > 0:
+        cpu_reference_sample(assets, a, min(3.0, per_step), cores)
+    vals, samples = [], []
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        calls, complete, secs = cpu_reference_sample(assets, a, per_step, cores)
+        n = len(calls)
+        vals.append((n / total_calls(a)) / secs)
+        samples.append(n)
+    ms = (time.perf_counter() - t0) / max(1, a.steps) * 1e3
+    v = float(np.mean(vals))
+    sample = (f"first {samples[0]} of {total_calls(a)} mechanism calls of one image per step (~{per_step:.0f} s budget), "
+              f"images/s = (calls done / {total_calls(a)}) / seconds; early calls carry the most CG iterations, so this "
+              f"is a lower bound on the CPU's whole-image rate")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/c128",
+        "data": "synthetic", "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (numpy)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def algorithmic_bytes(kernel, k_rows, B, n_y=None):
+    """Algorithmic bytes per launch of the library's kernels (DESIGN.md "Kernels"): every operand touched once.
+    k_rows = rows of Z (2 per BFGS pair); unit = one float32 image vector."""
+    u = D_VEC_BYTES * B
+    table = {
+        "fh_k_dots": (2 + k_rows) * u,                 # v, delta, Z rows
+        "fh_k_lowrank_apply": (3 + k_rows) * u,        # v, delta, Z rows, out
+        "fh_k_dct_rows_t<false>": 2 * u, "fh_k_dct_rows_t<true>": 2 * u,
+        "fh_k_conv_sep": 2 * u, "fh_k_conv_taps": 2 * u,
+        "fh_k_cg_q": 3 * u, "fh_k_cg_update1": 6 * u, "fh_k_cg_update2": 3 * u,
+        "fh_k_gram": (1 + k_rows) * u,
+    }
+    return table.get(kernel)
+
+
+def run_b200(a, assets):
+    import torch
+    import torch.distributed as dist
+    from free_hunch_b200 import engine as E
+    from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism, PhaseTimer
+    from free_hunch_b200.measurements import get_operator
+    from free_hunch_b200.sampler import AnalyticDCTGaussianDenoiser, conditional_sampler, edm_sigma_steps
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: free_hunch_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.batch
+    var = assets["dct_variance"]
+    t_steps = edm_sigma_steps(a.num_steps)
+    n_iter = a.warmup + 2 * a.steps + 1            # value steps + e2e steps + one profiled step
+    # every step samples NEW images: global image index = step * world * B + rank * B + b  (weak scaling)
+    seed_of = lambda step: 1000 + (step * world + rank) * B
+
+    def make_problem(step):
+        x_clean, noise, ynoise = synth_inputs(assets, a.operator, B, seed_of(step))
+        kw = dict(in_shape=(B, 3, 256, 256), sigma_s=0.1, device=dev)
+        if a.operator == "inpainting":
+            masks = np.stack([random_mask(seed_of(step) + b) for b in range(B)])
+            op = get_operator("inpainting", mask=torch.from_numpy(masks)[:, None].repeat(1, 3, 1, 1), **kw)
+            y = (x_clean + 0.1 * ynoise) * masks[:, None]
+        else:
+            sf = 4 if a.operator == "super_resolution" else 1
+            op = get_operator(a.operator, kernel=assets[OPERATORS[a.operator]], scale_factor=sf, **kw)
+            xa = op.A(torch.from_numpy(x_clean).float().to(dev)).double().cpu().numpy()
+            y = xa + 0.1 * ynoise[..., :256 // sf, :256 // sf]
+        return op, y.astype(np.float32), noise.astype(np.float32)
+
+    def make_mechanism(op, timer=None):
+        return choose_conditioning_mechanism("free_hunch")(
+            1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(float(t_steps[0]) ** 2, dtype=torch.float64),
+            data_dim=3 * 256 * 256, max_vector_count=100000, dct_variance=var, image_base_covariance="dct_diagonal",
+            denoiser_mean_error_threshold=0.2, use_analytical_score_time_update=True, project_to_diagonal=False,
+            space_step_update_threshold=10.0, space_step_update_lower_threshold=1.0, max_rtol=1.0, do_space_updates=True,
+            use_analytic_var_at_end=False, solver_type="customcuda", use_rtol_func=True, device=dev, batch=B, timer=timer)
+
+    problems = [make_problem(s) for s in range(n_iter)]
+    ctx = problems[0][0].ctx
+    net = AnalyticDCTGaussianDenoiser(var, ctx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 256 MiB > 126 MB L2
+
+    def sample(op, y_dev, noise_dev, timer=None):
+        mech = make_mechanism(op, timer)
+        x = conditional_sampler(mech, net, y_dev, noise_dev, t_steps, solver=a.solver)
+        return x, mech
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    it = 0
+    for _ in range(a.warmup):
+        op, y, noise = problems[it]; it += 1
+        sample(op, torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev))
+    # ---- device-resident arm: inputs already in HBM, CUDA events per step, L2 flushed between steps
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    E.launch_count(reset=True)
+    ms_steps, cg_iters, ranks_k = [], [], []
+    for _ in range(a.steps):
+        op, y, noise = problems[it]; it += 1
+        y_dev, noise_dev = torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x, mech = sample(op, y_dev, noise_dev)
+        e1.record()
+        e1.synchronize()
+        ms_steps.append(e0.elapsed_time(e1))
+        cg_iters.append(sum(max(r["niter"]) for r in mech.log))
+        ranks_k.append(mech.covariance_model.vector_count)
+        assert bool(torch.isfinite(x).all()), "non-finite sample"
+    barrier()
+    launches = E.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = reduce_max(float(sum(ms_steps)))
+    value = world * B * a.steps / (total_ms * 1e-3)
+    # ---- end-to-end arm: pinned host buffers in, host image out, wall clock of the user-facing call
+    e2e_ms = []
+    for _ in range(a.steps):
+        op, y, noise = problems[it]; it += 1
+        y_pin, n_pin = torch.from_numpy(y).pin_memory(), torch.from_numpy(noise).pin_memory()
+        out_pin = torch.empty((B, 3, 256, 256), dtype=torch.float64).pin_memory()
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        x, _ = sample(op, y_pin.to(dev, non_blocking=True), n_pin.to(dev, non_blocking=True))
+        out_pin.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_total = reduce_max(float(sum(e2e_ms)))
+    e2e_value = world * B * a.steps / (e2e_total * 1e-3)
+    h2d = int(problems[0][1].nbytes + problems[0][2].nbytes)
+    d2h = int(B * 3 * 256 * 256 * 8)
+    # ---- one profiled step: phase timers + per-kernel CUDA-event timing inside the library
+    op, y, noise = problems[it]; it += 1
+    timer = PhaseTimer(True)
+    E.profile_kernels(True)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    x, mech = sample(op, torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev), timer)
+    p1.record(); p1.synchronize()
+    E.profile_kernels(False)
+    prof_ms = p0.elapsed_time(p1)
+    kprof = E.kernel_profile()
+    phases = timer.totals()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_calls = len(mech.log)
+    n_cg = sum(max(r["niter"]) for r in mech.log)
+    hot_ms = sum(phases.get(p, (0, 0.0))[1] for p in ("time_update", "space_update", "mat_solver"))
+    kern_total = sum(ms for _, ms in kprof.values())
+    top = max(kprof.items(), key=lambda kv: kv[1][1])
+    top_name, (top_n, top_ms) = top
+    # algorithmic bytes of the dominant kernel: Z rows grow during the run, so weight by the live rank per call
+    k_mean = float(np.mean([2 * r["k"] for r in mech.log for _ in range(max(1, max(r["niter"])))]))
+    ab = algorithmic_bytes(top_name, k_mean, B)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (ab / (top_ms / top_n * 1e-3) / 1e9) if ab else None
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "launches": top_n, "avg_us": top_ms / top_n * 1e3, "share_of_kernel_time": top_ms / kern_total,
+                "algorithmic_bytes_per_launch": ab, "mean_Z_rows": k_mean}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (f64 reductions and k x k algebra)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (PyTorch + library DCT)",
+                   "l2": "256 MiB flush between steps; every step samples new images", "mechanism_calls": n_calls,
+                   "cg_iterations_per_image": float(np.mean(cg_iters)), "final_bfgs_pairs": ranks_k[-1]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_total / a.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "hot_path": {"ms_per_image_step": prof_ms / B, "cov_plus_cg_ms_per_mechanism_call": hot_ms / n_calls,
+                     "cov_plus_cg_us_per_cg_iteration": hot_ms / max(1, n_cg) * 1e3, "cg_iterations": n_cg,
+                     "phases_ms": {k: round(v[1], 3) for k, v in phases.items()},
+                     "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(kprof.items(), key=lambda kv: -kv[1][1])}},
+    }
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        calls, complete, secs = cpu_reference_sample(assets, a, a.cpu_seconds, cores)
+        v = (len(calls) / total_calls(a)) / secs
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"oracle/fh_oracle.py (float64 CG, complex128 state), first {len(calls)} of "
+                                         f"{total_calls(a)} mechanism calls of one image in {secs:.1f} s, scaled by call count"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    assets = np.load(os.path.join(ROOT, "tests", "golden", "assets.npz"))
+    if a.impl == "reference":
+        run_reference_arm(a, assets)
+    else:
+        run_b200(a, assets)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,237 @@
+"""`conditioning_mechanism=free_hunch`: host-side mirror of the Free Hunch pieces of
+conditioning_utils/conditioning_mechanisms.py (reference :16-50, :190-294, :307-323, :562-600).
+
+Same registry function, constructor kwargs and call contract as the reference's `online_covariance`
+(BFGSOnlineUpdate); the covariance model, the Sigma.v products, the measurement operators and the CG guidance
+solve all run in the sm_100a library.  The denoiser (`model`) and its VJP stay in PyTorch.
+"""
+import math
+from warnings import warn
+
+import torch
+
+from . import engine
+from .covariance import CovarianceHessianBFGS, CovarianceHessianBFGSDCT
+
+
+class PhaseTimer:
+    """CUDA-event timers around the phases the reference times with time.time() prints
+    (conditioning_mechanisms.py:242-271): no host sync inside the loop, elapsed times are read at the end."""
+
+    def __init__(self, enabled=False):
+        self.enabled = enabled
+        self.pairs = []
+
+    def __call__(self, name):
+        return _Phase(self, name)
+
+    def totals(self):
+        """{phase: (calls, total_ms)}; synchronises."""
+        out = {}
+        if self.pairs:
+            torch.cuda.synchronize()
+        for name, a, b in self.pairs:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+
+class _Phase:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        if self.timer.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.timer.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.timer.pairs.append((self.name, self.a, b))
+        return False
+
+
+def choose_conditioning_mechanism(name):
+    """conditioning_mechanisms.py:16-36 with the new `free_hunch` entry (F1 of SURVEY.md: the reference calls the
+    same mechanism `online_covariance`).  The other entries are baselines, not Free Hunch, and are not provided."""
+    if name in ("free_hunch", "online_covariance"):
+        return FreeHunch
+    if name in ("dps", "pigdm", "pigdm_videodiff_schedule", "peng_convert", "peng_analytic", "tmpd", "diffpir"):
+        raise ValueError(f"conditioning mechanism '{name}' is a baseline of the reference and outside free_hunch_b200")
+    if name == "ddnm":
+        raise ValueError("DDNM conditioning mechanism not implemented in this branch of the codebase")
+    raise ValueError(f"Unknown conditioning mechanism: {name}")
+
+
+class ConditioningMechanism:
+    """conditioning_mechanisms.py:38-50."""
+
+    def __init__(self, cond_scaling, forward_operator, clip_x0_mean, init_denoiser_variance=None,
+                 init_noise_variance=None, data_dim=None, pigdm_posthoc_scaling=False, **argv):
+        self.cond_scaling = cond_scaling
+        self.forward_operator = forward_operator
+        self.clip_x0_mean = clip_x0_mean
+
+    def __call__(self, x_t, x_0_mean, y, sigma):
+        x_0_mean_new = self.x0_mean_update(x_t, x_0_mean, y, sigma)
+        if self.clip_x0_mean:
+            x_0_mean_new = x_0_mean_new.clip(-1, 1)
+        return x_0_mean_new
+
+
+def rtol_func(sigma, rtol_max=1e0, rtol_min=1e-14):
+    """conditioning_mechanisms.py:307-323, including the clamp expression of :313 as written."""
+    sigma_min, sigma_max = 0.1, 80.0
+    sigma = max(min(sigma, sigma_max), max(sigma_min, sigma))
+    p = 0.1
+    log_factor = ((math.log10(sigma) - math.log10(sigma_min)) / (math.log10(sigma_max) - math.log10(sigma_min))) ** p
+    log_rtol = log_factor * (math.log10(rtol_max) - math.log10(rtol_min)) + math.log10(rtol_min)
+    return 10 ** log_rtol
+
+
+def choose_solver(operator_name, operator, y, x0_mean, theta0_var=None, covariance_model=None, method="customcuda",
+                  max_rtol=1, ortho_tf=None, sigma_t=None, use_rtol_func=False, maxiter=5000, return_info=False,
+                  fixed_iters=0):
+    """conditioning_mechanisms.py:562-600 for method='customcuda' (the reference default, config.yaml:121): returns
+    mat = A^T (A Sigma A^T + sigma_y^2 I)^-1 (y - A x0_mean) from the CG solve with x0 = b and
+    rtol = rtol_func(sigma_t, max_rtol).  The scipy paths of the reference are CPU baselines and are not provided."""
+    if operator_name not in ("gaussian_blur", "super_resolution", "motion_blur", "inpainting"):
+        raise ValueError("Invalid operator name. Please choose 'gaussian_blur', 'super_resolution', 'motion_blur', or 'inpainting'.")
+    if method != "customcuda":
+        raise ValueError(f"solver_type '{method}' is a CPU path of the reference; free_hunch_b200 provides 'customcuda' only")
+    # sigma_s is a 1-element float32 tensor; clip and square in float32 like the reference (:387,:491,:642)
+    sig = operator.sigma_s.detach().to(torch.float32).cpu().clip(min=0.001)
+    if operator_name == "super_resolution":
+        sig = sig.clip(min=1e-2)
+    sy2 = float((sig ** 2).item())
+    mat, info = engine.cg_solve(covariance_model.state, operator.op, y, x0_mean, sy2, rtol_func(sigma_t, max_rtol),
+                                maxiter=maxiter, fixed_iters=fixed_iters)
+    if any(n >= maxiter for n in info["niter"]):
+        warn("CG not converge.")
+    mat = mat.to(x0_mean.dtype)
+    return (mat, info) if return_info else mat
+
+
+class FreeHunch(ConditioningMechanism):
+    """The Free Hunch mechanism = the reference's BFGSOnlineUpdate (conditioning_mechanisms.py:190-294).
+    One instance per sampled image batch; stateful (history of sigma, x, denoiser mean kept ON DEVICE)."""
+
+    def __init__(self, cond_scaling, forward_operator, clip_x0_mean, init_denoiser_variance, init_noise_variance, data_dim,
+                 pigdm_posthoc_scaling=False, **argv):
+        super().__init__(cond_scaling, forward_operator, clip_x0_mean)
+        argv.setdefault("solver_type", "customcuda")
+        argv.setdefault("max_rtol", 1.0)
+        argv.setdefault("use_rtol_func", True)
+        argv.setdefault("project_to_diagonal", False)
+        argv.setdefault("image_base_covariance", "dct_diagonal")
+        argv.setdefault("max_vector_count", None)
+        argv.setdefault("do_space_updates", True)
+        argv.setdefault("denoiser_mean_error_threshold", 0.2)
+        argv.setdefault("use_analytical_score_time_update", True)
+        argv.setdefault("space_step_update_threshold", 10.0)
+        argv.setdefault("space_step_update_lower_threshold", 1.0)
+        argv.setdefault("use_analytic_var_at_end", False)
+        if argv["use_analytic_var_at_end"]:
+            raise ValueError("use_analytic_var_at_end (scipy baseline branch, conditioning_mechanisms.py:273-278) is not provided")
+        self.argv = argv
+        self.batch = int(argv.get("batch", 1))
+        device = argv.get("device", getattr(forward_operator, "device", None))
+        nv = init_noise_variance.item() if torch.is_tensor(init_noise_variance) else float(init_noise_variance)
+        base = argv["image_base_covariance"]
+        mvc = argv["max_vector_count"]
+        if mvc is not None and mvc >= engine.MAX_RANK // 2:
+            mvc = None                        # the reference default (100000) never drops; capacity is MAX_RANK/2 pairs
+        if base == "identity":
+            shape = tuple(getattr(forward_operator, "in_shape", (1, 1, 1, data_dim))[-3:])
+            self.covariance_model = CovarianceHessianBFGS(init_denoiser_variance, nv, data_dim, max_vector_count=mvc,
+                                                          project_to_diagonal=argv["project_to_diagonal"], device=device,
+                                                          batch=self.batch, image_shape=shape)
+        elif base in ("dct_diagonal", "dct_diagonal_noinfo"):
+            self.covariance_model = CovarianceHessianBFGSDCT(argv.get("data_dir"), nv, data_dim, max_vector_count=mvc,
+                                                             dct_variance=argv.get("dct_variance"),
+                                                             use_precalculated_info=(base == "dct_diagonal"),
+                                                             project_to_diagonal=argv["project_to_diagonal"], device=device,
+                                                             batch=self.batch)
+        else:
+            raise ValueError(f"image_base_covariance '{base}' is not available (pca_dct_diagonal is undefined in the reference too)")
+        self.do_space_updates = argv["do_space_updates"]
+        self.init_denoiser_variance = init_denoiser_variance
+        self.init_noise_variance = init_noise_variance
+        self.data_dim = data_dim
+        self.sigmas, self.xs, self.denoiser_means = [], [], []
+        self.denoiser_mean_error_threshold = argv["denoiser_mean_error_threshold"]
+        self.use_analytical_score_time_update = argv["use_analytical_score_time_update"]
+        self.space_step_update_threshold = argv["space_step_update_threshold"]
+        self.space_step_update_lower_threshold = argv["space_step_update_lower_threshold"]
+        self.log = []
+        self.timer = argv.get("timer") or PhaseTimer(False)
+
+    def mat_solver(self, y, x0_mean, covariance_model=None, sigma_t=None, return_info=False):
+        return choose_solver(self.forward_operator.name, self.forward_operator, y, x0_mean, None,
+                             covariance_model or self.covariance_model, self.argv["solver_type"], self.argv["max_rtol"],
+                             None, sigma_t, use_rtol_func=self.argv["use_rtol_func"], return_info=return_info)
+
+    def update_time_step(self, x_t, sigma_t, sigma_tnext, score_t):
+        self.covariance_model.update_time_step(x_t, sigma_t, sigma_tnext, score_t)
+
+    def update_space_step(self, denoiser_mean_at_x, denoiser_mean_at_xnext, sigma_t, x, xnext):
+        self.covariance_model.update_space_step(denoiser_mean_at_x, denoiser_mean_at_xnext, sigma_t, x, xnext)
+
+    def x0_mean_update(self, x_t, model, y, sigma):
+        """conditioning_mechanisms.py:237-294."""
+        sigma_f = float(sigma.item()) if torch.is_tensor(sigma) else float(sigma)
+        x_t = x_t.requires_grad_()
+        with self.timer("denoiser"):
+            x_0_mean, _ = model(x_t, sigma)
+        cov = self.covariance_model
+        rec = {"sigma": sigma_f, "time_update": False, "space_update": False}
+        if self.do_space_updates:
+            prev_mean_at_sigma = None
+            if len(self.sigmas) != 0 and sigma_f != self.sigmas[-1]:                                     # :241-244
+                score_previous = (self.denoiser_means[-1] - self.xs[-1]) / self.sigmas[-1] ** 2
+                with self.timer("time_update"):
+                    prev_mean_at_sigma, _ = cov.update_time_step(self.xs[-1], self.sigmas[-1], sigma_f, score_previous)
+                rec["time_update"] = True
+            elif len(self.sigmas) != 0:                                                                  # :248-249
+                prev_mean_at_sigma = self.denoiser_means[-1]
+            if len(self.xs) != 0 and not torch.allclose(x_t.detach(), self.xs[-1]):                     # :250
+                if not self.use_analytical_score_time_update:                                            # :252-254
+                    with torch.no_grad():
+                        prev_mean_at_sigma, _ = model(self.xs[-1], sigma)
+                if self.space_step_update_lower_threshold < sigma_f < self.space_step_update_threshold:  # :256
+                    with self.timer("space_update"):
+                        cov.update_space_step(prev_mean_at_sigma, x_0_mean.detach(), sigma_f, self.xs[-1], x_t.detach())
+                    rec["space_update"] = True
+        elif len(self.sigmas) != 0 and sigma_f != self.sigmas[-1]:                                       # :261-263
+            score_previous = (self.denoiser_means[-1] - self.xs[-1]) / self.sigmas[-1] ** 2
+            with self.timer("time_update"):
+                cov.update_time_step(self.xs[-1], self.sigmas[-1], sigma_f, score_previous, only_covariance=True)
+            rec["time_update"] = True
+
+        with self.timer("mat_solver"):
+            mat, info = self.mat_solver(y, x_0_mean.detach(), sigma_t=sigma_f, return_info=True)        # :268
+        s2 = sigma_f ** 2
+        with self.timer("denoiser"):
+            p_y_xt_grad = torch.autograd.grad((mat.detach() * x_0_mean).sum(), x_t)[0]                   # :280
+        if (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold:                                # :283-285
+            p_y_xt_grad = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
+            rec["fallback"] = True
+        else:                                                                                            # :287-288
+            p_y_xt_grad = p_y_xt_grad * self.cond_scaling
+            rec["fallback"] = False
+        x_0_mean_new = x_0_mean + p_y_xt_grad * s2
+        # :290-292 -- history stays ON DEVICE; only the last entry is ever read, so only it is kept
+        self.sigmas.append(sigma_f)
+        self.xs = [x_t.detach()]
+        self.denoiser_means = [x_0_mean.detach()]
+        rec["niter"] = info["niter"]
+        rec["k"] = cov.vector_count
+        self.log.append(rec)
+        return x_0_mean_new
+
+
+# the reference's name for the same class
+BFGSOnlineUpdate = FreeHunch

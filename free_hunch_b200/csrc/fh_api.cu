@@ -4,6 +4,7 @@
 #include "fh_common.cuh"
 #include "fh_dct.cuh"
 #include "fh_kernels.cuh"
+#include "fh_cg.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -18,6 +19,63 @@
 
 long long fh_g_launches = 0;
 static thread_local std::string g_err;
+
+// ------------------------------------------------------------------------------------------- profiling
+#ifndef FH_EMU
+#include <map>
+int fh_g_prof_on = 0;
+namespace {
+struct ProfPair { const char* name; cudaEvent_t a, b; };
+std::vector<ProfPair> g_prof_pairs;
+std::vector<cudaEvent_t> g_prof_free;
+std::map<std::string, std::pair<long long, double>> g_prof_acc;   // name -> (launches, total ms)
+cudaEvent_t prof_event() {
+  if (!g_prof_free.empty()) { cudaEvent_t e = g_prof_free.back(); g_prof_free.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_drain() {
+  for (auto& p : g_prof_pairs) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    auto& acc = g_prof_acc[p.name];
+    acc.first += 1; acc.second += ms;
+    g_prof_free.push_back(p.a); g_prof_free.push_back(p.b);
+  }
+  g_prof_pairs.clear();
+}
+}  // namespace
+void fh_prof_begin(const char* name, cudaStream_t stream) {
+  ProfPair p{name, prof_event(), prof_event()};
+  cudaEventRecord(p.a, stream);
+  g_prof_pairs.push_back(p);
+}
+void fh_prof_end(cudaStream_t stream) {
+  cudaEventRecord(g_prof_pairs.back().b, stream);
+  if (g_prof_pairs.size() >= 16384) prof_drain();
+}
+extern "C" int fh_prof_enable(int on) {
+  if (on && !fh_g_prof_on) g_prof_acc.clear();
+  if (!on && fh_g_prof_on) prof_drain();
+  fh_g_prof_on = on ? 1 : 0;
+  return FH_OK;
+}
+// Writes "name count total_ms\n" lines; returns the number of bytes needed (call with buf = NULL to size).
+extern "C" int fh_prof_report(char* buf, int buflen) {
+  prof_drain();
+  std::string out;
+  char line[256];
+  for (auto& kv : g_prof_acc) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && buflen > 0) { strncpy(buf, out.c_str(), (size_t)buflen - 1); buf[buflen - 1] = 0; }
+  return (int)out.size() + 1;
+}
+#else
+extern "C" int fh_prof_enable(int) { return FH_OK; }
+extern "C" int fh_prof_report(char* buf, int buflen) { if (buf && buflen > 0) buf[0] = 0; return 1; }
+#endif
 
 #define FH_FAIL(code, ...)                         \
   do {                                             \
@@ -42,7 +100,8 @@ struct fh_ctx {
   long d;
   float2 *tw256, *post, *cw;          // DCT tables
   float* plane_tmp;                   // (max_batch, d) scratch for the 2-pass DCT
-  float* scratch[6];                  // (max_batch, d) general scratch vectors
+  float* scratch[7];                  // (max_batch, d) general scratch vectors
+  double* Gtmp;                       // (max_batch, FH_MAXM*FH_MAXM) core of a Hessian-side Sigma that differs from the state's
   double* dot_partial;                // (max_batch, nchunk, FH_MAXM+2)
   double* csum;                       // (max_batch, FH_MAXM+2)
   double* coef;                       // (max_batch, FH_MAXM)
@@ -53,13 +112,17 @@ struct fh_ctx {
   FhCgScalars* cg_sc_host;            // pinned
   int* status;                        // device error counter (singular small matrices)
   float* cgv[6];                      // CG vectors b,x,r,p,q,t  (max_batch, d)
+  double* strip_dots;                 // (max_batch, C*32, FH_MAXM) per-strip partial dots of the fused CG
+  unsigned* tickets;                  // (max_batch, 4) arrival counters of the fused CG (self re-arming)
+  int sms;                            // multiprocessors of the device (grid sizing)
 };
 
 struct fh_state {
   fh_ctx* ctx;
   int B, basis, m;
   long d;
-  double var2;                        // effective sigma^2 of the state
+  double var2;                        // sigma^2 of the Hessian side: drifts by the reference's float32-rounded shifts
+  double sig2;                        // sigma^2 of the Sigma side (exact: the reference's Sigma^-1 shifts are ~1e-7 accurate)
   float *pi, *delta, *Z;              // (B,d), (B,d), (B,FH_MAXM,d)
   double *Gz, *Gs;                    // (B,FH_MAXM,FH_MAXM)
 };
@@ -109,7 +172,8 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMemcpy(c->cw, cw.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
   const size_t vec = (size_t)max_batch * c->d * sizeof(float);
   FH_CUDA(cudaMalloc((void**)&c->plane_tmp, vec));
-  for (int i = 0; i < 6; ++i) FH_CUDA(cudaMalloc((void**)&c->scratch[i], vec));
+  for (int i = 0; i < 7; ++i) FH_CUDA(cudaMalloc((void**)&c->scratch[i], vec));
+  FH_CUDA(cudaMalloc((void**)&c->Gtmp, (size_t)max_batch * FH_MAXM * FH_MAXM * sizeof(double)));
   for (int i = 0; i < 6; ++i) FH_CUDA(cudaMalloc((void**)&c->cgv[i], vec));
   const int nch = fh_nchunks(c->d);
   FH_CUDA(cudaMalloc((void**)&c->dot_partial, (size_t)max_batch * nch * (FH_MAXM + 2) * sizeof(double)));
@@ -123,6 +187,13 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMallocHost((void**)&c->cg_sc_host, (size_t)max_batch * sizeof(FhCgScalars)));
   FH_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
   FH_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+  FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * 32 * FH_MAXM * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->tickets, (size_t)max_batch * 4 * sizeof(unsigned)));
+  FH_CUDA(cudaMemset(c->tickets, 0, (size_t)max_batch * 4 * sizeof(unsigned)));
+  c->sms = 148;
+#ifndef FH_EMU
+  { cudaDeviceProp pr; FH_CUDA(cudaGetDeviceProperties(&pr, device)); c->sms = pr.multiProcessorCount; }
+#endif
 #ifndef FH_EMU
   const int core_smem = (2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * (int)sizeof(double);
   FH_CUDA(cudaFuncSetAttribute(fh_k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, core_smem));
@@ -135,7 +206,9 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
 extern "C" int fh_ctx_destroy(fh_ctx* c) {
   if (!c) return FH_OK;
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
-  for (int i = 0; i < 6; ++i) { cudaFree(c->scratch[i]); cudaFree(c->cgv[i]); }
+  for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
+  for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
+  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->tickets);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
   cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFree(c->status);
   free(c);
@@ -143,24 +216,43 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
 }
 
 // --------------------------------------------------------------------------------------------- DCT
-static int dct2_planes(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, void* stream) {
+// named instantiations (FH_LAUNCH stringifies the kernel name for the profiler)
+static constexpr auto fh_k_pass_fwd = fh_k_pass<false, false>;
+static constexpr auto fh_k_pass_fwd_t = fh_k_pass<false, true>;
+static constexpr auto fh_k_pass_inv = fh_k_pass<true, false>;
+static constexpr auto fh_k_pass_inv_t = fh_k_pass<true, true>;
+
+// grid for a strip-loop kernel: enough CTAs to fill the machine, never more than there are strips
+static inline dim3 strip_grid(const fh_ctx* c, int nstrips) { return dim3((unsigned)std::min(nstrips, c->sms * 6)); }
+
+// second_transposed = 1: natural layout out (public fh_dct2); 0: the library's basis layout (see fh_dct.cuh)
+static int dct2_planes(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, int second_transposed, void* stream) {
   if (c->H != FH_N || c->W != FH_N) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 planes (got %dx%d)", c->H, c->W);
   if ((size_t)nplanes * FH_N * FH_N > (size_t)c->max_batch * c->d) FH_FAIL(FH_EINVAL, "too many planes for the scratch buffer");
   FhDctTables tab{c->tw256, c->post, c->cw};
-  dim3 grid(FH_N / FH_DCT_ROWS, nplanes), block(FH_DCT_THREADS);
+  const int nstrips = nplanes * 32;
+  dim3 grid = strip_grid(c, nstrips), block(FH_PASS_THREADS);
   if (inverse) {
-    FH_LAUNCH(fh_k_dct_rows_t<true>, grid, block, 0, stream, in, c->plane_tmp, tab);
-    FH_LAUNCH(fh_k_dct_rows_t<true>, grid, block, 0, stream, c->plane_tmp, out, tab);
+    FH_LAUNCH(fh_k_pass_inv_t, grid, block, 0, stream, in, c->plane_tmp, nstrips, tab);
+    if (second_transposed) FH_LAUNCH(fh_k_pass_inv_t, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
+    else FH_LAUNCH(fh_k_pass_inv, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
   } else {
-    FH_LAUNCH(fh_k_dct_rows_t<false>, grid, block, 0, stream, in, c->plane_tmp, tab);
-    FH_LAUNCH(fh_k_dct_rows_t<false>, grid, block, 0, stream, c->plane_tmp, out, tab);
+    FH_LAUNCH(fh_k_pass_fwd_t, grid, block, 0, stream, in, c->plane_tmp, nstrips, tab);
+    if (second_transposed) FH_LAUNCH(fh_k_pass_fwd_t, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
+    else FH_LAUNCH(fh_k_pass_fwd, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
   }
+  FH_KCHECK();
+  return FH_OK;
+}
+// natural <-> basis layout of DCT-domain vectors (import/export only)
+static int transpose_planes(fh_ctx* c, const float* in, float* out, int nplanes, void* stream) {
+  FH_LAUNCH(fh_k_transpose, dim3(8, 8, nplanes), dim3(32, 8), 0, stream, in, out);
   FH_KCHECK();
   return FH_OK;
 }
 extern "C" int fh_dct2(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, void* stream) {
   if (!c || !in || !out || nplanes < 1) FH_FAIL(FH_EINVAL, "bad fh_dct2 arguments");
-  return dct2_planes(c, in, out, nplanes, inverse, stream);
+  return dct2_planes(c, in, out, nplanes, inverse, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------- state
@@ -168,7 +260,7 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
   if (!c || !out || batch < 1 || batch > c->max_batch) FH_FAIL(FH_EINVAL, "bad fh_state_create arguments");
   if (basis == FH_BASIS_DCT && (c->H != FH_N || c->W != FH_N)) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 images");
   fh_state* s = (fh_state*)calloc(1, sizeof(fh_state));
-  s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0;
+  s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0; s->sig2 = 1.0;
   const size_t vec = (size_t)batch * s->d * sizeof(float);
   FH_CUDA(cudaMalloc((void**)&s->pi, vec));
   FH_CUDA(cudaMalloc((void**)&s->delta, vec));
@@ -185,7 +277,7 @@ extern "C" int fh_state_destroy(fh_state* s) {
   return FH_OK;
 }
 extern "C" int fh_state_rank(const fh_state* s) { return s ? s->m : -1; }
-extern "C" double fh_state_var2(const fh_state* s) { return s ? s->var2 : -1.0; }
+extern "C" double fh_state_var2(const fh_state* s) { return s ? s->sig2 : -1.0; }
 
 // Z is allocated with row capacity ctx->max_rank but indexed with stride FH_MAXM in the kernels: keep them equal.
 static int check_rank_layout(fh_state* s) {
@@ -194,7 +286,7 @@ static int check_rank_layout(fh_state* s) {
 }
 
 static int refresh_delta(fh_state* s, void* stream) {
-  FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->pi, s->delta, (float)(1.0 / s->var2), s->d, vec_ok(s->d));
+  FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->pi, s->delta, (float)(1.0 / s->sig2), s->d, vec_ok(s->d));
   FH_KCHECK();
   return FH_OK;
 }
@@ -210,27 +302,32 @@ static int gram(fh_state* s, int m, FhRowPtrs xr, int nx, const float* w, void* 
   return FH_OK;
 }
 
-// Recompute Gs for the current (pi, Z, Gz, var2).  If tu_s != null (score in the state's basis) also leaves the
-// time-update coefficient vector in ctx->coef.
-static int refresh_core(fh_state* s, const float* tu_s, double var2_old, void* stream) {
+// Core of Sigma at diagonal `delta` (= 1/(pi + 1/sigma^2)):  Gs_out = -Gz (I + Z delta Z^T Gz)^-1.  If tu_s != null
+// (score in the state's basis) also leaves the time-update coefficient vector in ctx->coef.
+static int core_at(fh_state* s, const float* delta, double* Gs_out, const float* tu_s, double var2_old, void* stream) {
   fh_ctx* c = s->ctx;
-  int rc = refresh_delta(s, stream);
-  if (rc) return rc;
   if (s->m == 0) return FH_OK;
   FhRowPtrs xr{};
   int nx = 0;
   if (tu_s) {
-    FH_LAUNCH(fh_k_tu_rows, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, tu_s, s->pi, s->delta, c->scratch[4], c->scratch[5], s->d, vec_ok(s->d));
+    FH_LAUNCH(fh_k_tu_rows, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, tu_s, s->pi, delta, c->scratch[4], c->scratch[5], s->d, vec_ok(s->d));
     FH_KCHECK();
     xr.p[0] = tu_s; xr.p[1] = c->scratch[4]; xr.p[2] = c->scratch[5];
     nx = 3;
   }
-  rc = gram(s, s->m, xr, nx, s->delta, stream);
+  int rc = gram(s, s->m, xr, nx, delta, stream);
   if (rc) return rc;
   const size_t smem = (size_t)(2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * sizeof(double);
-  FH_LAUNCH(fh_k_core, dim3(s->B), dim3(256), smem, stream, c->gramK, s->Gz, s->m, s->Gs, tu_s ? 1 : 0, var2_old, c->coef, c->status);
+  FH_LAUNCH(fh_k_core, dim3(s->B), dim3(256), smem, stream, c->gramK, s->Gz, s->m, Gs_out, tu_s ? 1 : 0, var2_old, c->coef, c->status);
   FH_KCHECK();
   return FH_OK;
+}
+
+// Sigma side of the state at s->sig2: delta and Gs.
+static int refresh_core(fh_state* s, void* stream) {
+  int rc = refresh_delta(s, stream);
+  if (rc) return rc;
+  return core_at(s, s->delta, s->Gs, nullptr, 0.0, stream);
 }
 
 extern "C" int fh_state_init(fh_state* s, const float* var_dev, double init_noise_variance, void* stream) {
@@ -239,6 +336,11 @@ extern "C" int fh_state_init(fh_state* s, const float* var_dev, double init_nois
   if (rc) return rc;
   s->m = 0;
   s->var2 = init_noise_variance;
+  s->sig2 = init_noise_variance;
+  if (s->basis == FH_BASIS_DCT) {              // init_variance is given in the natural (c, ki, kj) order
+    if ((rc = transpose_planes(s->ctx, var_dev, s->ctx->scratch[0], s->ctx->C, stream))) return rc;
+    var_dev = s->ctx->scratch[0];
+  }
   FH_LAUNCH(fh_k_init_pi, dim3((unsigned)((s->d + 255) / 256), s->B), dim3(256), 0, stream, var_dev, s->pi, 1.0 / init_noise_variance, s->d);
   FH_KCHECK();
   FH_CUDA(cudaMemsetAsync(s->Gz, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
@@ -248,12 +350,12 @@ extern "C" int fh_state_init(fh_state* s, const float* var_dev, double init_nois
 
 // to / from the state's basis
 static int to_basis(fh_state* s, const float* in, float* out, void* stream) {
-  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 0, stream);
+  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 0, 0, stream);
   FH_CUDA(cudaMemcpyAsync(out, in, (size_t)s->B * s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return FH_OK;
 }
 static int from_basis(fh_state* s, const float* in, float* out, void* stream) {
-  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 1, stream);
+  if (s->basis == FH_BASIS_DCT) return dct2_planes(s->ctx, in, out, s->B * s->ctx->C, 1, 0, stream);
   FH_CUDA(cudaMemcpyAsync(out, in, (size_t)s->B * s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return FH_OK;
 }
@@ -274,15 +376,41 @@ static int cov_dot_basis(fh_state* s, const float* v, float* out, void* stream) 
   return FH_OK;
 }
 
+static FhCgFused fused_params(fh_state* s, fh_op* o) {
+  fh_ctx* c = s->ctx;
+  FhCgFused P{};
+  P.B = s->B; P.C = c->C; P.m = s->m;
+  P.fuse = 0;
+  P.strips_per_image = c->C * 32;
+  if (o && o->kind == FH_OP_INPAINT) { P.fuse = 1; P.mask = o->mask; P.mask_batch = o->mask_batch; }
+  if (o && o->kind == FH_OP_BLUR && o->separable && o->nr <= FH_MAX_SEP_TAPS && o->nc <= FH_MAX_SEP_TAPS) {
+    P.fuse = 2; P.kr = o->kr; P.kc = o->kc; P.nr = o->nr; P.nc = o->nc; P.cr = o->cr; P.cc = o->cc;
+  }
+  P.Z = s->Z; P.delta = s->delta; P.Gs = s->Gs;
+  P.x = c->cgv[1]; P.r = c->cgv[2]; P.p = c->cgv[3]; P.q = c->cgv[4];
+  P.T = c->plane_tmp; P.W = c->scratch[2];
+  P.dots_partial = c->strip_dots; P.coef = c->coef; P.part_a = c->part_a; P.part_b = c->part_b;
+  P.tickets = c->tickets; P.sc = nullptr; P.sy2 = 0.f;
+  P.tab = FhDctTables{c->tw256, c->post, c->cw};
+  return P;
+}
+
+// out = Sigma in, both in pixel space, DCT basis: four fused launches (no operator folded in)
+static int sigma_apply_pixels(fh_state* s, const float* in, float* out, void* stream) {
+  FhCgFused P = fused_params(s, nullptr);
+  const dim3 grid = strip_grid(s->ctx, P.B * P.strips_per_image), block(FH_PASS_THREADS);
+  FH_LAUNCH(fh_k_cg_fwd_rows, grid, block, 0, stream, P, in, (const float*)nullptr, 0, 0);
+  FH_LAUNCH(fh_k_cg_fwd_cols, grid, block, 0, stream, P);
+  FH_LAUNCH(fh_k_cg_inv_cols, grid, block, 0, stream, P);
+  FH_LAUNCH(fh_k_cg_inv_rows, grid, block, 0, stream, P, out, (const float*)nullptr, 0);
+  FH_KCHECK();
+  return FH_OK;
+}
+
 extern "C" int fh_cov_dot(fh_state* s, const float* v, float* out, void* stream) {
   if (!s || !v || !out) FH_FAIL(FH_EINVAL, "bad fh_cov_dot arguments");
-  fh_ctx* c = s->ctx;
   if (s->basis == FH_BASIS_IDENTITY) return cov_dot_basis(s, v, out, stream);
-  int rc = to_basis(s, v, c->scratch[0], stream);
-  if (rc) return rc;
-  rc = cov_dot_basis(s, c->scratch[0], c->scratch[0], stream);
-  if (rc) return rc;
-  return from_basis(s, c->scratch[0], out, stream);
+  return sigma_apply_pixels(s, v, out, stream);
 }
 
 extern "C" int fh_time_update(fh_state* s, const float* x, const float* score, double sigma_t, double sigma_tnext,
@@ -290,20 +418,38 @@ extern "C" int fh_time_update(fh_state* s, const float* x, const float* score, d
   if (!s || !(sigma_t > 0) || !(sigma_tnext > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update arguments");
   if (!only_cov && (!x || !score || !mean_out || !score_out)) FH_FAIL(FH_EINVAL, "fh_time_update needs x, score and outputs");
   fh_ctx* c = s->ctx;
+  const int vec = vec_ok(s->d);
+  int rc;
+  // Sigma side (online_update_bfgs.py:166): diag(Sigma^-1) += sigma'^-2 - sigma^-2.  The float32 rounding of that
+  // shift is ~1e-7 relative at every step, so the state simply sits at the exact new sigma.
+  s->sig2 = sigma_tnext * sigma_tnext;
+  if (only_cov) return refresh_core(s, stream);
+  // Hessian side (:172): diag(H^-1) -= float32(sigma'^2 - sigma^2), an ABSOLUTE rounding error that accumulates
+  // until a space update rebuilds H from Sigma (:294).  var2 carries that drift; it only enters the score transfer.
   const double var2_old = s->var2;
-  // the reference shifts the inverse-Hessian diagonal by a float32-rounded amount (online_update_bfgs.py:172)
   s->var2 = var2_old + (double)(float)(sigma_tnext * sigma_tnext - sigma_t * sigma_t);
   if (!(s->var2 > 0)) FH_FAIL(FH_ESTATE, "non-positive effective variance after time update");
-  if (only_cov) return refresh_core(s, nullptr, var2_old, stream);
-  int rc;
   float* xh = c->scratch[0];
   float* sh = c->scratch[1];
   if ((rc = to_basis(s, x, xh, stream))) return rc;
   if ((rc = to_basis(s, score, sh, stream))) return rc;
-  if ((rc = refresh_core(s, sh, var2_old, stream))) return rc;
-  FH_LAUNCH(fh_k_tu_apply, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, c->coef, sh, s->pi, s->delta, xh,
-            (float)var2_old, (float)(1.0 / s->var2), (float)(sigma_tnext * sigma_tnext), c->scratch[2], c->scratch[3], s->d, vec_ok(s->d));
+  const bool consistent = fabs(s->var2 - s->sig2) <= 1e-7 * s->sig2;
+  const float* dl = s->delta;
+  if (consistent) {
+    // one core serves both sides
+    if ((rc = refresh_delta(s, stream))) return rc;
+    if ((rc = core_at(s, s->delta, s->Gs, sh, var2_old, stream))) return rc;
+  } else {
+    float* dH = c->scratch[6];
+    FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->pi, dH, (float)(1.0 / s->var2), s->d, vec);
+    FH_KCHECK();
+    if ((rc = core_at(s, dH, c->Gtmp, sh, var2_old, stream))) return rc;
+    dl = dH;
+  }
+  FH_LAUNCH(fh_k_tu_apply, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, s->m, c->coef, sh, s->pi, dl, xh,
+            (float)var2_old, (float)(1.0 / s->var2), (float)(sigma_tnext * sigma_tnext), c->scratch[2], c->scratch[3], s->d, vec);
   FH_KCHECK();
+  if (!consistent && (rc = refresh_core(s, stream))) return rc;
   if ((rc = from_basis(s, c->scratch[2], score_out, stream))) return rc;
   return from_basis(s, c->scratch[3], mean_out, stream);
 }
@@ -316,11 +462,9 @@ extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float*
   fh_ctx* c = s->ctx;
   const int vec = vec_ok(s->d);
   int rc;
-  // H is rebuilt from Sigma at the true sigma (online_update_bfgs.py:294): drop the float32 drift of var2
-  if (s->var2 != sigma_t * sigma_t) {
-    s->var2 = sigma_t * sigma_t;
-    if ((rc = refresh_delta(s, stream))) return rc;
-  }
+  // H is rebuilt from Sigma at the true sigma (online_update_bfgs.py:294): the float32 drift of var2 is dropped.
+  // Sigma itself stays where the last time update left it (s->sig2).
+  s->var2 = sigma_t * sigma_t;
   float* dxp = c->scratch[0];
   float* dep = c->scratch[1];
   FH_LAUNCH(fh_k_su_diffs, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, x, xnext, mean_at_x, mean_at_xnext,
@@ -341,7 +485,7 @@ extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float*
   FH_LAUNCH(fh_k_bfgs_block, dim3((s->B + 63) / 64), dim3(64), 0, stream, s->Gz, s->m, c->csum, c->part_b, fh_nchunks(s->d), s->B);
   FH_KCHECK();
   s->m += 2;
-  return refresh_core(s, nullptr, s->var2, stream);
+  return refresh_core(s, stream);
 }
 
 extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, const float* V, int kv, double sigma, void* stream) {
@@ -355,7 +499,9 @@ extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, con
   for (int b = 0; b < s->B; ++b)
     for (int i = 0; i < m; ++i) {
       const float* src = (i < ku) ? U + (size_t)i * s->d : V + (size_t)(i - ku) * s->d;
-      FH_CUDA(cudaMemcpyAsync(s->Z + ((size_t)b * FH_MAXM + i) * s->d, src, (size_t)s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      float* dst = s->Z + ((size_t)b * FH_MAXM + i) * s->d;
+      if (s->basis == FH_BASIS_DCT) { if ((rc = transpose_planes(c, src, dst, c->C, stream))) return rc; }
+      else FH_CUDA(cudaMemcpyAsync(dst, src, (size_t)s->d * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
   // w = 1/delta = P  -> scratch[0];  Kp = W diag(P) W^T
   FH_LAUNCH(fh_k_delta, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->delta, c->scratch[0], 0.0f, s->d, vec);   // 1/(delta+0)
@@ -375,7 +521,8 @@ extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, con
     }
   // the diagonal of Sigma^-1 is P = 1/delta exactly as before: pi unchanged.  sigma fixes the H relation.
   (void)sigma;         // Sigma's diagonal is defined at the current var2; `sigma` only fixes the H relation
-  return refresh_core(s, nullptr, s->var2, stream);
+  s->var2 = s->sig2;
+  return refresh_core(s, stream);
 }
 
 extern "C" int fh_state_drop_all(fh_state* s, double sigma, void* stream) {
@@ -390,13 +537,20 @@ extern "C" int fh_state_drop_all(fh_state* s, double sigma, void* stream) {
 
 extern "C" int fh_state_export(fh_state* s, float* pi, float* Z, double* Gz, double* Gs, float* delta, void* stream) {
   if (!s) FH_FAIL(FH_EINVAL, "null state");
+  fh_ctx* c = s->ctx;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t vec = (size_t)s->B * s->d * sizeof(float);
-  if (pi) FH_CUDA(cudaMemcpyAsync(pi, s->pi, vec, cudaMemcpyDeviceToDevice, st));
-  if (delta) FH_CUDA(cudaMemcpyAsync(delta, s->delta, vec, cudaMemcpyDeviceToDevice, st));
+  int rc;
+  // DCT basis: the internal layout is (c, kj, ki); exported vectors are in the natural (c, ki, kj) order
+  auto put = [&](float* dst, const float* src, int nimg) -> int {
+    if (s->basis == FH_BASIS_DCT) return transpose_planes(c, src, dst, nimg * c->C, stream);
+    FH_CUDA(cudaMemcpyAsync(dst, src, (size_t)nimg * s->d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FH_OK;
+  };
+  if (pi && (rc = put(pi, s->pi, s->B))) return rc;
+  if (delta && (rc = put(delta, s->delta, s->B))) return rc;
   if (Z)
     for (int b = 0; b < s->B; ++b)
-      if (s->m) FH_CUDA(cudaMemcpyAsync(Z + (size_t)b * s->m * s->d, s->Z + (size_t)b * FH_MAXM * s->d, (size_t)s->m * s->d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (s->m && (rc = put(Z + (size_t)b * s->m * s->d, s->Z + (size_t)b * FH_MAXM * s->d, s->m))) return rc;
   for (int which = 0; which < 2; ++which) {
     double* dst = which ? Gs : Gz;
     const double* src = which ? s->Gs : s->Gz;
@@ -546,11 +700,96 @@ static int apply_ASAt(fh_state* s, fh_op* o, const float* p, float* t, void* str
   return fh_op_apply(o, img, t, s->B, 0, stream);
 }
 
+// DCT-basis solve: the iteration of fh_cg.cuh.  5 launches per iteration when the operator folds into the DCT passes
+// (mask, separable blur), 9 otherwise (p update, A^T, 4 passes, A, q, x/r update).
+static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
+                          int maxiter, int fixed_iters, float* mat_out, int* niter_host, int* optimal_host,
+                          double* resid_host, void* stream) {
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n = (long)c->C * (c->H / o->sf) * (c->W / o->sf);
+  if (n % FH_STRIP_ELEMS) FH_FAIL(FH_EINVAL, "measurement size %ld is not a multiple of %d", n, FH_STRIP_ELEMS);
+  const int B = s->B;
+  const int ystrips = (int)(n / FH_STRIP_ELEMS);
+  const long hw = (long)(c->H / o->sf) * (c->W / o->sf);
+  FhCgFused P = fused_params(s, o);
+  P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
+  const bool fusedop = P.fuse != 0;
+  const dim3 block(FH_PASS_THREADS);
+  const dim3 gimg = strip_grid(c, B * P.strips_per_image), gy = strip_grid(c, B * ystrips);
+  float *bv = c->cgv[0], *x = c->cgv[1], *t = c->cgv[5];
+  float *img = c->scratch[0], *img2 = c->scratch[1];
+  int rc;
+  // rhs and x0 = b
+  const float* amu = mu;
+  if (o->kind != FH_OP_INPAINT) {
+    if ((rc = fh_op_apply(o, mu, t, B, 0, stream))) return rc;
+    amu = t;
+  }
+  FH_LAUNCH(fh_k_cg_rhs, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, amu, P.mask, P.mask_batch, hw, bv, x, n);
+  FH_KCHECK();
+  FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
+  // one application of the system operator on `vec` (x for the initial residual, p afterwards) -> q (+ alpha)
+  auto apply = [&](const float* vec, int update_p, int first, int it) -> int {
+    if (fusedop) {
+      FH_LAUNCH(fh_k_cg_fwd_rows, gimg, block, 0, stream, P, (const float*)nullptr, vec, update_p, first);
+      FH_LAUNCH(fh_k_cg_fwd_cols, gimg, block, 0, stream, P);
+      FH_LAUNCH(fh_k_cg_inv_cols, gimg, block, 0, stream, P);
+      FH_LAUNCH(fh_k_cg_inv_rows, gimg, block, 0, stream, P, (float*)nullptr, vec, it);
+    } else {
+      if (update_p) FH_LAUNCH(fh_k_cg_p, gy, block, 0, stream, P, ystrips, first);
+      const float* pv = vec ? vec : P.p;
+      int rc2;
+      if ((rc2 = fh_op_apply(o, pv, img, B, 1, stream))) return rc2;
+      FH_LAUNCH(fh_k_cg_fwd_rows, gimg, block, 0, stream, P, (const float*)img, (const float*)nullptr, 0, 0);
+      FH_LAUNCH(fh_k_cg_fwd_cols, gimg, block, 0, stream, P);
+      FH_LAUNCH(fh_k_cg_inv_cols, gimg, block, 0, stream, P);
+      FH_LAUNCH(fh_k_cg_inv_rows, gimg, block, 0, stream, P, img2, (const float*)nullptr, 0);
+      if ((rc2 = fh_op_apply(o, img2, t, B, 0, stream))) return rc2;
+      FH_LAUNCH(fh_k_cg_q2, gy, block, 0, stream, P, (const float*)t, vec, ystrips, it);
+    }
+    FH_KCHECK();
+    return FH_OK;
+  };
+  if ((rc = apply(x, 0, 0, 0))) return rc;                         // q = A_op x0
+  const int use_stop = fixed_iters > 0 ? 0 : 1;
+  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
+  FH_LAUNCH(fh_k_cg_r0, gy, block, 0, stream, P, (const float*)bv, ystrips, rtol, 0.0, use_stop);   // r0 = b - q, scalars
+  FH_KCHECK();
+  int poll = 4, since = 0;
+  for (int it = 1; it <= last; ++it) {
+    if ((rc = apply(nullptr, 1, it == 1 ? 1 : 0, it))) return rc;  // p update, q = A_op p, alpha
+    FH_LAUNCH(fh_k_cg_xr, gy, block, 0, stream, P, ystrips, it, last);
+    FH_KCHECK();
+    if (++since >= poll || it == last) {
+      since = 0;
+      FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+      FH_CUDA(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < B; ++b) all = all && c->cg_sc_host[b].done;
+      if (all) break;
+      if (poll < 32) poll *= 2;
+    }
+  }
+  for (int b = 0; b < B; ++b) {
+    if (niter_host) niter_host[b] = c->cg_sc_host[b].niter;
+    if (optimal_host) optimal_host[b] = c->cg_sc_host[b].optimal;
+    if (resid_host) resid_host[b] = sqrt(c->cg_sc_host[b].resid2);
+  }
+  if (o->kind == FH_OP_INPAINT) {
+    FH_CUDA(cudaMemcpyAsync(mat_out, x, (size_t)B * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return FH_OK;
+  }
+  return fh_op_apply(o, x, mat_out, B, 1, stream);
+}
+
 extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
                            int maxiter, int fixed_iters, float* mat_out, int* niter_host, int* optimal_host,
                            double* resid_host, void* stream) {
   if (!s || !o || !y || !mu || !mat_out || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve arguments");
   if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  if (s->basis == FH_BASIS_DCT)
+    return cg_solve_fused(s, o, y, mu, sigma_y2, rtol, maxiter, fixed_iters, mat_out, niter_host, optimal_host, resid_host, stream);
   fh_ctx* c = s->ctx;
   cudaStream_t st = (cudaStream_t)stream;
   const long n = op_ylen(o);

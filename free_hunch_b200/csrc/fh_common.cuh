@@ -17,9 +17,16 @@
 #define FH_DYN_SMEM(type, name)                         \
   extern __shared__ __align__(16) unsigned char fh_dyn_smem_raw[]; \
   type* name = reinterpret_cast<type*>(fh_dyn_smem_raw)
+// Per-kernel device timing for bench.py (fh_prof_enable): one cudaEvent pair around every launch, on the
+// launching stream.  Off by default; when off the cost is one predictable branch.
+extern int fh_g_prof_on;
+void fh_prof_begin(const char* name, cudaStream_t stream);
+void fh_prof_end(cudaStream_t stream);
 #define FH_LAUNCH(kern, grid, block, smem, stream, ...)                    \
   do {                                                                     \
+    if (fh_g_prof_on) fh_prof_begin(#kern, (cudaStream_t)(stream));        \
     kern<<<grid, block, smem, (cudaStream_t)(stream)>>>(__VA_ARGS__);      \
+    if (fh_g_prof_on) fh_prof_end((cudaStream_t)(stream));                 \
     ++fh_g_launches;                                                       \
   } while (0)
 #endif
@@ -28,6 +35,19 @@ extern long long fh_g_launches;
 
 #define FH_MAXM 64          // max rows of Z (2 per space update): 32 BFGS pairs
 #define FH_N 256            // DCT size (H = W = 256 in the DCT basis)
+
+// Per-image scalars of a CG solve (device resident; the host only polls `done`).
+struct FhCgScalars {
+  double rr[2];        // r.r, ping-pong by iteration parity
+  double bnorm2;       // |b|^2
+  double stop2;        // (rtol*|b|)^2, or -1 when the residual test is disabled
+  double resid2;       // last |r|^2
+  double alpha, beta;  // step lengths of the current iteration
+  int done;            // 1 once the loop has broken for this image
+  int optimal;         // 1 if broken by the residual test
+  int niter;           // k of cg.py:244 at the break (or iterations run so far)
+  int pad;
+};
 
 __device__ __forceinline__ double fh_warp_sum(double v) {
 #pragma unroll

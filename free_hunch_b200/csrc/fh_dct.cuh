@@ -1,11 +1,18 @@
-// Orthonormal 256-point DCT-II / DCT-III along rows, two rows packed into one 256-point complex FFT
-// (Makhoul reordering), FFT done as a 16 x 16 four-step transform with 16 threads per FFT and a
-// 16-point FFT held in registers.  A CTA transforms R = 8 rows and stores the result TRANSPOSED, so
-// running the same kernel twice yields the 2-D transform in the original orientation.
+// Orthonormal 256-point DCT-II / DCT-III along rows of 256x256 planes.
+//
+// Core: two real rows are packed into one 256-point complex FFT (Makhoul reordering); the FFT is a 16 x 16
+// four-step transform done by 16 threads, each holding a 16-point FFT in registers.  A CTA of 256 threads
+// owns a strip of 8 consecutive rows (2048 contiguous floats) staged in shared memory: all 256 threads move
+// data (coalesced float4) and do the fused element-wise / convolution / dot-product work of the CG kernels in
+// fh_cg.cuh, threads 0..63 (4 groups of 16) run the FFTs.
+//
+// A 2-D transform is two row passes: the first stores its result TRANSPOSED, the second stores it as is.  The
+// covariance state therefore lives in the "basis layout"  W[c][kj][ki]  (DCT coefficient (ki,kj) of channel c),
+// which no one outside the library sees: fh_dct2 (public) transposes twice and returns the natural layout.
 //
 // Replaces torch_dct.dct_2d / idct_2d(norm='ortho') (reference call sites
-// conditioning_utils/online_update_bfgs.py:352-374; torch-dct 0.1.6 computes the same transform through
-// an FFT of the even/odd reordered sequence).
+// conditioning_utils/online_update_bfgs.py:352-374; torch-dct 0.1.6 computes the same transform through an FFT
+// of the even/odd reordered sequence).
 #pragma once
 #include "fh_common.cuh"
 
@@ -13,6 +20,19 @@ struct FhDctTables {
   const float2* tw256;   // exp(-2 pi i j / 256), j = 0..255
   const float2* post;    // f_k * exp(-i pi k / 512): forward post-twiddle incl. orthonormal scale
   const float2* cw;      // exp(+i pi k / 512): inverse pre-twiddle
+};
+
+#define FH_STRIP 8            // rows per CTA strip
+#define FH_RS 264             // shared-memory row stride in floats (16-B aligned rows, conflict-free FFT stores)
+#define FH_PASS_THREADS 256
+#define FH_STRIP_ELEMS (FH_STRIP * FH_N)
+
+struct FhStripSmem {
+  float a[FH_STRIP * FH_RS];
+  float b[FH_STRIP * FH_RS];
+  float2 grp[FH_STRIP / 2][16 * 17];
+  float2 tw[FH_N];
+  float2 tab[FH_N];
 };
 
 __device__ __forceinline__ float2 fh_cmul(float2 a, float2 b) {
@@ -69,42 +89,26 @@ __device__ __forceinline__ void fh_fft16(float2 (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
 
-#define FH_DCT_ROWS 8        // rows per CTA
-#define FH_DCT_THREADS 64    // 4 FFT groups of 16 threads, 2 rows each
-#define FH_OUTT_STRIDE 10    // floats per transposed row in smem (8 used): conflict-free float2 stores
-
-// in:  planes [nplanes][256][256] (row-major).  out: same shape, each plane TRANSPOSED after the row transform.
-// grid = (256 / FH_DCT_ROWS, nplanes), block = FH_DCT_THREADS.
+// Load the twiddle tables of one direction into the strip's shared memory (all threads; caller syncs).
 template <bool INV>
-__global__ void __launch_bounds__(FH_DCT_THREADS)
-fh_k_dct_rows_t(const float* __restrict__ in, float* __restrict__ out, FhDctTables tab) {
-  __shared__ __align__(16) float rows[FH_DCT_ROWS][FH_N];
-  __shared__ __align__(16) float2 scratch[4][16 * 17];
-  __shared__ __align__(16) float2 zb[4][FH_N];
-  __shared__ __align__(16) float outT[FH_N * FH_OUTT_STRIDE];
-  __shared__ __align__(16) float2 s_tw[FH_N];
-  __shared__ __align__(16) float2 s_tab[FH_N];
+__device__ __forceinline__ void fh_strip_tables(FhStripSmem& sm, const FhDctTables& tab) {
+  for (int i = threadIdx.x; i < FH_N; i += blockDim.x) {
+    const float2 w = tab.tw256[i];
+    sm.tw[i] = INV ? make_float2(w.x, -w.y) : w;
+    sm.tab[i] = INV ? tab.cw[i] : tab.post[i];
+  }
+}
 
+// Transform the 8 rows in `in` (shared, stride FH_RS) into `out` (shared, stride FH_RS; must not alias `in`).
+// Call with threadIdx.x < 64 only, from whole warps (it synchronises with __syncwarp).
+template <bool INV>
+__device__ __forceinline__ void fh_dct8_core(const float* __restrict__ in, float* __restrict__ out, FhStripSmem& sm) {
   const int tid = threadIdx.x;
   const int g = tid >> 4, t = tid & 15;
-  const int row0 = blockIdx.x * FH_DCT_ROWS;
-  const size_t plane = (size_t)blockIdx.y * FH_N * FH_N;
-
-  // tables + input rows (coalesced float4)
-  for (int i = tid; i < FH_N; i += FH_DCT_THREADS) {
-    float2 w = tab.tw256[i];
-    s_tw[i] = INV ? make_float2(w.x, -w.y) : w;
-    s_tab[i] = INV ? tab.cw[i] : tab.post[i];
-  }
-  {
-    const float4* src = reinterpret_cast<const float4*>(in + plane + (size_t)row0 * FH_N);
-    float4* dst = reinterpret_cast<float4*>(&rows[0][0]);
-    for (int i = tid; i < FH_DCT_ROWS * FH_N / 4; i += FH_DCT_THREADS) dst[i] = src[i];
-  }
-  __syncthreads();
-
-  const float* ra = rows[2 * g];
-  const float* rb = rows[2 * g + 1];
+  const float* ra = in + (2 * g) * FH_RS;
+  const float* rb = ra + FH_RS;
+  float* oa = out + (2 * g) * FH_RS;
+  float* ob = oa + FH_RS;
   float2 v[16];
   if (!INV) {
     // z[n] = va[n] + i vb[n],  v[n] = a[2n] (n<128) | a[511-2n] (n>=128);  this thread: n = t + 16*n2
@@ -125,25 +129,23 @@ fh_k_dct_rows_t(const float* __restrict__ in, float* __restrict__ out, FhDctTabl
       const float sn = (k == 0) ? 0.f : sc1;
       const float A = ra[k] * sk + rb[kn] * sn;
       const float B = rb[k] * sk - ra[kn] * sn;
-      v[n2] = fh_cmul(s_tab[k], make_float2(A, B));
+      v[n2] = fh_cmul(sm.tab[k], make_float2(A, B));
     }
   }
   // ---- four-step FFT: n = n1 + 16 n2 (n1 = t), k = 16 k1 + k2
   constexpr int SIGN = INV ? +1 : -1;
   fh_fft16<SIGN>(v);                                   // over n2 -> Y[n1=t][k2]
-  float2* S = scratch[g];
+  float2* S = sm.grp[g];
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) {
-    float2 y = fh_cmul(v[k2], s_tw[(t * k2) & (FH_N - 1)]);
-    S[t * 17 + k2] = y;
-  }
+  for (int k2 = 0; k2 < 16; ++k2) S[t * 17 + k2] = fh_cmul(v[k2], sm.tw[(t * k2) & (FH_N - 1)]);
   __syncwarp();
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) v[n1] = S[n1 * 17 + t];   // this thread: k2 = t
   fh_fft16<SIGN>(v);                                   // over n1 -> X[16 k1 + t]
 
   if (!INV) {
-    float2* Z = zb[g];
+    __syncwarp();                                      // every read of S done before it is reused as Z
+    float2* Z = S;
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) Z[16 * k1 + t] = v[k1];
     __syncwarp();
@@ -154,26 +156,123 @@ fh_k_dct_rows_t(const float* __restrict__ in, float* __restrict__ out, FhDctTabl
       const float2 zn = Z[(FH_N - k) & (FH_N - 1)];
       const float2 va = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       const float2 vb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-      const float2 p = s_tab[k];
-      const float xa = p.x * va.x - p.y * va.y;
-      const float xb = p.x * vb.x - p.y * vb.y;
-      *reinterpret_cast<float2*>(&outT[k * FH_OUTT_STRIDE + 2 * g]) = make_float2(xa, xb);
+      const float2 p = sm.tab[k];
+      oa[k] = p.x * va.x - p.y * va.y;
+      ob[k] = p.x * vb.x - p.y * vb.y;
     }
+    __syncwarp();                                      // Z (= S) is free again for the next strip
   } else {
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
       const int n = 16 * k1 + t;
       const int pos = (n < 128) ? 2 * n : 511 - 2 * n;
-      *reinterpret_cast<float2*>(&outT[pos * FH_OUTT_STRIDE + 2 * g]) = v[k1];
+      oa[pos] = v[k1].x;
+      ob[pos] = v[k1].y;
     }
+    __syncwarp();
+  }
+}
+
+// ---- strip movers (all 256 threads) -------------------------------------------------------------
+// thread owns float4 #tid and #tid+256 of the strip's 2048 contiguous floats: element offset e = 4*(tid+256h)
+__device__ __forceinline__ void fh_strip_load(float* sm_rows, const float* __restrict__ src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = threadIdx.x + FH_PASS_THREADS * h;
+    const float4 v = s4[f];
+    *reinterpret_cast<float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63)) = v;
+  }
+}
+__device__ __forceinline__ void fh_strip_get(const float* sm_rows, float (&r)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = threadIdx.x + FH_PASS_THREADS * h;
+    const float4 v = *reinterpret_cast<const float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63));
+    r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void fh_strip_put(float* sm_rows, const float (&r)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = threadIdx.x + FH_PASS_THREADS * h;
+    *reinterpret_cast<float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63)) = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+  }
+}
+__device__ __forceinline__ void fh_g_get(const float* __restrict__ src, float (&r)[8]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 v = s4[threadIdx.x + FH_PASS_THREADS * h];
+    r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void fh_g_put(float* __restrict__ dst, const float (&r)[8]) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) d4[threadIdx.x + FH_PASS_THREADS * h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+}
+__device__ __forceinline__ void fh_strip_store(const float* sm_rows, float* __restrict__ dst) {
+  float r[8];
+  fh_strip_get(sm_rows, r);
+  fh_g_put(dst, r);
+}
+// transposed store of the strip: dst_plane[k][row0 + r] = rows[r][k]  (thread k writes 32 contiguous bytes)
+__device__ __forceinline__ void fh_strip_store_t(const float* sm_rows, float* __restrict__ dst_plane, int row0) {
+  const int k = threadIdx.x;
+  float4* d = reinterpret_cast<float4*>(dst_plane + (size_t)k * FH_N + row0);
+  d[0] = make_float4(sm_rows[k], sm_rows[FH_RS + k], sm_rows[2 * FH_RS + k], sm_rows[3 * FH_RS + k]);
+  d[1] = make_float4(sm_rows[4 * FH_RS + k], sm_rows[5 * FH_RS + k], sm_rows[6 * FH_RS + k], sm_rows[7 * FH_RS + k]);
+}
+
+// In-place circular convolution along the rows of the strip with taps k[0..n) centred at c:
+//   transpose = 0:  out[j] = sum_a k[a] in[(j - (a - c)) mod 256]       transpose = 1:  in[(j + (a - c)) mod 256]
+// (all 256 threads; contains two __syncthreads)
+__device__ __forceinline__ void fh_strip_conv(float* sm_rows, const float* __restrict__ taps, int n, int c, int transpose) {
+  const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* rr = sm_rows + row * FH_RS;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int a = 0; a < n; ++a) {
+    const float w = taps[a];
+    const int off = transpose ? (a - c) : -(a - c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, rr[(lane + 32 * j + off) & (FH_N - 1)], acc[j]);
   }
   __syncthreads();
-  // transposed store: out[plane][j][row0 .. row0+8)
-  for (int j = tid; j < FH_N; j += FH_DCT_THREADS) {
-    const float2* s = reinterpret_cast<const float2*>(&outT[j * FH_OUTT_STRIDE]);
-    float2 a = s[0], b = s[1], c = s[2], d = s[3];
-    float4* dst = reinterpret_cast<float4*>(out + plane + (size_t)j * FH_N + row0);
-    dst[0] = make_float4(a.x, a.y, b.x, b.y);
-    dst[1] = make_float4(c.x, c.y, d.x, d.y);
+  float* wr = sm_rows + row * FH_RS;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wr[lane + 32 * j] = acc[j];
+  __syncthreads();
+}
+
+// Plain row pass: out = (TR ? transpose : identity)( DCT/IDCT along rows of in ).  grid.x strides over the
+// nplanes*32 strips.
+template <bool INV, bool TR>
+__global__ void __launch_bounds__(FH_PASS_THREADS)
+fh_k_pass(const float* __restrict__ in, float* __restrict__ out, int nstrips, FhDctTables tab) {
+  __shared__ __align__(16) FhStripSmem sm;
+  fh_strip_tables<INV>(sm, tab);
+  for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+    const size_t base = (size_t)s * FH_STRIP_ELEMS;
+    __syncthreads();
+    fh_strip_load(sm.a, in + base);
+    __syncthreads();
+    if (threadIdx.x < 64) fh_dct8_core<INV>(sm.a, sm.b, sm);
+    __syncthreads();
+    if (TR) fh_strip_store_t(sm.b, out + (size_t)(s >> 5) * FH_N * FH_N, (s & 31) * FH_STRIP);
+    else fh_strip_store(sm.b, out + base);
   }
+}
+
+// Plane transpose (import/export of basis-layout vectors, not on the hot path). grid = (8, 8, nplanes), block (32, 8).
+__global__ void fh_k_transpose(const float* __restrict__ in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const size_t plane = (size_t)blockIdx.z * FH_N * FH_N;
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) tile[j][threadIdx.x] = in[plane + (size_t)(y0 + j) * FH_N + x];
+  __syncthreads();
+  const int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) out[plane + (size_t)(oy0 + j) * FH_N + ox] = tile[threadIdx.x][j];
 }

@@ -688,16 +688,6 @@ fh_k_sr_transpose(const float* __restrict__ in, float* __restrict__ out, FhTaps 
 
 // ------------------------------------------------------------------------------------------------
 // CG vector kernels (y-space vectors of length n per image).  Per-image scalars live in FhCgScalars.
-struct FhCgScalars {
-  double rr[2];        // r.r, ping-pong by iteration parity
-  double bnorm2;       // |b|^2
-  double stop2;        // (rtol*|b|)^2, or -1 when the residual test is disabled
-  double resid2;       // last |r|^2
-  int done;            // 1 once the loop has broken for this image
-  int optimal;         // 1 if broken by the residual test
-  int niter;           // k of cg.py:244 at the break (or iterations run so far)
-  int pad;
-};
 
 // b = (mask? mask.*)(y - Amu) ;  x = b   (Amu = A mu, or mu itself for inpainting)
 __global__ void __launch_bounds__(FH_EW_THREADS)
@@ -777,6 +767,7 @@ __global__ void fh_k_cg_init_scalars(FhCgScalars* sc, const double* part_rr, con
   const double stop = fmax(rtol * sqrt(bb), atol);      // cg.py:237
   s.stop2 = use_stop ? stop * stop : -1.0;
   s.resid2 = rr;
+  s.alpha = 0.0; s.beta = 0.0;
   s.done = 0; s.optimal = 0; s.niter = 0; s.pad = 0;
   sc[b] = s;
 }

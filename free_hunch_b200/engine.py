@@ -217,3 +217,20 @@ def cg_solve(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
 
 def launch_count(reset=False):
     return int(_lib.lib().fh_launch_count(1 if reset else 0))
+
+
+def profile_kernels(enable):
+    """Bracket every kernel launch with CUDA events on its stream (bench.py's live per-kernel timing)."""
+    _lib.check(_lib.lib().fh_prof_enable(1 if enable else 0))
+
+
+def kernel_profile():
+    """{kernel_name: (launches, total_ms)} accumulated since profiling was enabled."""
+    n = _lib.lib().fh_prof_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    _lib.lib().fh_prof_report(buf, n + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

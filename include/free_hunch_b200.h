@@ -110,6 +110,10 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
                 double* resid_host, void* stream);
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 long long fh_launch_count(int reset);
+/* Per-kernel device timing for bench.py: while enabled every launch is bracketed by a cudaEvent pair on its
+ * stream.  fh_prof_report writes "kernel_name launches total_ms" lines into buf and returns the bytes needed. */
+int fh_prof_enable(int on);
+int fh_prof_report(char* buf, int buflen);
 
 #ifdef __cplusplus
 }

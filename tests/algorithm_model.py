@@ -22,17 +22,21 @@ class PrecisionFormModel:
         self.pi = (1.0 / v - 1.0 / sigma0 ** 2).astype(store)      # prior precision diagonal
         self.Z = np.zeros((0, self.d), store)
         self.Gz = np.zeros((0, 0))
-        self.var2 = float(sigma0) ** 2                               # effective sigma^2 of the state
+        self.var2 = float(sigma0) ** 2                               # sigma^2 of the Hessian side (float32 drift)
+        self.sig2 = float(sigma0) ** 2                               # sigma^2 of the Sigma side (exact)
         self._core()
 
     # --- per-sigma core: delta = diag of Sigma, Gs = core of Sigma's low-rank part
-    def _core(self):
-        tau = 1.0 / self.var2
-        self.delta = (1.0 / (self.pi.astype(np.float64) + tau)).astype(self.store)
+    def _core_at(self, var2):
+        delta = (1.0 / (self.pi.astype(np.float64) + 1.0 / var2)).astype(self.store)
         Z = self.Z.astype(np.float64)
-        self.K = (Z * self.delta.astype(np.float64)) @ Z.T
+        K = (Z * delta.astype(np.float64)) @ Z.T
         m = Z.shape[0]
-        self.Gs = -self.Gz @ np.linalg.inv(np.eye(m) + self.K @ self.Gz) if m else np.zeros((0, 0))
+        Gs = -self.Gz @ np.linalg.inv(np.eye(m) + K @ self.Gz) if m else np.zeros((0, 0))
+        return delta, K, Gs
+
+    def _core(self):
+        self.delta, self.K, self.Gs = self._core_at(self.sig2)
 
     def cov_dot(self, w):
         """Sigma w = delta*w + delta * Z^T Gs Z (delta*w)"""
@@ -44,7 +48,7 @@ class PrecisionFormModel:
     def inv_cov_dot(self, w):
         w = np.asarray(w, np.float64).reshape(-1)
         Z = self.Z.astype(np.float64)
-        return (self.pi.astype(np.float64) + 1.0 / self.var2) * w + Z.T @ (self.Gz @ (Z @ w))
+        return (self.pi.astype(np.float64) + 1.0 / self.sig2) * w + Z.T @ (self.Gz @ (Z @ w))
 
     def time_update(self, x, sigma, sigma_next, score, only_covariance=False):
         """s' = (I + var2' Lambda)^-1 (I + var2 Lambda) s ;  mu' = x + sigma_next^2 s'.
@@ -52,19 +56,21 @@ class PrecisionFormModel:
         inverse-Hessian diagonal (online_update_bfgs.py:172, `* torch.ones(d)`)."""
         x = np.asarray(x, np.float64).reshape(-1)
         s = np.asarray(score, np.float64).reshape(-1)
-        var2_old = self.var2
-        self.var2 = var2_old + float(np.float32(sigma_next ** 2 - sigma ** 2))
+        self.sig2 = float(sigma_next) ** 2               # Sigma side: exact (its float32 rounding is ~1e-7 relative)
         self._core()
         if only_covariance:
             return x.copy(), x.copy()
+        var2_old = self.var2
+        self.var2 = var2_old + float(np.float32(sigma_next ** 2 - sigma ** 2))
         Z = self.Z.astype(np.float64)
         pi = self.pi.astype(np.float64)
-        dl = self.delta.astype(np.float64)
+        dl, K, Gs = self._core_at(self.var2)             # Hessian side: Sigma evaluated at the drifted var2
+        dl = dl.astype(np.float64)
         # t = s + var2 * Lambda s ;  s' = Sigma' t / var2'
         c1 = self.Gz @ (Z @ s)
         # Z (delta' * t) = Z(delta' s) + var2 Z(delta' pi s) + var2 K' c1
-        zt = Z @ (dl * s) + var2_old * (Z @ (dl * pi * s)) + var2_old * (self.K @ c1)
-        c2 = self.Gs @ zt
+        zt = Z @ (dl * s) + var2_old * (Z @ (dl * pi * s)) + var2_old * (K @ c1)
+        c2 = Gs @ zt
         s_new = dl / self.var2 * (s * (1 + var2_old * pi) + Z.T @ (var2_old * c1 + c2))
         mu_new = x + sigma_next ** 2 * s_new
         return mu_new, s_new
@@ -96,13 +102,13 @@ class PrecisionFormModel:
         Kp = (W * P) @ W.T
         self.Z = (W * P).astype(self.store)
         self.Gz = -J @ np.linalg.inv(np.eye(ku + kv) + Kp @ J)
-        self.var2 = float(sigma) ** 2
+        self.var2 = self.sig2
         self._core()
 
     def dense(self, sigma):
         """(Sigma, Sigma^-1, H, H^-1) as dense matrices (test hook, small d)."""
         Z = self.Z.astype(np.float64)
-        inv_cov = np.diag(self.pi.astype(np.float64) + 1.0 / self.var2) + Z.T @ self.Gz @ Z
+        inv_cov = np.diag(self.pi.astype(np.float64) + 1.0 / self.sig2) + Z.T @ self.Gz @ Z
         cov = np.linalg.inv(inv_cov)
         eye = np.eye(self.d)
         hes = (cov / sigma ** 2 - eye) / sigma ** 2
