@@ -113,8 +113,8 @@ struct fh_ctx {
   int* status;                        // device error counter (singular small matrices)
   float* cgv[6];                      // CG vectors b,x,r,p,q,t  (max_batch, d)
   double* strip_dots;                 // (max_batch, C*32, FH_MAXM) per-strip partial dots of the fused CG
-  unsigned* tickets;                  // (max_batch, 4) arrival counters of the fused CG (self re-arming)
   int sms;                            // multiprocessors of the device (grid sizing)
+  long long* trace;                   // FH_TRACE=1: clock64 checkpoints of the fused CG kernels (8 kernels x 16 slots)
 };
 
 struct fh_state {
@@ -181,16 +181,17 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMalloc((void**)&c->coef, (size_t)max_batch * FH_MAXM * sizeof(double)));
   FH_CUDA(cudaMalloc((void**)&c->gram_partial, (size_t)max_batch * FH_GRAM_CTAS * FH_GRAM_LD * FH_GRAM_LD * sizeof(double)));
   FH_CUDA(cudaMalloc((void**)&c->gramK, (size_t)max_batch * FH_GRAM_LD * FH_GRAM_LD * sizeof(double)));
-  FH_CUDA(cudaMalloc((void**)&c->part_a, (size_t)max_batch * nch * sizeof(double)));
-  FH_CUDA(cudaMalloc((void**)&c->part_b, (size_t)max_batch * nch * sizeof(double)));
+  const size_t npart = std::max((size_t)nch, (size_t)channels * (FH_N / 2));
+  FH_CUDA(cudaMalloc((void**)&c->part_a, (size_t)max_batch * npart * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&c->part_b, (size_t)max_batch * npart * sizeof(double)));
   FH_CUDA(cudaMalloc((void**)&c->cg_sc, (size_t)max_batch * sizeof(FhCgScalars)));
   FH_CUDA(cudaMallocHost((void**)&c->cg_sc_host, (size_t)max_batch * sizeof(FhCgScalars)));
   FH_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
   FH_CUDA(cudaMemset(c->status, 0, sizeof(int)));
-  FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * 32 * FH_MAXM * sizeof(double)));
-  FH_CUDA(cudaMalloc((void**)&c->tickets, (size_t)max_batch * 4 * sizeof(unsigned)));
-  FH_CUDA(cudaMemset(c->tickets, 0, (size_t)max_batch * 4 * sizeof(unsigned)));
+  FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * (FH_N / 2) * FH_MAXM * sizeof(double)));
   c->sms = 148;
+  c->trace = nullptr;
+  if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
 #ifndef FH_EMU
   { cudaDeviceProp pr; FH_CUDA(cudaGetDeviceProperties(&pr, device)); c->sms = pr.multiProcessorCount; }
 #endif
@@ -198,8 +199,23 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   const int core_smem = (2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * (int)sizeof(double);
   FH_CUDA(cudaFuncSetAttribute(fh_k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, core_smem));
   FH_CUDA(cudaFuncSetAttribute(fh_k_core_from_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, core_smem));
+  // 5 rounds x 32 KB of Z in flight + ~42 KB static: the most one CTA can hold
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_fwd_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_fwd_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_fwd_cols<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
 #endif
   *out = c;
+  return FH_OK;
+}
+
+// Debug: copies the 8 x 16 clock64 checkpoints recorded by CTA 0 of the fused CG kernels (FH_TRACE=1) to the host.
+extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
+  if (!c || !c->trace || !out_host) FH_FAIL(FH_EINVAL, "tracing is off (set FH_TRACE=1 before fh_ctx_create)");
+  FH_CUDA(cudaDeviceSynchronize());
+  FH_CUDA(cudaMemcpy(out_host, c->trace, 8 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return FH_OK;
 }
 
@@ -208,7 +224,7 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
-  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->tickets);
+  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
   cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFree(c->status);
   free(c);
@@ -216,30 +232,53 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
 }
 
 // --------------------------------------------------------------------------------------------- DCT
-// named instantiations (FH_LAUNCH stringifies the kernel name for the profiler)
-static constexpr auto fh_k_pass_fwd = fh_k_pass<false, false>;
-static constexpr auto fh_k_pass_fwd_t = fh_k_pass<false, true>;
-static constexpr auto fh_k_pass_inv = fh_k_pass<true, false>;
-static constexpr auto fh_k_pass_inv_t = fh_k_pass<true, true>;
-
+// Strip height by problem size: short strips for small batches so that every SM gets work.
+static inline int pick_rows(const fh_ctx* c, int nplanes) {
+#ifdef FH_EMU
+  if (const char* e = getenv("FH_EMU_ROWS")) return atoi(e);      // CPU emulation: the test picks the instantiation
+#endif
+  // 8-row strips everywhere: the consumer-side reductions of the CG kernels read one partial per strip, and the
+  // shorter instantiations (more, smaller CTAs) measured slower on B200 even at batch 1 (profiles/).
+  (void)c; (void)nplanes;
+  return 8;
+}
+static inline int pick_zstages(const fh_ctx* c, int nstrips) {
+  if (const char* e = getenv("FH_ZSTAGES")) { int v = atoi(e); if (v >= 1 && v <= FH_ZMAX_STAGES) return v; }
+  return nstrips <= c->sms ? 5 : 2;         // one CTA per SM with a deep Z pipeline, or two CTAs per SM
+}
+#define FH_ROWS_SWITCH(R, ...)                                    \
+  switch (R) {                                                    \
+    case 8: { constexpr int RR = 8; __VA_ARGS__; } break;         \
+    case 4: { constexpr int RR = 4; __VA_ARGS__; } break;         \
+    default: { constexpr int RR = 2; __VA_ARGS__; } break;        \
+  }
 // grid for a strip-loop kernel: enough CTAs to fill the machine, never more than there are strips
 static inline dim3 strip_grid(const fh_ctx* c, int nstrips) { return dim3((unsigned)std::min(nstrips, c->sms * 6)); }
+
+template <bool INV, bool TR>
+static void launch_pass(fh_ctx* c, const float* in, float* out, int nplanes, void* stream) {
+  FhDctTables tab{c->tw256, c->post, c->cw};
+  const int R = pick_rows(c, nplanes);
+  const int nstrips = nplanes * (FH_N / R);
+  const dim3 grid = strip_grid(c, nstrips), block(FH_PASS_THREADS);
+  FH_ROWS_SWITCH(R, {
+    constexpr auto fh_k_pass_ = fh_k_pass<INV, TR, RR>;
+    FH_LAUNCH(fh_k_pass_, grid, block, 0, stream, in, out, nstrips, tab);
+  });
+}
 
 // second_transposed = 1: natural layout out (public fh_dct2); 0: the library's basis layout (see fh_dct.cuh)
 static int dct2_planes(fh_ctx* c, const float* in, float* out, int nplanes, int inverse, int second_transposed, void* stream) {
   if (c->H != FH_N || c->W != FH_N) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 planes (got %dx%d)", c->H, c->W);
   if ((size_t)nplanes * FH_N * FH_N > (size_t)c->max_batch * c->d) FH_FAIL(FH_EINVAL, "too many planes for the scratch buffer");
-  FhDctTables tab{c->tw256, c->post, c->cw};
-  const int nstrips = nplanes * 32;
-  dim3 grid = strip_grid(c, nstrips), block(FH_PASS_THREADS);
   if (inverse) {
-    FH_LAUNCH(fh_k_pass_inv_t, grid, block, 0, stream, in, c->plane_tmp, nstrips, tab);
-    if (second_transposed) FH_LAUNCH(fh_k_pass_inv_t, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
-    else FH_LAUNCH(fh_k_pass_inv, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
+    launch_pass<true, true>(c, in, c->plane_tmp, nplanes, stream);
+    if (second_transposed) launch_pass<true, true>(c, c->plane_tmp, out, nplanes, stream);
+    else launch_pass<true, false>(c, c->plane_tmp, out, nplanes, stream);
   } else {
-    FH_LAUNCH(fh_k_pass_fwd_t, grid, block, 0, stream, in, c->plane_tmp, nstrips, tab);
-    if (second_transposed) FH_LAUNCH(fh_k_pass_fwd_t, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
-    else FH_LAUNCH(fh_k_pass_fwd, grid, block, 0, stream, c->plane_tmp, out, nstrips, tab);
+    launch_pass<false, true>(c, in, c->plane_tmp, nplanes, stream);
+    if (second_transposed) launch_pass<false, true>(c, c->plane_tmp, out, nplanes, stream);
+    else launch_pass<false, false>(c, c->plane_tmp, out, nplanes, stream);
   }
   FH_KCHECK();
   return FH_OK;
@@ -376,12 +415,15 @@ static int cov_dot_basis(fh_state* s, const float* v, float* out, void* stream) 
   return FH_OK;
 }
 
-static FhCgFused fused_params(fh_state* s, fh_op* o) {
+static FhCgFused fused_params(fh_state* s, fh_op* o, int R) {
   fh_ctx* c = s->ctx;
   FhCgFused P{};
   P.B = s->B; P.C = c->C; P.m = s->m;
   P.fuse = 0;
-  P.strips_per_image = c->C * 32;
+  P.strips_per_image = c->C * (FH_N / R);
+  P.ystrips = P.strips_per_image;
+  P.zstages = pick_zstages(c, s->B * P.strips_per_image);
+  P.last_allowed = 1 << 30;
   if (o && o->kind == FH_OP_INPAINT) { P.fuse = 1; P.mask = o->mask; P.mask_batch = o->mask_batch; }
   if (o && o->kind == FH_OP_BLUR && o->separable && o->nr <= FH_MAX_SEP_TAPS && o->nc <= FH_MAX_SEP_TAPS) {
     P.fuse = 2; P.kr = o->kr; P.kc = o->kc; P.nr = o->nr; P.nc = o->nc; P.cr = o->cr; P.cc = o->cc;
@@ -389,20 +431,24 @@ static FhCgFused fused_params(fh_state* s, fh_op* o) {
   P.Z = s->Z; P.delta = s->delta; P.Gs = s->Gs;
   P.x = c->cgv[1]; P.r = c->cgv[2]; P.p = c->cgv[3]; P.q = c->cgv[4];
   P.T = c->plane_tmp; P.W = c->scratch[2];
-  P.dots_partial = c->strip_dots; P.coef = c->coef; P.part_a = c->part_a; P.part_b = c->part_b;
-  P.tickets = c->tickets; P.sc = nullptr; P.sy2 = 0.f;
+  P.dots_partial = c->strip_dots; P.part_a = c->part_a; P.part_b = c->part_b;
+  P.sc = nullptr; P.sy2 = 0.f; P.trace = c->trace;
   P.tab = FhDctTables{c->tw256, c->post, c->cw};
   return P;
 }
 
 // out = Sigma in, both in pixel space, DCT basis: four fused launches (no operator folded in)
 static int sigma_apply_pixels(fh_state* s, const float* in, float* out, void* stream) {
-  FhCgFused P = fused_params(s, nullptr);
+  const int R = pick_rows(s->ctx, s->B * s->ctx->C);
+  FhCgFused P = fused_params(s, nullptr, R);
   const dim3 grid = strip_grid(s->ctx, P.B * P.strips_per_image), block(FH_PASS_THREADS);
-  FH_LAUNCH(fh_k_cg_fwd_rows, grid, block, 0, stream, P, in, (const float*)nullptr, 0, 0);
-  FH_LAUNCH(fh_k_cg_fwd_cols, grid, block, 0, stream, P);
-  FH_LAUNCH(fh_k_cg_inv_cols, grid, block, 0, stream, P);
-  FH_LAUNCH(fh_k_cg_inv_rows, grid, block, 0, stream, P, out, (const float*)nullptr, 0);
+  const size_t zbytes = (size_t)P.zstages * FH_ZROUND_FLOATS * 4;
+  FH_ROWS_SWITCH(R, {
+    FH_LAUNCH(fh_k_cg_fwd_rows<RR>, grid, block, 0, stream, P, in, (const float*)nullptr, 0);
+    FH_LAUNCH(fh_k_cg_fwd_cols<RR>, grid, block, zbytes, stream, P);
+    FH_LAUNCH(fh_k_cg_inv_cols<RR>, grid, block, zbytes, stream, P);
+    FH_LAUNCH(fh_k_cg_inv_rows<RR>, grid, block, 0, stream, P, out, (const float*)nullptr, 0);
+  });
   FH_KCHECK();
   return FH_OK;
 }
@@ -708,15 +754,21 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   fh_ctx* c = s->ctx;
   cudaStream_t st = (cudaStream_t)stream;
   const long n = (long)c->C * (c->H / o->sf) * (c->W / o->sf);
-  if (n % FH_STRIP_ELEMS) FH_FAIL(FH_EINVAL, "measurement size %ld is not a multiple of %d", n, FH_STRIP_ELEMS);
   const int B = s->B;
-  const int ystrips = (int)(n / FH_STRIP_ELEMS);
+  const int R = pick_rows(c, B * c->C);
+  const int selems = R * FH_N;
+  if (n % selems) FH_FAIL(FH_EINVAL, "measurement size %ld is not a multiple of %d", n, selems);
+  const int ystrips = (int)(n / selems);
   const long hw = (long)(c->H / o->sf) * (c->W / o->sf);
-  FhCgFused P = fused_params(s, o);
-  P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
+  FhCgFused P = fused_params(s, o, R);
+  P.sc = c->cg_sc; P.sy2 = (float)sigma_y2; P.ystrips = ystrips;
+  const int use_stop = fixed_iters > 0 ? 0 : 1;
+  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
+  P.last_allowed = last;
   const bool fusedop = P.fuse != 0;
   const dim3 block(FH_PASS_THREADS);
   const dim3 gimg = strip_grid(c, B * P.strips_per_image), gy = strip_grid(c, B * ystrips);
+  const size_t zbytes = (size_t)P.zstages * FH_ZROUND_FLOATS * 4;
   float *bv = c->cgv[0], *x = c->cgv[1], *t = c->cgv[5];
   float *img = c->scratch[0], *img2 = c->scratch[1];
   int rc;
@@ -729,40 +781,44 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   FH_LAUNCH(fh_k_cg_rhs, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, amu, P.mask, P.mask_batch, hw, bv, x, n);
   FH_KCHECK();
   FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
-  // one application of the system operator on `vec` (x for the initial residual, p afterwards) -> q (+ alpha)
-  auto apply = [&](const float* vec, int update_p, int first, int it) -> int {
-    if (fusedop) {
-      FH_LAUNCH(fh_k_cg_fwd_rows, gimg, block, 0, stream, P, (const float*)nullptr, vec, update_p, first);
-      FH_LAUNCH(fh_k_cg_fwd_cols, gimg, block, 0, stream, P);
-      FH_LAUNCH(fh_k_cg_inv_cols, gimg, block, 0, stream, P);
-      FH_LAUNCH(fh_k_cg_inv_rows, gimg, block, 0, stream, P, (float*)nullptr, vec, it);
-    } else {
-      if (update_p) FH_LAUNCH(fh_k_cg_p, gy, block, 0, stream, P, ystrips, first);
-      const float* pv = vec ? vec : P.p;
-      int rc2;
-      if ((rc2 = fh_op_apply(o, pv, img, B, 1, stream))) return rc2;
-      FH_LAUNCH(fh_k_cg_fwd_rows, gimg, block, 0, stream, P, (const float*)img, (const float*)nullptr, 0, 0);
-      FH_LAUNCH(fh_k_cg_fwd_cols, gimg, block, 0, stream, P);
-      FH_LAUNCH(fh_k_cg_inv_cols, gimg, block, 0, stream, P);
-      FH_LAUNCH(fh_k_cg_inv_rows, gimg, block, 0, stream, P, img2, (const float*)nullptr, 0);
-      if ((rc2 = fh_op_apply(o, img2, t, B, 0, stream))) return rc2;
-      FH_LAUNCH(fh_k_cg_q2, gy, block, 0, stream, P, (const float*)t, vec, ystrips, it);
-    }
+  // one application of the system operator: it == 0 on x (initial residual), it >= 1 on p (updated first) -> q, p.q partials
+  auto apply = [&](int it) -> int {
+    int rc2 = FH_OK;
+    const float* vec = it == 0 ? x : nullptr;
+    FH_ROWS_SWITCH(R, {
+      if (fusedop) {
+        FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, vec, it);
+        FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, vec, it);
+      } else {
+        if (it >= 1) FH_LAUNCH(fh_k_cg_p<RR>, gy, block, 0, stream, P, it);
+        const float* pv = vec ? vec : P.p;
+        if ((rc2 = fh_op_apply(o, pv, img, B, 1, stream))) return rc2;
+        FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)img, (const float*)nullptr, 0);
+        FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, img2, (const float*)nullptr, 0);
+        if ((rc2 = fh_op_apply(o, img2, t, B, 0, stream))) return rc2;
+        FH_LAUNCH(fh_k_cg_q2<RR>, gy, block, 0, stream, P, (const float*)t, vec, it);
+      }
+    });
     FH_KCHECK();
-    return FH_OK;
+    return rc2;
   };
-  if ((rc = apply(x, 0, 0, 0))) return rc;                         // q = A_op x0
-  const int use_stop = fixed_iters > 0 ? 0 : 1;
-  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
-  FH_LAUNCH(fh_k_cg_r0, gy, block, 0, stream, P, (const float*)bv, ystrips, rtol, 0.0, use_stop);   // r0 = b - q, scalars
+  if ((rc = apply(0))) return rc;                                  // q = A_op x0
+  FH_ROWS_SWITCH(R, { FH_LAUNCH(fh_k_cg_r0<RR>, gy, block, 0, stream, P, (const float*)bv); });   // r0 = b - q
+  FH_LAUNCH(fh_k_cg_r0_scalars, dim3(B), block, 0, stream, P, rtol, 0.0, use_stop);
   FH_KCHECK();
   int poll = 4, since = 0;
   for (int it = 1; it <= last; ++it) {
-    if ((rc = apply(nullptr, 1, it == 1 ? 1 : 0, it))) return rc;  // p update, q = A_op p, alpha
-    FH_LAUNCH(fh_k_cg_xr, gy, block, 0, stream, P, ystrips, it, last);
+    if ((rc = apply(it))) return rc;                               // (stop test of it-1,) p update, q = A_op p
+    FH_ROWS_SWITCH(R, { FH_LAUNCH(fh_k_cg_xr<RR>, gy, block, 0, stream, P, it); });
     FH_KCHECK();
     if (++since >= poll || it == last) {
       since = 0;
+      FH_LAUNCH(fh_k_cg_finish, dim3(B), block, 0, stream, P, it + 1);   // records the stop test of iteration `it`
+      FH_KCHECK();
       FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
       FH_CUDA(cudaStreamSynchronize(st));
       bool all = true;

@@ -78,3 +78,39 @@ __device__ __forceinline__ double fh_sum_partials(const double* p, int n) {
   for (int i = 0; i < n; ++i) s += p[i];
   return s;
 }
+
+// ---- TMA (1-D bulk copy) + mbarrier helpers ---------------------------------------------------------
+// cp.async.bulk moves a contiguous, 16-byte aligned block global -> shared with one instruction issued by
+// one thread; completion is signalled on an mbarrier by transaction bytes.  Under FH_EMU the copy is a
+// memcpy by the issuing thread and the wait is a CTA barrier.
+#ifdef FH_EMU
+typedef unsigned long long fh_mbar_t;
+static inline void fh_mbar_init(fh_mbar_t*, unsigned) {}
+static inline void fh_mbar_fence_init() {}
+static inline void fh_mbar_expect_tx(fh_mbar_t*, unsigned) {}
+static inline void fh_tma_load_1d(void* dst, const void* src, unsigned bytes, fh_mbar_t*) { std::memcpy(dst, src, bytes); }
+static inline void fh_mbar_wait(fh_mbar_t*, unsigned) { __syncthreads(); }
+#else
+typedef unsigned long long fh_mbar_t;
+__device__ __forceinline__ unsigned fh_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fh_mbar_init(fh_mbar_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fh_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fh_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fh_mbar_expect_tx(fh_mbar_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fh_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fh_tma_load_1d(void* dst, const void* src, unsigned bytes, fh_mbar_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(fh_smem_u32(dst)), "l"(src), "r"(bytes), "r"(fh_smem_u32(bar)) : "memory");
+}
+// Bounded wait: a lost transaction traps the kernel (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void fh_mbar_wait(fh_mbar_t* bar, unsigned parity) {
+  unsigned ok = 0;
+  for (unsigned spins = 0; !ok; ++spins) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(fh_smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && spins > 4000000u) __trap();
+  }
+}
+#endif

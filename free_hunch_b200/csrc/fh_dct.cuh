@@ -1,10 +1,11 @@
 // Orthonormal 256-point DCT-II / DCT-III along rows of 256x256 planes.
 //
-// Core: two real rows are packed into one 256-point complex FFT (Makhoul reordering); the FFT is a 16 x 16
-// four-step transform done by 16 threads, each holding a 16-point FFT in registers.  A CTA of 256 threads
-// owns a strip of 8 consecutive rows (2048 contiguous floats) staged in shared memory: all 256 threads move
-// data (coalesced float4) and do the fused element-wise / convolution / dot-product work of the CG kernels in
-// fh_cg.cuh, threads 0..63 (4 groups of 16) run the FFTs.
+// Core: two real rows are packed into one 256-point complex FFT (Makhoul reordering).  The FFT is a radix-4
+// Stockham autosort transform: 64 threads per FFT, 4 stages, one 4-point butterfly per thread and stage, data
+// ping-ponging between two shared-memory buffers.  A CTA of 256 threads owns a strip of ROWS in {2,4,8}
+// consecutive rows (ROWS*256 contiguous floats): all threads move data with coalesced vector accesses and do the
+// fused element-wise / convolution / dot-product work of the CG kernels in fh_cg.cuh; ROWS/2 groups of 64 threads
+// run the FFTs.  Small batches use short strips so that every SM gets work (B=1: 384 strips of 2 rows).
 //
 // A 2-D transform is two row passes: the first stores its result TRANSPOSED, the second stores it as is.  The
 // covariance state therefore lives in the "basis layout"  W[c][kj][ki]  (DCT coefficient (ki,kj) of channel c),
@@ -22,15 +23,15 @@ struct FhDctTables {
   const float2* cw;      // exp(+i pi k / 512): inverse pre-twiddle
 };
 
-#define FH_STRIP 8            // rows per CTA strip
-#define FH_RS 264             // shared-memory row stride in floats (16-B aligned rows, conflict-free FFT stores)
+#define FH_RS 264             // shared-memory row stride in floats (16-B aligned rows)
 #define FH_PASS_THREADS 256
-#define FH_STRIP_ELEMS (FH_STRIP * FH_N)
 
+template <int ROWS>
 struct FhStripSmem {
-  float a[FH_STRIP * FH_RS];
-  float b[FH_STRIP * FH_RS];
-  float2 grp[FH_STRIP / 2][16 * 17];
+  float a[ROWS * FH_RS];
+  float b[ROWS * FH_RS];
+  float2 X[ROWS / 2][FH_N];
+  float2 Y[ROWS / 2][FH_N];
   float2 tw[FH_N];
   float2 tab[FH_N];
 };
@@ -57,212 +58,235 @@ __device__ __forceinline__ void fh_dft4(float2& a0, float2& a1, float2& a2, floa
   a3 = fh_csub(d02, d13);
 }
 
-// 16-point DFT in registers: in v[n], out v[k] (natural order), W = exp(SIGN*2 pi i/16).
-template <int SIGN>
-__device__ __forceinline__ void fh_fft16(float2 (&v)[16]) {
-  // step A: for each n1 (0..3): DFT4 over n2 of v[n1 + 4 n2]  -> y[n1][k2] kept at v[n1 + 4 k2]
-#pragma unroll
-  for (int n1 = 0; n1 < 4; ++n1) fh_dft4<SIGN>(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
-  // twiddles W16^(n1*k2)
-  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
-  // W16^j = (cos(2 pi j/16), SIGN*sin(2 pi j/16))
-  const float2 w1 = make_float2(c1, SIGN * s1), w2 = make_float2(r2, SIGN * r2), w3 = make_float2(s1, SIGN * c1);
-  const float2 w6 = make_float2(-r2, SIGN * r2), w9 = make_float2(-c1, -SIGN * s1);
-  v[1 + 4] = fh_cmul(v[1 + 4], w1);               // n1=1,k2=1
-  v[1 + 8] = fh_cmul(v[1 + 8], w2);               // n1=1,k2=2
-  v[1 + 12] = fh_cmul(v[1 + 12], w3);             // n1=1,k2=3
-  v[2 + 4] = fh_cmul(v[2 + 4], w2);               // n1=2,k2=1
-  v[2 + 8] = fh_rot90<SIGN>(v[2 + 8]);            // n1=2,k2=2 : W16^4 = exp(SIGN i pi/2)
-  v[2 + 12] = fh_cmul(v[2 + 12], w6);             // n1=2,k2=3
-  v[3 + 4] = fh_cmul(v[3 + 4], w3);               // n1=3,k2=1
-  v[3 + 8] = fh_cmul(v[3 + 8], w6);               // n1=3,k2=2
-  v[3 + 12] = fh_cmul(v[3 + 12], w9);             // n1=3,k2=3
-  // step B: for each k2: DFT4 over n1 of v[n1 + 4 k2] -> X[4 k1 + k2]
-  float2 o[16];
-#pragma unroll
-  for (int k2 = 0; k2 < 4; ++k2) {
-    float2 a0 = v[4 * k2], a1 = v[4 * k2 + 1], a2 = v[4 * k2 + 2], a3 = v[4 * k2 + 3];
-    fh_dft4<SIGN>(a0, a1, a2, a3);
-    o[k2] = a0; o[4 + k2] = a1; o[8 + k2] = a2; o[12 + k2] = a3;
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = o[i];
-}
-
 // Load the twiddle tables of one direction into the strip's shared memory (all threads; caller syncs).
-template <bool INV>
-__device__ __forceinline__ void fh_strip_tables(FhStripSmem& sm, const FhDctTables& tab) {
+template <bool INV, int ROWS>
+__device__ __forceinline__ void fh_strip_tables(FhStripSmem<ROWS>& sm, const FhDctTables& tab) {
   for (int i = threadIdx.x; i < FH_N; i += blockDim.x) {
     const float2 w = tab.tw256[i];
-    sm.tw[i] = INV ? make_float2(w.x, -w.y) : w;
+    sm.tw[i] = INV ? make_float2(w.x, -w.y) : w;      // exp(SIGN * 2 pi i j / 256)
     sm.tab[i] = INV ? tab.cw[i] : tab.post[i];
   }
 }
 
-// Transform the 8 rows in `in` (shared, stride FH_RS) into `out` (shared, stride FH_RS; must not alias `in`).
-// Call with threadIdx.x < 64 only, from whole warps (it synchronises with __syncwarp).
-template <bool INV>
-__device__ __forceinline__ void fh_dct8_core(const float* __restrict__ in, float* __restrict__ out, FhStripSmem& sm) {
-  const int tid = threadIdx.x;
-  const int g = tid >> 4, t = tid & 15;
-  const float* ra = in + (2 * g) * FH_RS;
-  const float* rb = ra + FH_RS;
-  float* oa = out + (2 * g) * FH_RS;
-  float* ob = oa + FH_RS;
-  float2 v[16];
-  if (!INV) {
-    // z[n] = va[n] + i vb[n],  v[n] = a[2n] (n<128) | a[511-2n] (n>=128);  this thread: n = t + 16*n2
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) {
-      const int n = t + 16 * n2;
-      const int src = (n < 128) ? 2 * n : 511 - 2 * n;
-      v[n2] = make_float2(ra[src], rb[src]);
-    }
-  } else {
-    // Z[k] = cw[k] * ((Ca[k] + Cb[N-k]) + i (Cb[k] - Ca[N-k])),  C[k] = X[k]*g_k/N, C[N] = 0
-    const float sc0 = 0.0625f, sc1 = 0.044194173824159216f;     // 1/sqrt(N), 1/sqrt(2N)
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) {
-      const int k = t + 16 * n2;
-      const float sk = (k == 0) ? sc0 : sc1;
-      const int kn = (FH_N - k) & (FH_N - 1);
-      const float sn = (k == 0) ? 0.f : sc1;
-      const float A = ra[k] * sk + rb[kn] * sn;
-      const float B = rb[k] * sk - ra[kn] * sn;
-      v[n2] = fh_cmul(sm.tab[k], make_float2(A, B));
-    }
+// One Stockham radix-4 stage of a 256-point FFT for thread j in [0, 64): sub-transform length Ns -> 4 Ns.
+template <int SIGN, int NS>
+__device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, float2* __restrict__ out, int j, const float2* __restrict__ tw) {
+  const int k = j & (NS - 1);
+  float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
+  if (NS > 1) {
+    const int t = k * (64 / NS);                       // angle = SIGN * 2 pi k r / (4 Ns)
+    v1 = fh_cmul(v1, tw[t]);
+    v2 = fh_cmul(v2, tw[2 * t]);
+    v3 = fh_cmul(v3, tw[3 * t]);
   }
-  // ---- four-step FFT: n = n1 + 16 n2 (n1 = t), k = 16 k1 + k2
-  constexpr int SIGN = INV ? +1 : -1;
-  fh_fft16<SIGN>(v);                                   // over n2 -> Y[n1=t][k2]
-  float2* S = sm.grp[g];
-#pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) S[t * 17 + k2] = fh_cmul(v[k2], sm.tw[(t * k2) & (FH_N - 1)]);
-  __syncwarp();
-#pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = S[n1 * 17 + t];   // this thread: k2 = t
-  fh_fft16<SIGN>(v);                                   // over n1 -> X[16 k1 + t]
+  fh_dft4<SIGN>(v0, v1, v2, v3);
+  const int j0 = ((j - k) << 2) + k;
+  out[j0] = v0; out[j0 + NS] = v1; out[j0 + 2 * NS] = v2; out[j0 + 3 * NS] = v3;
+}
 
-  if (!INV) {
-    __syncwarp();                                      // every read of S done before it is reused as Z
-    float2* Z = S;
+// Transform the ROWS rows in `in` (shared, stride FH_RS) into `out` (shared, stride FH_RS; must not alias `in`).
+// COLLECTIVE: every thread of the 256-thread CTA calls it (it contains __syncthreads); `in` must be complete
+// (caller synchronised) and `out` is complete only after the caller's next __syncthreads.
+template <bool INV, int ROWS>
+__device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float* __restrict__ out, FhStripSmem<ROWS>& sm) {
+  constexpr int SIGN = INV ? +1 : -1;
+  const int f = threadIdx.x >> 6, j = threadIdx.x & 63;
+  const bool act = f < ROWS / 2;
+  const int fc = act ? f : 0;
+  const float* ra = in + (2 * fc) * FH_RS;
+  const float* rb = ra + FH_RS;
+  float* oa = out + (2 * fc) * FH_RS;
+  float* ob = oa + FH_RS;
+  float2* X = sm.X[fc];
+  float2* Y = sm.Y[fc];
+  if (act) {
+    float2 v[4];
+    if (!INV) {
+      // z[n] = va[n] + i vb[n],  v[n] = a[2n] (n<128) | a[511-2n] (n>=128);  this thread: n = j + 64 r
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) Z[16 * k1 + t] = v[k1];
-    __syncwarp();
+      for (int r = 0; r < 4; ++r) {
+        const int n = j + 64 * r;
+        const int src = (n < 128) ? 2 * n : 511 - 2 * n;
+        v[r] = make_float2(ra[src], rb[src]);
+      }
+    } else {
+      // Z[k] = cw[k] * ((Ca[k] + Cb[N-k]) + i (Cb[k] - Ca[N-k])),  C[k] = X[k]*g_k/N, C[N] = 0
+      const float sc0 = 0.0625f, sc1 = 0.044194173824159216f;     // 1/sqrt(N), 1/sqrt(2N)
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      const int k = 16 * k1 + t;
-      const float2 zk = v[k1];
-      const float2 zn = Z[(FH_N - k) & (FH_N - 1)];
-      const float2 va = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 vb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-      const float2 p = sm.tab[k];
-      oa[k] = p.x * va.x - p.y * va.y;
-      ob[k] = p.x * vb.x - p.y * vb.y;
+      for (int r = 0; r < 4; ++r) {
+        const int k = j + 64 * r;
+        const float sk = (k == 0) ? sc0 : sc1;
+        const int kn = (FH_N - k) & (FH_N - 1);
+        const float sn = (k == 0) ? 0.f : sc1;
+        const float A = ra[k] * sk + rb[kn] * sn;
+        const float B = rb[k] * sk - ra[kn] * sn;
+        v[r] = fh_cmul(sm.tab[k], make_float2(A, B));
+      }
     }
-    __syncwarp();                                      // Z (= S) is free again for the next strip
-  } else {
+    fh_dft4<SIGN>(v[0], v[1], v[2], v[3]);             // stage Ns = 1 (no twiddles): out[4 j + r]
+    Y[4 * j] = v[0]; Y[4 * j + 1] = v[1]; Y[4 * j + 2] = v[2]; Y[4 * j + 3] = v[3];
+  }
+  __syncthreads();
+  if (act) fh_fft256_stage<SIGN, 4>(Y, X, j, sm.tw);
+  __syncthreads();
+  if (act) fh_fft256_stage<SIGN, 16>(X, Y, j, sm.tw);
+  __syncthreads();
+  if (act) fh_fft256_stage<SIGN, 64>(Y, X, j, sm.tw);
+  __syncthreads();
+  if (act) {
+    if (!INV) {
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
-      const int n = 16 * k1 + t;
-      const int pos = (n < 128) ? 2 * n : 511 - 2 * n;
-      oa[pos] = v[k1].x;
-      ob[pos] = v[k1].y;
+      for (int r = 0; r < 4; ++r) {
+        const int k = j + 64 * r;
+        const float2 zk = X[k];
+        const float2 zn = X[(FH_N - k) & (FH_N - 1)];
+        const float2 va = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 vb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        const float2 p = sm.tab[k];
+        oa[k] = p.x * va.x - p.y * va.y;
+        ob[k] = p.x * vb.x - p.y * vb.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = j + 64 * r;
+        const int pos = (n < 128) ? 2 * n : 511 - 2 * n;
+        const float2 z = X[n];
+        oa[pos] = z.x;
+        ob[pos] = z.y;
+      }
     }
-    __syncwarp();
   }
 }
 
 // ---- strip movers (all 256 threads) -------------------------------------------------------------
-// thread owns float4 #tid and #tid+256 of the strip's 2048 contiguous floats: element offset e = 4*(tid+256h)
+// A strip is ROWS*256 contiguous floats; thread t owns ROWS of them as one vector per 256*W floats:
+//   ROWS = 8: float4 #t and #t+256      ROWS = 4: float4 #t      ROWS = 2: float2 #t
+template <int ROWS> struct FhVec { static constexpr int W = (ROWS >= 4) ? 4 : 2; static constexpr int NV = ROWS / W; };
+
+template <int ROWS>
+__device__ __forceinline__ void fh_g_get(const float* __restrict__ src, float (&r)[ROWS]) {
+  if constexpr (ROWS >= 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int h = 0; h < ROWS / 4; ++h) {
+      const float4 v = s4[threadIdx.x + FH_PASS_THREADS * h];
+      r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+    }
+  } else {
+    const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x];
+    r[0] = v.x; r[1] = v.y;
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void fh_g_put(float* __restrict__ dst, const float (&r)[ROWS]) {
+  if constexpr (ROWS >= 4) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int h = 0; h < ROWS / 4; ++h) d4[threadIdx.x + FH_PASS_THREADS * h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+  } else {
+    reinterpret_cast<float2*>(dst)[threadIdx.x] = make_float2(r[0], r[1]);
+  }
+}
+// element offset (inside the strip) of the thread's vector h
+template <int ROWS>
+__device__ __forceinline__ int fh_vec_off(int h) { return FhVec<ROWS>::W * (threadIdx.x + FH_PASS_THREADS * h); }
+
+template <int ROWS>
+__device__ __forceinline__ void fh_strip_get(const float* sm_rows, float (&r)[ROWS]) {
+  constexpr int W = FhVec<ROWS>::W;
+#pragma unroll
+  for (int h = 0; h < FhVec<ROWS>::NV; ++h) {
+    const int e = fh_vec_off<ROWS>(h);
+    const float* p = sm_rows + (e >> 8) * FH_RS + (e & 255);
+    if constexpr (W == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p);
+      r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(p);
+      r[2 * h] = v.x; r[2 * h + 1] = v.y;
+    }
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void fh_strip_put(float* sm_rows, const float (&r)[ROWS]) {
+  constexpr int W = FhVec<ROWS>::W;
+#pragma unroll
+  for (int h = 0; h < FhVec<ROWS>::NV; ++h) {
+    const int e = fh_vec_off<ROWS>(h);
+    float* p = sm_rows + (e >> 8) * FH_RS + (e & 255);
+    if constexpr (W == 4) *reinterpret_cast<float4*>(p) = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+    else *reinterpret_cast<float2*>(p) = make_float2(r[2 * h], r[2 * h + 1]);
+  }
+}
+template <int ROWS>
 __device__ __forceinline__ void fh_strip_load(float* sm_rows, const float* __restrict__ src) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int f = threadIdx.x + FH_PASS_THREADS * h;
-    const float4 v = s4[f];
-    *reinterpret_cast<float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63)) = v;
-  }
+  float r[ROWS];
+  fh_g_get<ROWS>(src, r);
+  fh_strip_put<ROWS>(sm_rows, r);
 }
-__device__ __forceinline__ void fh_strip_get(const float* sm_rows, float (&r)[8]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int f = threadIdx.x + FH_PASS_THREADS * h;
-    const float4 v = *reinterpret_cast<const float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63));
-    r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
-  }
-}
-__device__ __forceinline__ void fh_strip_put(float* sm_rows, const float (&r)[8]) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int f = threadIdx.x + FH_PASS_THREADS * h;
-    *reinterpret_cast<float4*>(sm_rows + (f >> 6) * FH_RS + 4 * (f & 63)) = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
-  }
-}
-__device__ __forceinline__ void fh_g_get(const float* __restrict__ src, float (&r)[8]) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float4 v = s4[threadIdx.x + FH_PASS_THREADS * h];
-    r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
-  }
-}
-__device__ __forceinline__ void fh_g_put(float* __restrict__ dst, const float (&r)[8]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) d4[threadIdx.x + FH_PASS_THREADS * h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
-}
+template <int ROWS>
 __device__ __forceinline__ void fh_strip_store(const float* sm_rows, float* __restrict__ dst) {
-  float r[8];
-  fh_strip_get(sm_rows, r);
-  fh_g_put(dst, r);
+  float r[ROWS];
+  fh_strip_get<ROWS>(sm_rows, r);
+  fh_g_put<ROWS>(dst, r);
 }
-// transposed store of the strip: dst_plane[k][row0 + r] = rows[r][k]  (thread k writes 32 contiguous bytes)
+// transposed store of the strip: dst_plane[k][row0 + r] = rows[r][k]  (thread k writes ROWS contiguous floats)
+template <int ROWS>
 __device__ __forceinline__ void fh_strip_store_t(const float* sm_rows, float* __restrict__ dst_plane, int row0) {
   const int k = threadIdx.x;
-  float4* d = reinterpret_cast<float4*>(dst_plane + (size_t)k * FH_N + row0);
-  d[0] = make_float4(sm_rows[k], sm_rows[FH_RS + k], sm_rows[2 * FH_RS + k], sm_rows[3 * FH_RS + k]);
-  d[1] = make_float4(sm_rows[4 * FH_RS + k], sm_rows[5 * FH_RS + k], sm_rows[6 * FH_RS + k], sm_rows[7 * FH_RS + k]);
+  float* d = dst_plane + (size_t)k * FH_N + row0;
+  if constexpr (ROWS >= 4) {
+#pragma unroll
+    for (int h = 0; h < ROWS / 4; ++h)
+      reinterpret_cast<float4*>(d)[h] = make_float4(sm_rows[(4 * h) * FH_RS + k], sm_rows[(4 * h + 1) * FH_RS + k],
+                                                    sm_rows[(4 * h + 2) * FH_RS + k], sm_rows[(4 * h + 3) * FH_RS + k]);
+  } else {
+    *reinterpret_cast<float2*>(d) = make_float2(sm_rows[k], sm_rows[FH_RS + k]);
+  }
 }
 
 // In-place circular convolution along the rows of the strip with taps k[0..n) centred at c:
 //   transpose = 0:  out[j] = sum_a k[a] in[(j - (a - c)) mod 256]       transpose = 1:  in[(j + (a - c)) mod 256]
 // (all 256 threads; contains two __syncthreads)
+template <int ROWS>
 __device__ __forceinline__ void fh_strip_conv(float* sm_rows, const float* __restrict__ taps, int n, int c, int transpose) {
-  const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TPR = FH_PASS_THREADS / ROWS;        // threads per row; each produces ROWS outputs
+  const int row = threadIdx.x / TPR, l = threadIdx.x % TPR;
   const float* rr = sm_rows + row * FH_RS;
-  float acc[8];
+  float acc[ROWS];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int j = 0; j < ROWS; ++j) acc[j] = 0.f;
   for (int a = 0; a < n; ++a) {
     const float w = taps[a];
     const int off = transpose ? (a - c) : -(a - c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, rr[(lane + 32 * j + off) & (FH_N - 1)], acc[j]);
+    for (int j = 0; j < ROWS; ++j) acc[j] = fmaf(w, rr[(l + TPR * j + off) & (FH_N - 1)], acc[j]);
   }
   __syncthreads();
   float* wr = sm_rows + row * FH_RS;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wr[lane + 32 * j] = acc[j];
+  for (int j = 0; j < ROWS; ++j) wr[l + TPR * j] = acc[j];
   __syncthreads();
 }
 
 // Plain row pass: out = (TR ? transpose : identity)( DCT/IDCT along rows of in ).  grid.x strides over the
-// nplanes*32 strips.
-template <bool INV, bool TR>
+// nplanes*(256/ROWS) strips.
+template <bool INV, bool TR, int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_pass(const float* __restrict__ in, float* __restrict__ out, int nstrips, FhDctTables tab) {
-  __shared__ __align__(16) FhStripSmem sm;
+  __shared__ __align__(16) FhStripSmem<ROWS> sm;
+  constexpr int SPP = FH_N / ROWS;                   // strips per plane
   fh_strip_tables<INV>(sm, tab);
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
-    const size_t base = (size_t)s * FH_STRIP_ELEMS;
+    const size_t base = (size_t)s * ROWS * FH_N;
     __syncthreads();
-    fh_strip_load(sm.a, in + base);
+    fh_strip_load<ROWS>(sm.a, in + base);
     __syncthreads();
-    if (threadIdx.x < 64) fh_dct8_core<INV>(sm.a, sm.b, sm);
+    fh_dct_strip<INV, ROWS>(sm.a, sm.b, sm);
     __syncthreads();
-    if (TR) fh_strip_store_t(sm.b, out + (size_t)(s >> 5) * FH_N * FH_N, (s & 31) * FH_STRIP);
-    else fh_strip_store(sm.b, out + base);
+    if (TR) fh_strip_store_t<ROWS>(sm.b, out + (size_t)(s / SPP) * FH_N * FH_N, (s % SPP) * ROWS);
+    else fh_strip_store<ROWS>(sm.b, out + base);
   }
 }
 

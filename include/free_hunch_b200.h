@@ -112,6 +112,8 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
 long long fh_launch_count(int reset);
 /* Per-kernel device timing for bench.py: while enabled every launch is bracketed by a cudaEvent pair on its
  * stream.  fh_prof_report writes "kernel_name launches total_ms" lines into buf and returns the bytes needed. */
+/* Debug (FH_TRACE=1 in the environment at fh_ctx_create): 8 x 16 clock64 checkpoints of CTA 0 of the fused CG kernels. */
+int fh_trace_read(fh_ctx* ctx, long long* out_host);
 int fh_prof_enable(int on);
 int fh_prof_report(char* buf, int buflen);
 

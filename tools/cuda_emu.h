@@ -131,6 +131,8 @@ static inline double atomicAdd(double* p, double v) { static std::mutex m; std::
 static inline float atomicAdd(float* p, float v) { static std::mutex m; std::lock_guard<std::mutex> g(m); float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { static std::mutex m; std::lock_guard<std::mutex> g(m); int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { static std::mutex m; std::lock_guard<std::mutex> g(m); unsigned o = *p; *p = o + v; return o; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline char* emu_dyn_smem() { return (char*)(((uintptr_t)emu::g_block->dyn_smem.data() + 15) & ~uintptr_t(15)); }
 
