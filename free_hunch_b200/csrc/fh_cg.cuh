@@ -22,7 +22,7 @@
 #include "fh_common.cuh"
 #include "fh_dct.cuh"
 
-#define FH_MAX_SEP_TAPS 64
+#define FH_MAX_SEP_TAPS 64       // taps are staged zero-padded to a multiple of 4
 #define FH_ZROUND_FLOATS 8192    // floats per TMA round: 32 / ROWS rows of Z, each a strip-wide slice of ROWS*256 floats (32 KB)
 #define ZROUND_FLOATS 8192    // floats per TMA round: 32 / ROWS rows of Z, each a strip-wide slice of ROWS*256 floats
 #define FH_ZSTAGES 2            // rounds in flight (double buffer): 2 * 32 KB = 64 KB of dynamic shared memory
@@ -70,22 +70,26 @@ __device__ __forceinline__ double fh_reduce_partials(const double* part, int n, 
   return fh_block_sum(s, s_red);
 }
 
-// CTA-uniform read of the image's done flag (another CTA of the same launch may be setting it).  Contains __syncthreads.
-__device__ __forceinline__ bool fh_done_uniform(const FhCgFused& P, int b) {
-  __shared__ int s_done;
-  __syncthreads();
-  if (threadIdx.x == 0) s_done = P.sc ? *(volatile const int*)&P.sc[b].done : 0;
-  __syncthreads();
-  return s_done != 0;
+// The (done, tag) word of an image.  A kernel whose own CTAs may set `done` while others are starting (K1 / the p
+// kernel on convergence, xr on the p.Ap break) must reach the same decision in every thread: "stopped by an EARLIER
+// launch" = done set with a tag other than this launch's; if this very launch is setting it, every CTA re-derives the
+// stop from the same partials instead of trusting the racing flag.
+__device__ __forceinline__ bool fh_stopped_earlier(const FhCgFused& P, int b, int my_tag) {
+  if (!P.sc) return false;
+  const long long w = *(volatile const long long*)&P.sc[b].done;
+  return (int)w != 0 && (int)(w >> 32) != my_tag;
+}
+__device__ __forceinline__ void fh_set_done(FhCgScalars* sc, int tag) {
+  *(volatile long long*)&sc->done = ((long long)tag << 32) | 1LL;
 }
 
 // Consumer side of the r.r reduction of iteration `it - 1` (cg.py:258-263): returns true when image b has stopped.
-// `record` (one CTA per image) stores the scalars for the host; every CTA gets beta.
+// `record` (one CTA per image) stores the scalars for the host; every CTA gets beta.  Contains __syncthreads.
 __device__ __forceinline__ bool fh_cg_consume_rr(const FhCgFused& P, int b, int it, bool record, double* s_red, float* beta_out) {
-  const double rr_new = fh_reduce_partials(P.part_b + (size_t)b * P.ystrips, P.ystrips, s_red);
   const FhCgScalars* sc = P.sc + b;
-  const double rr_old = sc->rr[(it - 1) & 1];
+  const double rr_old = sc->rr[(it - 1) & 1];          // loads issued before the reduction's barriers
   const double stop2 = sc->stop2;
+  const double rr_new = fh_reduce_partials(P.part_b + (size_t)b * P.ystrips, P.ystrips, s_red);
   const bool converged = (stop2 >= 0.0) && (rr_new <= stop2);
   const bool stopped = converged || (it - 1 >= P.last_allowed);
   if (record && threadIdx.x == 0) {
@@ -94,7 +98,7 @@ __device__ __forceinline__ bool fh_cg_consume_rr(const FhCgFused& P, int b, int 
     w->rr[it & 1] = rr_new;
     w->niter = it - 1;
     if (converged) w->optimal = 1;
-    if (stopped) w->done = 1;
+    if (stopped) fh_set_done(w, it);
   }
   *beta_out = (float)(rr_new / rr_old);
   return stopped;
@@ -121,14 +125,19 @@ struct FhZStream {
   __device__ __forceinline__ void begin(const float* src_, long row_stride_, int m_) {
     src = src_; row_stride = row_stride_; m = m_; nrounds = (m_ + ZR - 1) / ZR;
   }
-  // thread 0 only
-  __device__ __forceinline__ void issue(int j) {
-    const int rows = min(ZR, m - j * ZR);
-    const unsigned st = issued % (unsigned)stages;
-    fh_mbar_expect_tx(bar + st, (unsigned)rows * SLICE * 4u);
-    for (int u = 0; u < rows; ++u)
-      fh_tma_load_1d(buf + (size_t)st * FH_ZROUND_FLOATS + (size_t)u * SLICE, src + (size_t)(j * ZR + u) * row_stride, SLICE * 4u, bar + st);
-    ++issued;
+  // all 32 lanes of warp 0: rounds [j0, j0 + count) -- one lane per row slice, so the copies are issued in parallel
+  __device__ __forceinline__ void issue(int j0, int count) {
+    const int lane = threadIdx.x & 31;
+    const int jr = lane / ZR, u = lane % ZR;
+    if (jr < count) {
+      const int j = j0 + jr;
+      const int rows = min(ZR, m - j * ZR);
+      const unsigned st = (issued + (unsigned)jr) % (unsigned)stages;
+      if (u == 0) fh_mbar_expect_tx(bar + st, (unsigned)rows * SLICE * 4u);
+      if (u < rows)
+        fh_tma_load_1d(buf + (size_t)st * FH_ZROUND_FLOATS + (size_t)u * SLICE, src + (size_t)(j * ZR + u) * row_stride, SLICE * 4u, bar + st);
+    }
+    issued += (unsigned)count;
   }
   // all threads; returns the buffer of the round just completed
   __device__ __forceinline__ const float* wait() {
@@ -147,11 +156,11 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_fwd_rows(FhCgFused P, const float* __restrict__ src, const float* __restrict__ vec, int it) {
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
-  __shared__ float s_taps[FH_MAX_SEP_TAPS];
+  __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ double s_red[33];
   FH_TRACE(P, 0, 0);
   fh_strip_tables<false, ROWS>(sm, P.tab);
-  if (P.fuse == 2 && threadIdx.x < P.nr) s_taps[threadIdx.x] = P.kr[threadIdx.x];
+  const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kr, P.nr, P.cr, 0) : 0;
   const int nstrips = P.B * P.strips_per_image;
   int cur_b = -1;
   bool stopped = false;
@@ -164,7 +173,7 @@ fh_k_cg_fwd_rows(FhCgFused P, const float* __restrict__ src, const float* __rest
     FH_TRACE(P, 0, 1);
     if (b != cur_b) {
       cur_b = b;
-      stopped = fh_done_uniform(P, b);
+      stopped = fh_stopped_earlier(P, b, it);
       FH_TRACE(P, 0, 2);
       if (!src && it >= 2 && !stopped) stopped = fh_cg_consume_rr(P, b, it, s == b * P.strips_per_image, s_red, &beta);
     }
@@ -192,7 +201,7 @@ fh_k_cg_fwd_rows(FhCgFused P, const float* __restrict__ src, const float* __rest
     fh_strip_put<ROWS>(sm.a, v);
     __syncthreads();
     FH_TRACE(P, 0, 4);
-    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.a, s_taps, P.nr, P.cr, 1);
+    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.a, s_taps, P.nr, tc);
     FH_TRACE(P, 0, 5);
     fh_dct_strip<false, ROWS>(sm.a, sm.b, sm);
     __syncthreads();
@@ -207,13 +216,13 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_fwd_cols(FhCgFused P) {
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
-  __shared__ float s_taps[FH_MAX_SEP_TAPS];
+  __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ double s_w[FH_PASS_THREADS / 32][FH_MAXM];
   __shared__ __align__(8) fh_mbar_t s_bar[FH_ZMAX_STAGES];
   FH_DYN_SMEM(float, zbuf);
   FH_TRACE(P, 1, 0);
   fh_strip_tables<false, ROWS>(sm, P.tab);
-  if (P.fuse == 2 && threadIdx.x < P.nc) s_taps[threadIdx.x] = P.kc[threadIdx.x];
+  const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kc, P.nc, P.cc, 0) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < P.zstages; ++i) fh_mbar_init(s_bar + i, 1);
@@ -231,13 +240,12 @@ fh_k_cg_fwd_cols(FhCgFused P) {
     const size_t off = base - (size_t)b * d;              // offset inside the image
     __syncthreads();                                      // previous strip fully consumed (smem, Z buffers); barriers initialised
     zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
-    if (tid == 0)                                         // Z does not depend on the transform: start it now
-      for (int j = 0; j < min(zs.stages, zs.nrounds); ++j) zs.issue(j);
+    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));    // Z does not depend on the transform: start it now
     FH_TRACE(P, 1, 1);
     fh_strip_load<ROWS>(sm.a, P.T + base);
     __syncthreads();
     FH_TRACE(P, 1, 2);
-    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.a, s_taps, P.nc, P.cc, 1);
+    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.a, s_taps, P.nc, tc);
     FH_TRACE(P, 1, 3);
     fh_dct_strip<false, ROWS>(sm.a, sm.b, sm);
     __syncthreads();
@@ -263,18 +271,35 @@ fh_k_cg_fwd_cols(FhCgFused P) {
 #pragma unroll
           for (int e = 0; e < ROWS; ++e) acc[u] = fmaf(z[e], w[e], acc[u]);
         }
+        if constexpr (ZR == 4) {
+          // 4 warp sums with 6 shuffles: halve the value set while halving the lane set, then finish one value per lane
+          const bool hi = lane & 16, mid = lane & 8;
+          float ka = hi ? acc[2] : acc[0], kb = hi ? acc[3] : acc[1];
+          ka += __shfl_xor_sync(0xffffffffu, hi ? acc[0] : acc[2], 16);
+          kb += __shfl_xor_sync(0xffffffffu, hi ? acc[1] : acc[3], 16);
+          float kp = mid ? kb : ka;
+          kp += __shfl_xor_sync(0xffffffffu, mid ? ka : kb, 8);
+          kp += __shfl_xor_sync(0xffffffffu, kp, 4);
+          kp += __shfl_xor_sync(0xffffffffu, kp, 2);
+          kp += __shfl_xor_sync(0xffffffffu, kp, 1);
+          if ((lane & 7) == 0 && j * ZR + (lane >> 3) < P.m) s_w[warp][j * ZR + (lane >> 3)] = (double)kp;   // lane 8r holds row r
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+          for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-          for (int u = 0; u < ZR; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-        if (lane == 0) {
+            for (int u = 0; u < ZR; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+          if (lane == 0) {
 #pragma unroll
-          for (int u = 0; u < ZR; ++u)
-            if (j * ZR + u < P.m) s_w[warp][j * ZR + u] = (double)acc[u];
+            for (int u = 0; u < ZR; ++u)
+              if (j * ZR + u < P.m) s_w[warp][j * ZR + u] = (double)acc[u];
+          }
         }
-        __syncthreads();                                  // everyone is done with this buffer
-        if (tid == 0 && j + zs.stages < zs.nrounds) zs.issue(j + zs.stages);
+        if (j + zs.stages < zs.nrounds) {                   // recycle this buffer for a later round
+          __syncthreads();
+          if (tid < 32) zs.issue(j + zs.stages, 1);
+        }
       }
+      __syncthreads();
       const int sidx = s - b * P.strips_per_image;
       if (tid < P.m) {
         double t = 0.0;
@@ -293,15 +318,14 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_inv_cols(FhCgFused P) {
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
-  __shared__ float s_taps[FH_MAX_SEP_TAPS];
+  __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ float s_c[FH_MAXM];
-  __shared__ double s_part[4][FH_MAXM];
   __shared__ double s_sum[FH_MAXM];
   __shared__ __align__(8) fh_mbar_t s_bar[FH_ZMAX_STAGES];
   FH_DYN_SMEM(float, zbuf);
   FH_TRACE(P, 2, 0);
   fh_strip_tables<true, ROWS>(sm, P.tab);
-  if (P.fuse == 2 && threadIdx.x < P.nc) s_taps[threadIdx.x] = P.kc[threadIdx.x];
+  const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kc, P.nc, P.cc, 1) : 0;
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i < P.zstages; ++i) fh_mbar_init(s_bar + i, 1);
@@ -320,8 +344,7 @@ fh_k_cg_inv_cols(FhCgFused P) {
     const size_t off = base - (size_t)b * d;
     __syncthreads();
     zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
-    if (tid == 0)
-      for (int j = 0; j < min(zs.stages, zs.nrounds); ++j) zs.issue(j);
+    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
     FH_TRACE(P, 2, 1);
     float acc[ROWS], dl[ROWS];
     fh_g_get<ROWS>(P.W + base, acc);
@@ -329,20 +352,37 @@ fh_k_cg_inv_cols(FhCgFused P) {
     if (b != cur_b && P.m > 0) {
       // coef = Gs * (sum over the strips of K2's partial dots), same order in every CTA; overlaps the Z copies
       cur_b = b;
-      const int i = tid & (FH_MAXM - 1), part = tid >> 6;
+      // thread (i, part): row i = tid / 4 of the partial matrix, strips k = part (mod 4); loads are batched 8 deep
+      const int i = tid >> 2, part = tid & 3;
+      double t = 0.0;
       if (i < P.m) {
-        double t = 0.0;
-        for (int k = part; k < P.strips_per_image; k += 4) t += fh_ldcg(&P.dots_partial[((size_t)b * P.strips_per_image + k) * FH_MAXM + i]);
-        s_part[part][i] = t;
+        const double* col = P.dots_partial + (size_t)b * P.strips_per_image * FH_MAXM + i;
+        for (int k0 = part; k0 < P.strips_per_image; k0 += 32) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = (k0 + 4 * u < P.strips_per_image) ? fh_ldcg(col + (size_t)(k0 + 4 * u) * FH_MAXM) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t += v[u];
+        }
       }
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      if (part == 0 && i < P.m) s_sum[i] = t;
       __syncthreads();
-      if (tid < P.m) s_sum[tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
-      __syncthreads();
-      if (tid < P.m) {
-        const double* g = P.Gs + ((size_t)b * FH_MAXM + tid) * FH_MAXM;
-        double t = 0.0;
-        for (int j = 0; j < P.m; ++j) t += g[j] * s_sum[j];
-        s_c[tid] = (float)t;
+      {
+        // coef_i = sum_j Gs[i][j] s_sum[j]: 4 threads per row, 16 columns each (m <= 64), loads batched
+        double a = 0.0;
+        if (i < P.m) {
+          const double* g = P.Gs + ((size_t)b * FH_MAXM + i) * FH_MAXM;
+          double gv[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) gv[u] = (part + 4 * u < P.m) ? g[part + 4 * u] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) a += gv[u] * ((part + 4 * u < P.m) ? s_sum[part + 4 * u] : 0.0);
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (part == 0 && i < P.m) s_c[i] = (float)a;
       }
       __syncthreads();
     }
@@ -359,8 +399,10 @@ fh_k_cg_inv_cols(FhCgFused P) {
 #pragma unroll
         for (int e = 0; e < ROWS; ++e) acc[e] = fmaf(c, live ? z[e] : 0.f, acc[e]);
       }
-      __syncthreads();
-      if (tid == 0 && j + zs.stages < zs.nrounds) zs.issue(j + zs.stages);
+      if (j + zs.stages < zs.nrounds) {
+        __syncthreads();
+        if (tid < 32) zs.issue(j + zs.stages, 1);
+      }
     }
 #pragma unroll
     for (int e = 0; e < ROWS; ++e) acc[e] *= dl[e];
@@ -370,7 +412,7 @@ fh_k_cg_inv_cols(FhCgFused P) {
     fh_dct_strip<true, ROWS>(sm.a, sm.b, sm);
     __syncthreads();
     FH_TRACE(P, 2, 12);
-    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.b, s_taps, P.nc, P.cc, 0);
+    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.b, s_taps, P.nc, tc);
     FH_TRACE(P, 2, 13);
     fh_strip_store_t<ROWS>(sm.b, P.T + (size_t)(s / (FH_N / ROWS)) * FH_N * FH_N, (s % (FH_N / ROWS)) * ROWS);
     FH_TRACE(P, 2, 14);
@@ -384,10 +426,10 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_inv_rows(FhCgFused P, float* __restrict__ dst, const float* __restrict__ vec, int it) {
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
-  __shared__ float s_taps[FH_MAX_SEP_TAPS];
+  __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ double s_red[33];
   fh_strip_tables<true, ROWS>(sm, P.tab);
-  if (P.fuse == 2 && threadIdx.x < P.nr) s_taps[threadIdx.x] = P.kr[threadIdx.x];
+  const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kr, P.nr, P.cr, 1) : 0;
   const int tid = threadIdx.x;
   const int nstrips = P.B * P.strips_per_image;
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
@@ -400,7 +442,7 @@ fh_k_cg_inv_rows(FhCgFused P, float* __restrict__ dst, const float* __restrict__
     __syncthreads();
     fh_dct_strip<true, ROWS>(sm.a, sm.b, sm);
     __syncthreads();
-    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.b, s_taps, P.nr, P.cr, 0);
+    if (P.fuse == 2) fh_strip_conv<ROWS>(sm.b, s_taps, P.nr, tc);
     float t[ROWS];
     fh_strip_get<ROWS>(sm.b, t);
     if (P.fuse == 1) fh_mask_mul<ROWS>(P, b, row0, t);
@@ -460,7 +502,7 @@ fh_k_cg_p(FhCgFused P, int it) {
     const int b = s / P.ystrips;
     if (b != cur_b) {
       cur_b = b;
-      stopped = fh_done_uniform(P, b);
+      stopped = fh_stopped_earlier(P, b, it);
       if (it >= 2 && !stopped) stopped = fh_cg_consume_rr(P, b, it, s == b * P.ystrips, s_red, &beta);
     }
     if (stopped) continue;
@@ -494,14 +536,15 @@ fh_k_cg_xr(FhCgFused P, int it) {
     const int b = s / P.ystrips;
     if (b != cur_b) {
       cur_b = b;
-      stopped = fh_done_uniform(P, b);
+      stopped = fh_stopped_earlier(P, b, -it);
       if (!stopped) {
+        const double rr_cur = P.sc[b].rr[it & 1];
         const double pAp = fh_reduce_partials(P.part_a + (size_t)b * P.ystrips, P.ystrips, s_red);
         if (pAp <= 1e-16) {
           stopped = true;
-          if (s == b * P.ystrips && tid == 0) { P.sc[b].done = 1; P.sc[b].niter = it; }
+          if (s == b * P.ystrips && tid == 0) { P.sc[b].niter = it; fh_set_done(P.sc + b, -it); }
         } else {
-          alpha = (float)(P.sc[b].rr[it & 1] / pAp);
+          alpha = (float)(rr_cur / pAp);
         }
       }
     }
@@ -579,7 +622,7 @@ fh_k_cg_r0_scalars(FhCgFused P, double rtol, double atol, int use_stop) {
     sc.stop2 = use_stop ? stop * stop : -1.0;
     sc.resid2 = rr0;
     sc.alpha = 0.0; sc.beta = 0.0;
-    sc.done = 0; sc.optimal = 0; sc.niter = 0; sc.pad = 0;
+    sc.done = 0; sc.done_tag = 0; sc.optimal = 0; sc.niter = 0;
     P.sc[b] = sc;
   }
 }

@@ -42,11 +42,11 @@ struct FhCgScalars {
   double bnorm2;       // |b|^2
   double stop2;        // (rtol*|b|)^2, or -1 when the residual test is disabled
   double resid2;       // last |r|^2
-  double alpha, beta;  // step lengths of the current iteration
-  int done;            // 1 once the loop has broken for this image
+  double alpha, beta;  // (legacy path) step lengths of the current iteration
+  int done;            // 1 once the loop has broken for this image   } one aligned 8-byte word: written and read
+  int done_tag;        // which launch set it (+it: K1 / p kernel, -it: xr) } atomically (fh_cg.cuh: stopped-earlier test)
   int optimal;         // 1 if broken by the residual test
   int niter;           // k of cg.py:244 at the break (or iterations run so far)
-  int pad;
 };
 
 __device__ __forceinline__ double fh_warp_sum(double v) {

@@ -246,28 +246,61 @@ __device__ __forceinline__ void fh_strip_store_t(const float* sm_rows, float* __
   }
 }
 
-// In-place circular convolution along the rows of the strip with taps k[0..n) centred at c:
-//   transpose = 0:  out[j] = sum_a k[a] in[(j - (a - c)) mod 256]       transpose = 1:  in[(j + (a - c)) mod 256]
-// (all 256 threads; contains two __syncthreads)
+// In-place circular CORRELATION along the rows of the strip with taps t[0..n) centred at c:
+//     out[j] = sum_a t[a] in[(j + a - c) mod 256]
+// (A^T of the blur uses the PSF taps as they are; A uses them reversed with centre n-1-c -- see fh_cg.cuh.)
+// `taps` is a shared-memory array zero-padded to a multiple of 4.  All 256 threads; contains two __syncthreads.
+// Fast path (8-row strips, c % 4 == 0): each thread produces 8 consecutive outputs from a register window that
+// slides over the row 4 taps at a time -- one LDS.128 per 32 FMAs.
 template <int ROWS>
-__device__ __forceinline__ void fh_strip_conv(float* sm_rows, const float* __restrict__ taps, int n, int c, int transpose) {
-  constexpr int TPR = FH_PASS_THREADS / ROWS;        // threads per row; each produces ROWS outputs
-  const int row = threadIdx.x / TPR, l = threadIdx.x % TPR;
-  const float* rr = sm_rows + row * FH_RS;
+__device__ __forceinline__ void fh_strip_conv(float* sm_rows, const float* __restrict__ taps, int n, int c) {
   float acc[ROWS];
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) acc[j] = 0.f;
+  if (ROWS == 8 && (c & 3) == 0) {
+    const int row = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const float* rr = sm_rows + row * FH_RS;
+    const int base = 8 * l - c;                           // multiple of 4
+    float4 f0 = *reinterpret_cast<const float4*>(rr + (base & (FH_N - 1)));
+    float4 f1 = *reinterpret_cast<const float4*>(rr + ((base + 4) & (FH_N - 1)));
+    for (int a0 = 0; a0 < n; a0 += 4) {
+      const float4 f2 = *reinterpret_cast<const float4*>(rr + ((base + a0 + 8) & (FH_N - 1)));
+      const float4 tk = *reinterpret_cast<const float4*>(taps + a0);
+      const float win[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+      const float tt[4] = {tk.x, tk.y, tk.z, tk.w};
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int e = 0; e < ROWS; ++e) acc[e] = fmaf(tt[aa], win[aa + e], acc[e]);
+      f0 = f1; f1 = f2;
+    }
+    __syncthreads();
+    float* wr = sm_rows + row * FH_RS + 8 * l;
+    *reinterpret_cast<float4*>(wr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(wr + 4) = make_float4(acc[4 % ROWS], acc[5 % ROWS], acc[6 % ROWS], acc[7 % ROWS]);
+    __syncthreads();
+    return;
+  }
+  constexpr int TPR = FH_PASS_THREADS / ROWS;        // threads per row; each produces ROWS outputs
+  const int row = threadIdx.x / TPR, l = threadIdx.x % TPR;
+  const float* rr = sm_rows + row * FH_RS;
   for (int a = 0; a < n; ++a) {
     const float w = taps[a];
-    const int off = transpose ? (a - c) : -(a - c);
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) acc[j] = fmaf(w, rr[(l + TPR * j + off) & (FH_N - 1)], acc[j]);
+    for (int j = 0; j < ROWS; ++j) acc[j] = fmaf(w, rr[(l + TPR * j + a - c) & (FH_N - 1)], acc[j]);
   }
   __syncthreads();
   float* wr = sm_rows + row * FH_RS;
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) wr[l + TPR * j] = acc[j];
   __syncthreads();
+}
+// Stage separable taps for fh_strip_conv: forward = 0 (A^T): t = k, centre c;  forward = 1 (A): t = reversed k,
+// centre n-1-c.  Zero-padded to a multiple of 4.  Caller syncs.  Returns the centre to pass to fh_strip_conv.
+__device__ __forceinline__ int fh_stage_taps(float* s_taps, const float* __restrict__ k, int n, int c, int forward) {
+  const int np = (n + 3) & ~3;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_taps[i] = (i < n) ? (forward ? k[n - 1 - i] : k[i]) : 0.f;
+  return forward ? n - 1 - c : c;
 }
 
 // Plain row pass: out = (TR ? transpose : identity)( DCT/IDCT along rows of in ).  grid.x strides over the

@@ -768,7 +768,7 @@ __global__ void fh_k_cg_init_scalars(FhCgScalars* sc, const double* part_rr, con
   s.stop2 = use_stop ? stop * stop : -1.0;
   s.resid2 = rr;
   s.alpha = 0.0; s.beta = 0.0;
-  s.done = 0; s.optimal = 0; s.niter = 0; s.pad = 0;
+  s.done = 0; s.done_tag = 0; s.optimal = 0; s.niter = 0;
   sc[b] = s;
 }
 
