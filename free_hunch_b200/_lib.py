@@ -1,9 +1,7 @@
 """ctypes binding of libfreehunch_b200.so (C ABI: include/free_hunch_b200.h).
 
-There is no CPU fallback: if the CUDA library is missing the import fails loudly.  The only other
-library this loader will accept is the CPU *emulation* build used by the CPU test-suite
-(tests/emu/build_emu.sh), and only when the test harness asks for it explicitly through
-FREE_HUNCH_B200_EMU_LIB -- it is never selected automatically and never on a machine's product path.
+There is no CPU fallback: the only library this loader opens is the sm_100a build next to this file, and every
+entry point fails with FH_ECUDA without a CUDA device.  If the library is missing, first use fails loudly.
 """
 import ctypes
 import os
@@ -63,25 +61,14 @@ def _bind(path):
 
 
 _lib = None
-_is_emu = False
 
 
 def lib():
     """The loaded library (loads on first use)."""
-    global _lib, _is_emu
+    global _lib
     if _lib is None:
-        emu = os.environ.get("FREE_HUNCH_B200_EMU_LIB")
-        if emu:
-            _lib = _bind(emu)
-            _is_emu = True
-        else:
-            _lib = _bind(_LIB_PATH)
+        _lib = _bind(_LIB_PATH)
     return _lib
-
-
-def is_emulated():
-    lib()
-    return _is_emu
 
 
 def check(rc):

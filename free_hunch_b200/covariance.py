@@ -30,8 +30,7 @@ def get_context(device, channels, height, width, max_batch=1):
 
 
 def _default_device():
-    from . import _lib
-    return torch.device("cpu") if _lib.is_emulated() else torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 class CovarianceHessianBFGS:

@@ -244,7 +244,9 @@ static inline int pick_rows(const fh_ctx* c, int nplanes) {
 }
 static inline int pick_zstages(const fh_ctx* c, int nstrips) {
   if (const char* e = getenv("FH_ZSTAGES")) { int v = atoi(e); if (v >= 1 && v <= FH_ZMAX_STAGES) return v; }
-  return nstrips <= c->sms ? 5 : 2;         // one CTA per SM with a deep Z pipeline, or two CTAs per SM
+  // one CTA per SM with a deep Z pipeline (4 x 32 KB leaves room for the next kernel's prologue to co-reside),
+  // or two CTAs per SM
+  return nstrips <= c->sms ? 4 : 2;
 }
 #define FH_ROWS_SWITCH(R, ...)                                    \
   switch (R) {                                                    \
@@ -787,20 +789,20 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
     const float* vec = it == 0 ? x : nullptr;
     FH_ROWS_SWITCH(R, {
       if (fusedop) {
-        FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, vec, it);
-        FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
-        FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
-        FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, vec, it);
+        FH_LAUNCH_PDL(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, vec, it);
+        FH_LAUNCH_PDL(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH_PDL(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH_PDL(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, vec, it);
       } else {
-        if (it >= 1) FH_LAUNCH(fh_k_cg_p<RR>, gy, block, 0, stream, P, it);
+        if (it >= 1) FH_LAUNCH_PDL(fh_k_cg_p<RR>, gy, block, 0, stream, P, it);
         const float* pv = vec ? vec : P.p;
         if ((rc2 = fh_op_apply(o, pv, img, B, 1, stream))) return rc2;
-        FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)img, (const float*)nullptr, 0);
-        FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
-        FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
-        FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, img2, (const float*)nullptr, 0);
+        FH_LAUNCH_PDL(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)img, (const float*)nullptr, 0);
+        FH_LAUNCH_PDL(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH_PDL(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        FH_LAUNCH_PDL(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, img2, (const float*)nullptr, 0);
         if ((rc2 = fh_op_apply(o, img2, t, B, 0, stream))) return rc2;
-        FH_LAUNCH(fh_k_cg_q2<RR>, gy, block, 0, stream, P, (const float*)t, vec, it);
+        FH_LAUNCH_PDL(fh_k_cg_q2<RR>, gy, block, 0, stream, P, (const float*)t, vec, it);
       }
     });
     FH_KCHECK();
@@ -813,7 +815,7 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   int poll = 4, since = 0;
   for (int it = 1; it <= last; ++it) {
     if ((rc = apply(it))) return rc;                               // (stop test of it-1,) p update, q = A_op p
-    FH_ROWS_SWITCH(R, { FH_LAUNCH(fh_k_cg_xr<RR>, gy, block, 0, stream, P, it); });
+    FH_ROWS_SWITCH(R, { FH_LAUNCH_PDL(fh_k_cg_xr<RR>, gy, block, 0, stream, P, it); });
     FH_KCHECK();
     if (++since >= poll || it == last) {
       since = 0;

@@ -159,8 +159,10 @@ fh_k_cg_fwd_rows(FhCgFused P, const float* __restrict__ src, const float* __rest
   __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ double s_red[33];
   FH_TRACE(P, 0, 0);
+  fh_pdl_trigger();
   fh_strip_tables<false, ROWS>(sm, P.tab);
   const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kr, P.nr, P.cr, 0) : 0;
+  fh_pdl_wait();                                        // everything below reads what the previous kernel wrote
   const int nstrips = P.B * P.strips_per_image;
   int cur_b = -1;
   bool stopped = false;
@@ -221,6 +223,7 @@ fh_k_cg_fwd_cols(FhCgFused P) {
   __shared__ __align__(8) fh_mbar_t s_bar[FH_ZMAX_STAGES];
   FH_DYN_SMEM(float, zbuf);
   FH_TRACE(P, 1, 0);
+  fh_pdl_trigger();
   fh_strip_tables<false, ROWS>(sm, P.tab);
   const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kc, P.nc, P.cc, 0) : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -233,14 +236,28 @@ fh_k_cg_fwd_cols(FhCgFused P) {
   zs.buf = zbuf; zs.bar = s_bar; zs.stages = P.zstages; zs.issued = 0; zs.waited = 0;
   const int nstrips = P.B * P.strips_per_image;
   const long d = (long)P.strips_per_image * (ROWS * FH_N);
+  // prologue (may overlap the previous kernel): Z of this CTA's first strip starts streaming now
+  __syncthreads();                                        // barriers initialised
+  if ((int)blockIdx.x < nstrips) {
+    const int b0 = blockIdx.x / P.strips_per_image;
+    zs.begin(P.Z + (size_t)b0 * FH_MAXM * d + ((size_t)blockIdx.x * (ROWS * FH_N) - (size_t)b0 * d), d, P.m);
+    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
+  }
+  fh_pdl_wait();
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
     const int b = s / P.strips_per_image;
-    if (P.sc && P.sc[b].done) continue;
+    const bool prefetched = (s == (int)blockIdx.x);
     const size_t base = (size_t)s * (ROWS * FH_N);
     const size_t off = base - (size_t)b * d;              // offset inside the image
-    __syncthreads();                                      // previous strip fully consumed (smem, Z buffers); barriers initialised
-    zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
-    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));    // Z does not depend on the transform: start it now
+    if (P.sc && P.sc[b].done) {
+      if (prefetched) for (int j = 0; j < min(zs.stages, zs.nrounds); ++j) zs.wait();   // drain the prologue's copies
+      continue;
+    }
+    __syncthreads();                                      // previous strip fully consumed (smem, Z buffers)
+    if (!prefetched) {
+      zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
+      if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
+    }
     FH_TRACE(P, 1, 1);
     fh_strip_load<ROWS>(sm.a, P.T + base);
     __syncthreads();
@@ -324,6 +341,7 @@ fh_k_cg_inv_cols(FhCgFused P) {
   __shared__ __align__(8) fh_mbar_t s_bar[FH_ZMAX_STAGES];
   FH_DYN_SMEM(float, zbuf);
   FH_TRACE(P, 2, 0);
+  fh_pdl_trigger();
   fh_strip_tables<true, ROWS>(sm, P.tab);
   const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kc, P.nc, P.cc, 1) : 0;
   const int tid = threadIdx.x;
@@ -337,14 +355,27 @@ fh_k_cg_inv_cols(FhCgFused P) {
   const int nstrips = P.B * P.strips_per_image;
   const long d = (long)P.strips_per_image * (ROWS * FH_N);
   int cur_b = -1;
+  __syncthreads();                                        // barriers initialised
+  if ((int)blockIdx.x < nstrips) {                        // prologue: Z of the first strip (independent of K2)
+    const int b0 = blockIdx.x / P.strips_per_image;
+    zs.begin(P.Z + (size_t)b0 * FH_MAXM * d + ((size_t)blockIdx.x * (ROWS * FH_N) - (size_t)b0 * d), d, P.m);
+    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
+  }
+  fh_pdl_wait();
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
     const int b = s / P.strips_per_image;
-    if (P.sc && P.sc[b].done) continue;
+    const bool prefetched = (s == (int)blockIdx.x);
     const size_t base = (size_t)s * (ROWS * FH_N);
     const size_t off = base - (size_t)b * d;
+    if (P.sc && P.sc[b].done) {
+      if (prefetched) for (int j = 0; j < min(zs.stages, zs.nrounds); ++j) zs.wait();
+      continue;
+    }
     __syncthreads();
-    zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
-    if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
+    if (!prefetched) {
+      zs.begin(P.Z + (size_t)b * FH_MAXM * d + off, d, P.m);
+      if (tid < 32) zs.issue(0, min(zs.stages, zs.nrounds));
+    }
     FH_TRACE(P, 2, 1);
     float acc[ROWS], dl[ROWS];
     fh_g_get<ROWS>(P.W + base, acc);
@@ -428,8 +459,10 @@ fh_k_cg_inv_rows(FhCgFused P, float* __restrict__ dst, const float* __restrict__
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
   __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
   __shared__ double s_red[33];
+  fh_pdl_trigger();
   fh_strip_tables<true, ROWS>(sm, P.tab);
   const int tc = (P.fuse == 2) ? fh_stage_taps(s_taps, P.kr, P.nr, P.cr, 1) : 0;
+  fh_pdl_wait();
   const int tid = threadIdx.x;
   const int nstrips = P.B * P.strips_per_image;
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
@@ -469,6 +502,8 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_q2(FhCgFused P, const float* __restrict__ t_in, const float* __restrict__ vec, int it) {
   __shared__ double s_red[33];
+  fh_pdl_trigger();
+  fh_pdl_wait();
   const int tid = threadIdx.x;
   const int nstrips = P.B * P.ystrips;
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
@@ -494,6 +529,8 @@ template <int ROWS>
 __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_p(FhCgFused P, int it) {
   __shared__ double s_red[33];
+  fh_pdl_trigger();
+  fh_pdl_wait();
   const int nstrips = P.B * P.ystrips;
   int cur_b = -1;
   bool stopped = false;
@@ -532,6 +569,8 @@ fh_k_cg_xr(FhCgFused P, int it) {
   bool stopped = false;
   float alpha = 0.f;
   FH_TRACE(P, 4, 0);
+  fh_pdl_trigger();
+  fh_pdl_wait();
   for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
     const int b = s / P.ystrips;
     if (b != cur_b) {

@@ -33,6 +33,38 @@ void fh_prof_end(cudaStream_t stream);
 
 extern long long fh_g_launches;
 
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The CG iteration is a chain of short dependent kernels.  Launched with the programmatic-stream-serialization
+// attribute, kernel N+1 may start while kernel N is still running; it does everything that does not depend on N
+// (twiddle tables, barrier init, the TMA prefetch of Z) and then blocks in fh_pdl_wait() until N has completed and
+// its writes are visible.  fh_pdl_trigger() (first statement of every chained kernel) is what allows N+1 to start.
+#ifdef FH_EMU
+#define FH_LAUNCH_PDL FH_LAUNCH
+static inline void fh_pdl_wait() {}
+static inline void fh_pdl_trigger() {}
+#else
+#include <utility>
+template <typename... KArgs, typename... Args>
+static inline void fh_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#define FH_LAUNCH_PDL(kern, grid, block, smem, stream, ...)                              \
+  do {                                                                                   \
+    if (fh_g_prof_on) fh_prof_begin(#kern, (cudaStream_t)(stream));                      \
+    fh_launch_pdl(kern, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__);         \
+    if (fh_g_prof_on) fh_prof_end((cudaStream_t)(stream));                               \
+    ++fh_g_launches;                                                                     \
+  } while (0)
+__device__ __forceinline__ void fh_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void fh_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 #define FH_MAXM 64          // max rows of Z (2 per space update): 32 BFGS pairs
 #define FH_N 256            // DCT size (H = W = 256 in the DCT basis)
 

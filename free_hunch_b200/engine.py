@@ -14,6 +14,11 @@ BASIS_IDENTITY, BASIS_DCT = 0, 1
 MAX_RANK = 64            # FH_MAXM: rows of Z (two per BFGS space update)
 
 
+def _check_device(device):
+    if device.type != "cuda":
+        raise _lib.FreeHunchLibraryError("free_hunch_b200 needs a CUDA device (no CPU fallback)")
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -23,8 +28,7 @@ class Context:
 
     def __init__(self, device, max_batch=1, channels=3, height=256, width=256):
         self.device = torch.device(device)
-        if self.device.type != "cuda" and not _lib.is_emulated():
-            raise _lib.FreeHunchLibraryError("free_hunch_b200 needs a CUDA device (no CPU fallback)")
+        _check_device(self.device)
         self.max_batch, self.C, self.H, self.W = max_batch, channels, height, width
         self.d = channels * height * width
         h = ctypes.c_void_p()

@@ -13,12 +13,20 @@ if ROOT not in sys.path:
 
 HAS_CUDA = torch.cuda.is_available()
 EMU_LIB = os.path.join(ROOT, "tests", "emu", "libfreehunch_emu.so")
-if not HAS_CUDA:
-    # CPU box: exercise the kernels through the emulation build (tests/emu/build_emu.sh); never used on a GPU box
+
+
+def use_emulation():
+    """CPU box only: point the package's binding at the g++ build of the SAME kernel sources (tests/emu/build_emu.sh,
+    tools/cuda_emu.h) so their index logic and algebra can be checked without a GPU.  This lives in the test harness:
+    the product loader knows nothing about it, and the -m gpu tests assert that the real library is the one loaded."""
+    assert not HAS_CUDA, "the emulation build is never used on a GPU box"
     if not os.path.exists(EMU_LIB):
         import subprocess
         subprocess.check_call(["bash", os.path.join(ROOT, "tests", "emu", "build_emu.sh")])
-    os.environ["FREE_HUNCH_B200_EMU_LIB"] = EMU_LIB
+    from free_hunch_b200 import _lib, engine
+    _lib._lib = _lib._bind(EMU_LIB)
+    engine._check_device = lambda device: None
+    return engine
 
 DEVICE = "cuda" if HAS_CUDA else "cpu"
 SUB = 97

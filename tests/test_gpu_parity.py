@@ -27,7 +27,7 @@ S0 = 80.2878
 @pytest.fixture(scope="module")
 def E():
     from free_hunch_b200 import engine, _lib
-    assert not _lib.is_emulated(), "GPU tests must run on the real sm_100a library"
+    assert _lib.lib()._name.endswith("libfreehunch_b200.so"), "GPU tests must run on the real sm_100a library"
     return engine
 
 

@@ -15,13 +15,15 @@ from oracle import fh_oracle as fo  # noqa: E402
 
 @pytest.fixture(scope="module")
 def E():
-    from free_hunch_b200 import engine
-    return engine
+    from free_hunch_b200 import _lib, engine
+    saved = (_lib._lib, engine._check_device)
+    yield H.use_emulation()
+    _lib._lib, engine._check_device = saved
 
 
-def test_emulated_library_is_marked(E):
+def test_emulation_is_the_test_harness_choice(E):
     from free_hunch_b200 import _lib
-    assert _lib.is_emulated()
+    assert _lib.lib()._name.endswith("libfreehunch_emu.so")
 
 
 @pytest.mark.parametrize("rows", [8, 4, 2])
