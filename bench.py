@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--solver", default="heun", choices=["heun", "euler"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batched", type=int, default=16, help="also report a B-images-per-GPU step (HBM-bound regime); 0 = off")
     return ap.parse_args()
 
 
@@ -173,6 +174,19 @@ def total_calls(a):
     return 2 * a.num_steps - 1 if a.solver == "heun" else a.num_steps
 
 
+def cpu_images_per_s(a, calls, secs):
+    """Scale the bounded prefix to whole images: by CG-iteration share when the oracle's full iteration profile of this
+    workload is committed (tests/golden/bench_oracle_iters.json, tools/make_bench_iters.py), else by call share."""
+    key = f"{a.operator}/{a.num_steps}/{a.solver}"
+    try:
+        prof = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_oracle_iters.json")))[key]
+        total = float(sum(prof["niters"]))
+        done = float(sum(c["niter"] for c in calls))
+        return (done / total) / secs, f"{int(done)} of {int(total)} CG iterations of one image (first {len(calls)} of {total_calls(a)} mechanism calls)"
+    except (OSError, KeyError):
+        return (len(calls) / total_calls(a)) / secs, f"first {len(calls)} of {total_calls(a)} mechanism calls of one image, scaled by call count"
+
+
 def run_reference_arm(a, assets):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,14 +200,12 @@ def run_reference_arm(a, assets):
     t0 = time.perf_counter()
     for _ in range(a.steps):
         calls, complete, secs = cpu_reference_sample(assets, a, per_step, cores)
-        n = len(calls)
-        vals.append((n / total_calls(a)) / secs)
-        samples.append(n)
+        v_, how = cpu_images_per_s(a, calls, secs)
+        vals.append(v_)
+        samples.append(how)
     ms = (time.perf_counter() - t0) / max(1, a.steps) * 1e3
     v = float(np.mean(vals))
-    sample = (f"first {samples[0]} of {total_calls(a)} mechanism calls of one image per step (~{per_step:.0f} s budget), "
-              f"images/s = (calls done / {total_calls(a)}) / seconds; early calls carry the most CG iterations, so this "
-              f"is a lower bound on the CPU's whole-image rate")
+    sample = f"per step ~{per_step:.0f} s of oracle/fh_oracle.py (float64 CG, complex128 state) on {cores} threads: {samples[0]}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/c128",
@@ -204,20 +216,18 @@ def run_reference_arm(a, assets):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def algorithmic_bytes(kernel, k_rows, B, n_y=None):
-    """Algorithmic bytes per launch of the library's kernels (DESIGN.md "Kernels"): every operand touched once.
-    k_rows = rows of Z (2 per BFGS pair); unit = one float32 image vector."""
+def algorithmic_bytes_per_launch(kernel, m_rows, B):
+    """Algorithmic bytes of ONE launch of a fused CG kernel at Z rank m_rows (DESIGN.md "Kernels"): every operand
+    touched once, unit = one float32 image vector (786 432 B) per image."""
     u = D_VEC_BYTES * B
     table = {
-        "fh_k_dots": (2 + k_rows) * u,                 # v, delta, Z rows
-        "fh_k_lowrank_apply": (3 + k_rows) * u,        # v, delta, Z rows, out
-        "fh_k_dct_rows_t<false>": 2 * u, "fh_k_dct_rows_t<true>": 2 * u,
-        "fh_k_conv_sep": 2 * u, "fh_k_conv_taps": 2 * u,
-        "fh_k_cg_q": 3 * u, "fh_k_cg_update1": 6 * u, "fh_k_cg_update2": 3 * u,
-        "fh_k_gram": (1 + k_rows) * u,
+        "fh_k_cg_fwd_rows<RR>": 4 * u,                 # r, p in; p, T out
+        "fh_k_cg_fwd_cols<RR>": (3 + m_rows) * u,      # T, delta, Z rows in; w_hat out
+        "fh_k_cg_inv_cols<RR>": (3 + m_rows) * u,      # w_hat, delta, Z rows in; T' out
+        "fh_k_cg_inv_rows<RR>": 3 * u,                 # T', p in; q out
+        "fh_k_cg_xr<RR>": 6 * u,                       # x, p, r, q in; x, r out
     }
     return table.get(kernel)
-
 
 def run_b200(a, assets):
     import torch
@@ -236,18 +246,16 @@ def run_b200(a, assets):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = a.batch
     var = assets["dct_variance"]
     t_steps = edm_sigma_steps(a.num_steps)
-    n_iter = a.warmup + 2 * a.steps + 1            # value steps + e2e steps + one profiled step
-    # every step samples NEW images: global image index = step * world * B + rank * B + b  (weak scaling)
-    seed_of = lambda step: 1000 + (step * world + rank) * B
 
-    def make_problem(step):
-        x_clean, noise, ynoise = synth_inputs(assets, a.operator, B, seed_of(step))
+    def make_problem(step, B):
+        # every step samples NEW images: global image index = (step * world + rank) * B + b  (weak scaling)
+        seed0 = 1000 + (step * world + rank) * B
+        x_clean, noise, ynoise = synth_inputs(assets, a.operator, B, seed0)
         kw = dict(in_shape=(B, 3, 256, 256), sigma_s=0.1, device=dev)
         if a.operator == "inpainting":
-            masks = np.stack([random_mask(seed_of(step) + b) for b in range(B)])
+            masks = np.stack([random_mask(seed0 + b) for b in range(B)])
             op = get_operator("inpainting", mask=torch.from_numpy(masks)[:, None].repeat(1, 3, 1, 1), **kw)
             y = (x_clean + 0.1 * ynoise) * masks[:, None]
         else:
@@ -257,7 +265,7 @@ def run_b200(a, assets):
             y = xa + 0.1 * ynoise[..., :256 // sf, :256 // sf]
         return op, y.astype(np.float32), noise.astype(np.float32)
 
-    def make_mechanism(op, timer=None):
+    def make_mechanism(op, B, timer=None):
         return choose_conditioning_mechanism("free_hunch")(
             1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(float(t_steps[0]) ** 2, dtype=torch.float64),
             data_dim=3 * 256 * 256, max_vector_count=100000, dct_variance=var, image_base_covariance="dct_diagonal",
@@ -265,14 +273,15 @@ def run_b200(a, assets):
             space_step_update_threshold=10.0, space_step_update_lower_threshold=1.0, max_rtol=1.0, do_space_updates=True,
             use_analytic_var_at_end=False, solver_type="customcuda", use_rtol_func=True, device=dev, batch=B, timer=timer)
 
-    problems = [make_problem(s) for s in range(n_iter)]
-    ctx = problems[0][0].ctx
-    net = AnalyticDCTGaussianDenoiser(var, ctx)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 256 MiB > 126 MB L2
+    nets = {}
 
     def sample(op, y_dev, noise_dev, timer=None):
-        mech = make_mechanism(op, timer)
-        x = conditional_sampler(mech, net, y_dev, noise_dev, t_steps, solver=a.solver)
+        B = y_dev.shape[0]
+        mech = make_mechanism(op, B, timer)
+        ctx = mech.covariance_model.ctx
+        if id(ctx) not in nets:
+            nets[id(ctx)] = AnalyticDCTGaussianDenoiser(var, ctx)
+        x = conditional_sampler(mech, nets[id(ctx)], y_dev, noise_dev, t_steps, solver=a.solver)
         return x, mech
 
     def barrier():
@@ -287,6 +296,10 @@ def run_b200(a, assets):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    B = a.batch
+    n_iter = a.warmup + 2 * a.steps + 1            # warm-up, device-resident steps, end-to-end steps, one profiled step
+    problems = [make_problem(s, B) for s in range(n_iter)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 256 MiB > 126 MB L2
     it = 0
     for _ in range(a.warmup):
         op, y, noise = problems[it]; it += 1
@@ -314,7 +327,6 @@ def run_b200(a, assets):
         assert bool(torch.isfinite(x).all()), "non-finite sample"
     barrier()
     launches = E.launch_count()
-    clk = clocks.stop() if rank == 0 else None
     total_ms = reduce_max(float(sum(ms_steps)))
     value = world * B * a.steps / (total_ms * 1e-3)
     # ---- end-to-end arm: pinned host buffers in, host image out, wall clock of the user-facing call
@@ -331,10 +343,11 @@ def run_b200(a, assets):
         torch.cuda.synchronize()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     e2e_total = reduce_max(float(sum(e2e_ms)))
+    clk = clocks.stop() if rank == 0 else None
     e2e_value = world * B * a.steps / (e2e_total * 1e-3)
     h2d = int(problems[0][1].nbytes + problems[0][2].nbytes)
     d2h = int(B * 3 * 256 * 256 * 8)
-    # ---- one profiled step: phase timers + per-kernel CUDA-event timing inside the library
+    # ---- one profiled step: phase timers + an event pair around every kernel launch (shares, not absolutes)
     op, y, noise = problems[it]; it += 1
     timer = PhaseTimer(True)
     E.profile_kernels(True)
@@ -355,28 +368,45 @@ def run_b200(a, assets):
     n_cg = sum(max(r["niter"]) for r in mech.log)
     hot_ms = sum(phases.get(p, (0, 0.0))[1] for p in ("time_update", "space_update", "mat_solver"))
     kern_total = sum(ms for _, ms in kprof.values())
-    top = max(kprof.items(), key=lambda kv: kv[1][1])
-    top_name, (top_n, top_ms) = top
-    # algorithmic bytes of the dominant kernel: Z rows grow during the run, so weight by the live rank per call
-    k_mean = float(np.mean([2 * r["k"] for r in mech.log for _ in range(max(1, max(r["niter"])))]))
-    ab = algorithmic_bytes(top_name, k_mean, B)
+    cg_names = [k for k in kprof if k.split("<")[0] in E.CG_KERNELS]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (ab / (top_ms / top_n * 1e-3) / 1e9) if ab else None
-    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "launches": top_n, "avg_us": top_ms / top_n * 1e3, "share_of_kernel_time": top_ms / kern_total,
-                "algorithmic_bytes_per_launch": ab, "mean_Z_rows": k_mean}
+
+    def kernel_roofline(state, op_handle, Bk):
+        """Dominant fused-CG kernel at the state's final rank: back-to-back launches between two CUDA events."""
+        m_rows = state.rank
+        times = {n: E.cg_kernel_time(state, op_handle, i, reps=200) for i, n in enumerate(E.CG_KERNELS)}
+        top = max(times, key=times.get)
+        ab = algorithmic_bytes_per_launch(top + "<RR>", m_rows, Bk)
+        ach = ab / (times[top] * 1e-3) / 1e9
+        return top, times, ab, ach, m_rows
+
+    roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+    fold = a.operator in ("gaussian_blur", "inpainting")
+    if fold:
+        top, times, ab, ach, m_rows = kernel_roofline(mech.covariance_model.state, mech.forward_operator.op, B)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))["kernels"][top]["dram_bytes_per_launch"]
+        except (OSError, KeyError):
+            pass
+        share = sum(kprof[k][1] for k in cg_names if k.startswith(top)) / kern_total
+        roofline.update({"kernel": top, "achieved": ach, "frac": ach / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                         "avg_us": times[top] * 1e3, "algorithmic_bytes_per_launch": ab, "Z_rows": m_rows,
+                         "all_kernels_us": {k: round(v * 1e3, 2) for k, v in times.items()},
+                         "share_of_kernel_time_in_step": share,
+                         "note": f"micro-batch {B}: " + ("the working set (<= 36 MB) is L2-resident, so the kernel is bound by "
+                                 "L2 / SM latency rather than HBM; `batched` has the HBM-bound regime" if B < 4 else "HBM-bound regime")})
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 reductions and k x k algebra)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (PyTorch + library DCT)",
+        "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (PyTorch + library DCT); the UNet is outside the hot path",
                    "l2": "256 MiB flush between steps; every step samples new images", "mechanism_calls": n_calls,
                    "cg_iterations_per_image": float(np.mean(cg_iters)), "final_bfgs_pairs": ranks_k[-1]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -384,18 +414,37 @@ def run_b200(a, assets):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
-        "hot_path": {"ms_per_image_step": prof_ms / B, "cov_plus_cg_ms_per_mechanism_call": hot_ms / n_calls,
+        "hot_path": {"profiled_step_ms": prof_ms, "cov_plus_cg_ms_per_mechanism_call": hot_ms / n_calls,
                      "cov_plus_cg_us_per_cg_iteration": hot_ms / max(1, n_cg) * 1e3, "cg_iterations": n_cg,
                      "phases_ms": {k: round(v[1], 3) for k, v in phases.items()},
-                     "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(kprof.items(), key=lambda kv: -kv[1][1])}},
+                     "kernels_ms_event_pairs": {k: [v[0], round(v[1], 3)] for k, v in sorted(kprof.items(), key=lambda kv: -kv[1][1])}},
     }
+    # ---- the HBM-bound regime: B independent images per GPU (one warm-up step, one timed step)
+    if fold and a.batched > 1 and B == 1 and world == 1:
+        Bb = a.batched
+        res = []
+        for stp in range(2):
+            opb, yb, nb = make_problem(100 + stp, Bb)
+            yd, nd = torch.from_numpy(yb).to(dev), torch.from_numpy(nb).to(dev)
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            xb, mechb = sample(opb, yd, nd)
+            e1.record(); e1.synchronize()
+            res.append(e0.elapsed_time(e1))
+        top, times, ab, ach, m_rows = kernel_roofline(mechb.covariance_model.state, mechb.forward_operator.op, Bb)
+        out["batched"] = {"micro_batch": Bb, "images_per_s": Bb / (res[-1] * 1e-3), "ms_per_step": res[-1],
+                          "cg_iterations_max_over_batch": sum(max(r["niter"]) for r in mechb.log),
+                          "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                       "avg_us": times[top] * 1e3, "algorithmic_bytes_per_launch": ab, "Z_rows": m_rows,
+                                       "all_kernels_us": {k: round(v * 1e3, 2) for k, v in times.items()}}}
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         calls, complete, secs = cpu_reference_sample(assets, a, a.cpu_seconds, cores)
-        v = (len(calls) / total_calls(a)) / secs
+        v, how = cpu_images_per_s(a, calls, secs)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"oracle/fh_oracle.py (float64 CG, complex128 state), first {len(calls)} of "
-                                         f"{total_calls(a)} mechanism calls of one image in {secs:.1f} s, scaled by call count"}
+                               "sample": f"oracle/fh_oracle.py (float64 CG, complex128 state) for {secs:.1f} s: {how}"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -907,3 +907,54 @@ extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* m
   }
   return fh_op_apply(o, x, mat_out, B, 1, stream);
 }
+
+// bench.py's roofline: `reps` back-to-back launches of ONE kernel of the fused iteration at the state's current
+// rank, timed with CUDA events on `stream` (inputs are whatever the workspace holds; sizes and access pattern are
+// those of a real iteration).  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols, 3 inv_rows, 4 xr.
+extern "C" int fh_cg_kernel_time(fh_state* s, fh_op* o, int which, int reps, float* ms_out, void* stream) {
+#ifdef FH_EMU
+  (void)s; (void)o; (void)which; (void)reps; (void)ms_out; (void)stream;
+  FH_FAIL(FH_EINVAL, "not available in the emulation build");
+#else
+  if (!s || !o || !ms_out || reps < 1 || which < 0 || which > 4) FH_FAIL(FH_EINVAL, "bad fh_cg_kernel_time arguments");
+  if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_EINVAL, "fused kernels need the DCT basis");
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = pick_rows(c, s->B * c->C);
+  FhCgFused P = fused_params(s, o, R);
+  if (P.fuse == 0) FH_FAIL(FH_EINVAL, "operator does not fold into the DCT passes");
+  P.sc = c->cg_sc; P.sy2 = 0.01f; P.last_allowed = 1 << 30;
+  // scalars that keep every kernel on its normal path: not done, no stop test, finite alpha / beta
+  std::vector<FhCgScalars> sc(s->B);
+  for (auto& v : sc) { memset(&v, 0, sizeof(v)); v.rr[0] = v.rr[1] = 1.0; v.stop2 = -1.0; }
+  FH_CUDA(cudaMemcpyAsync(c->cg_sc, sc.data(), sc.size() * sizeof(FhCgScalars), cudaMemcpyHostToDevice, st));
+  std::vector<double> ones((size_t)s->B * P.ystrips, 1.0);
+  FH_CUDA(cudaMemcpyAsync(c->part_a, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  FH_CUDA(cudaMemcpyAsync(c->part_b, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  FH_CUDA(cudaStreamSynchronize(st));
+  const dim3 block(FH_PASS_THREADS), gimg = strip_grid(c, s->B * P.strips_per_image);
+  const size_t zbytes = (size_t)P.zstages * FH_ZROUND_FLOATS * 4;
+  cudaEvent_t e0, e1;
+  FH_CUDA(cudaEventCreate(&e0)); FH_CUDA(cudaEventCreate(&e1));
+  for (int pass = 0; pass < 2; ++pass) {                 // pass 0 warms up
+    if (pass) FH_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < (pass ? reps : 3); ++i) {
+      FH_ROWS_SWITCH(R, {
+        if (which == 0) FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, (const float*)nullptr, 2);
+        else if (which == 1) FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        else if (which == 2) FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        else if (which == 3) FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, (const float*)nullptr, 2);
+        else FH_LAUNCH(fh_k_cg_xr<RR>, gimg, block, 0, stream, P, 2);
+      });
+    }
+    if (pass) FH_CUDA(cudaEventRecord(e1, st));
+  }
+  FH_KCHECK();
+  FH_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  FH_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_out = ms / reps;
+  return FH_OK;
+#endif
+}

@@ -238,3 +238,14 @@ def kernel_profile():
         name, cnt, ms = line.split()
         out[name] = (int(cnt), float(ms))
     return out
+
+
+CG_KERNELS = ("fh_k_cg_fwd_rows", "fh_k_cg_fwd_cols", "fh_k_cg_inv_cols", "fh_k_cg_inv_rows", "fh_k_cg_xr")
+
+
+def cg_kernel_time(state, op, which, reps=200):
+    """Average device time in ms of one launch of kernel `which` (index into CG_KERNELS) of the fused CG iteration at
+    the state's current rank: `reps` back-to-back launches between two CUDA events (bench.py's roofline)."""
+    ms = ctypes.c_float()
+    _lib.check(_lib.lib().fh_cg_kernel_time(state._h, op._h, int(which), int(reps), ctypes.byref(ms), state.ctx.stream()))
+    return float(ms.value)

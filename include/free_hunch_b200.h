@@ -108,6 +108,10 @@ int fh_op_apply(fh_op* op, const float* in_dev, float* out_dev, int batch, int t
 int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                 int maxiter, int fixed_iters, float* mat_out_dev, int* niter_host, int* optimal_host,
                 double* resid_host, void* stream);
+/* bench.py's roofline: average device time (ms) of `reps` back-to-back launches of ONE kernel of the fused CG
+ * iteration at the state's current rank, CUDA events on `stream`.  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols,
+ * 3 inv_rows, 4 xr.  Only for operators that fold into the DCT passes (inpainting, separable blur). */
+int fh_cg_kernel_time(fh_state* st, fh_op* op, int which, int reps, float* ms_out, void* stream);
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 long long fh_launch_count(int reset);
 /* Per-kernel device timing for bench.py: while enabled every launch is bracketed by a cudaEvent pair on its
