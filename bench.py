@@ -434,10 +434,15 @@ def run_b200(a, assets):
             e1.record(); e1.synchronize()
             res.append(e0.elapsed_time(e1))
         top, times, ab, ach, m_rows = kernel_roofline(mechb.covariance_model.state, mechb.forward_operator.op, Bb)
+        traffic_b = None
+        try:
+            traffic_b = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_batch16.json")))["kernels"][top]["dram_bytes_per_launch"] if Bb == 16 else None
+        except (OSError, KeyError):
+            pass
         out["batched"] = {"micro_batch": Bb, "images_per_s": Bb / (res[-1] * 1e-3), "ms_per_step": res[-1],
                           "cg_iterations_max_over_batch": sum(max(r["niter"]) for r in mechb.log),
                           "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                       "avg_us": times[top] * 1e3, "algorithmic_bytes_per_launch": ab, "Z_rows": m_rows,
+                                       "traffic": traffic_b, "avg_us": times[top] * 1e3, "algorithmic_bytes_per_launch": ab, "Z_rows": m_rows,
                                        "all_kernels_us": {k: round(v * 1e3, 2) for k, v in times.items()}}}
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1

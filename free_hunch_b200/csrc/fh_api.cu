@@ -134,6 +134,7 @@ struct fh_op {
   bool separable;
   int* t_dy; int* t_dx; float* t_w; int nt, ymin, ymax, xmin, xmax;
   float *kr, *kc; int nr, nc, cr, cc;
+  float* psf_dense; int ks;           // dense PSF on the device (fast x4 super-resolution kernels)
 };
 
 static inline dim3 ew_grid(long d, int B) { return dim3((unsigned)fh_nchunks(d), (unsigned)B, 1); }
@@ -638,6 +639,9 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
       }
     }
   if (w.empty()) { free(o); FH_FAIL(FH_EINVAL, "PSF is all zeros"); }
+  o->ks = ks;
+  FH_CUDA(cudaMalloc((void**)&o->psf_dense, (size_t)ks * ks * sizeof(float)));
+  FH_CUDA(cudaMemcpy(o->psf_dense, psf, (size_t)ks * ks * sizeof(float), cudaMemcpyHostToDevice));
   if (ymax - ymin >= c->H || xmax - xmin >= c->W) { free(o); FH_FAIL(FH_EINVAL, "PSF support larger than the image"); }
   o->nt = (int)w.size(); o->ymin = ymin; o->ymax = ymax; o->xmin = xmin; o->xmax = xmax;
   FH_CUDA(cudaMalloc((void**)&o->t_dy, w.size() * sizeof(int)));
@@ -679,7 +683,7 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
 
 extern "C" int fh_op_destroy(fh_op* o) {
   if (!o) return FH_OK;
-  cudaFree(o->t_dy); cudaFree(o->t_dx); cudaFree(o->t_w); cudaFree(o->kr); cudaFree(o->kc);
+  cudaFree(o->t_dy); cudaFree(o->t_dx); cudaFree(o->t_w); cudaFree(o->kr); cudaFree(o->kc); cudaFree(o->psf_dense);
   free(o);
   return FH_OK;
 }
@@ -711,14 +715,20 @@ extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int
       FH_LAUNCH(fh_k_conv_taps, grid, block, smem, stream, in, out, t, c->H, c->W, transpose);
     }
   } else {
-    FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
-    const size_t smem = (size_t)o->nt * 3 * sizeof(float);
-    if (!transpose) {
-      const int n = (c->H / o->sf) * (c->W / o->sf);
-      FH_LAUNCH(fh_k_sr_forward, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+    const bool fast = c->H == 256 && c->W == 256 && o->sf == 4 && o->ks <= FH_SR_KS && ((o->ks / 2) & 3) == 0;
+    if (fast) {
+      if (!transpose) FH_LAUNCH(fh_k_sr4_forward, dim3(16, planes), dim3(256), 0, stream, in, out, (const float*)o->psf_dense, o->ks);
+      else FH_LAUNCH(fh_k_sr4_transpose, dim3(16, planes), dim3(256), 0, stream, in, out, (const float*)o->psf_dense, o->ks);
     } else {
-      const int n = c->H * c->W;
-      FH_LAUNCH(fh_k_sr_transpose, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+      FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
+      const size_t smem = (size_t)o->nt * 3 * sizeof(float);
+      if (!transpose) {
+        const int n = (c->H / o->sf) * (c->W / o->sf);
+        FH_LAUNCH(fh_k_sr_forward, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+      } else {
+        const int n = c->H * c->W;
+        FH_LAUNCH(fh_k_sr_transpose, dim3((n + 255) / 256, planes), dim3(256), smem, stream, in, out, t, c->H, c->W, o->sf);
+      }
     }
   }
   FH_KCHECK();

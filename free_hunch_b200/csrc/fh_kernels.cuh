@@ -830,3 +830,82 @@ fh_k_cg_update2(const float* __restrict__ r, float* __restrict__ p, const double
     if (i < n) p[b * n + i] = fmaf(beta, p[b * n + i], r[b * n + i]);
   }
 }
+
+// ---- x4 super-resolution, fast path: 256x256 planes, sf = 4, dense ks x ks PSF with ks <= 25, centre c = ks/2 = 12 ----
+// (utils_sisr.py:44-61 + the FFT operator of conditioning_mechanisms.py:641-675 evaluated in pixel space)
+#define FH_SR_KS 25
+// forward: y[I][J] = sum_{a,b} k[a][b] x[(4I - a + 12) & 255][(4J - b + 12) & 255].  One CTA = 4 output rows of a plane:
+// the 37 image rows it needs are staged in shared memory de-interleaved by column phase (col = 4q + ph) so that the 64
+// threads of an output row read consecutive words.  grid = (16, planes), block 256.
+__global__ void __launch_bounds__(256)
+fh_k_sr4_forward(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ psf, int ks) {
+  __shared__ float xs[37][4][65];
+  __shared__ float sk[FH_SR_KS * FH_SR_KS];
+  const int tid = threadIdx.x;
+  const size_t plane = blockIdx.y;
+  const int I0 = blockIdx.x * 4;
+  const int c = ks / 2;
+  for (int i = tid; i < FH_SR_KS * FH_SR_KS; i += 256) {
+    const int a = i / FH_SR_KS, b = i % FH_SR_KS;
+    sk[i] = (a < ks && b < ks) ? psf[a * ks + b] : 0.f;
+  }
+  const float* src = in + plane * 65536;
+  const int nrows = 4 * 3 + 2 * c + 1;                     // rows 4 I0 - c ... 4 (I0 + 3) + c
+  for (int idx = tid; idx < nrows * 64; idx += 256) {
+    const int r = idx >> 6, q4 = idx & 63;
+    const int gi = (4 * I0 - c + r) & 255;
+    const float4 v = *reinterpret_cast<const float4*>(src + gi * 256 + 4 * q4);
+    xs[r][0][q4] = v.x; xs[r][1][q4] = v.y; xs[r][2][q4] = v.z; xs[r][3][q4] = v.w;
+  }
+  __syncthreads();
+  const int Il = tid >> 6, J = tid & 63;
+  float acc = 0.f;
+  for (int a = 0; a < ks; ++a) {
+    const int r = 4 * Il + 2 * c - a;                      // image row 4 (I0 + Il) - a + c
+    for (int b = 0; b < ks; ++b) {
+      const int col = 4 * J - b + c;                       // may be negative or >= 256: wrap
+      const int ph = col & 3, q = (col >> 2) & 63;
+      acc = fmaf(sk[a * FH_SR_KS + b], xs[r][ph][q], acc);
+    }
+  }
+  out[plane * 4096 + (size_t)(I0 + Il) * 64 + J] = acc;
+}
+// transpose: x[i][j] = sum over the taps with (i + a - 12) % 4 == 0 and (j + b - 12) % 4 == 0 of
+// k[a][b] y[((i + a - 12) & 255) / 4][((j + b - 12) & 255) / 4].  One CTA = 16 image rows of a plane; thread = one column.
+// grid = (16, planes), block 256.
+__global__ void __launch_bounds__(256)
+fh_k_sr4_transpose(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ psf, int ks) {
+  __shared__ float ys[12][64];
+  __shared__ float sk[FH_SR_KS * FH_SR_KS];
+  const int tid = threadIdx.x;
+  const size_t plane = blockIdx.y;
+  const int i0 = blockIdx.x * 16;
+  const int c = ks / 2;                                    // multiple of 4 (checked by the host)
+  for (int i = tid; i < FH_SR_KS * FH_SR_KS; i += 256) {
+    const int a = i / FH_SR_KS, b = i % FH_SR_KS;
+    sk[i] = (a < ks && b < ks) ? psf[a * ks + b] : 0.f;
+  }
+  const float* src = in + plane * 4096;
+  const int Ilo = (i0 - c) >> 2;                           // floor; y rows Ilo ... Ilo + 11 cover rows i0-c ... i0+15+c
+  for (int idx = tid; idx < 12 * 64; idx += 256) {
+    const int r = idx >> 6, q = idx & 63;
+    ys[r][q] = src[((Ilo + r) & 63) * 64 + q];
+  }
+  __syncthreads();
+  const int j = tid;
+  const int b0 = (4 - (j & 3)) & 3;                        // first tap column with (j + b - c) % 4 == 0
+  float* dst = out + plane * 65536;
+  for (int il = 0; il < 16; ++il) {
+    const int i = i0 + il;
+    const int a0 = (4 - (i & 3)) & 3;
+    float acc = 0.f;
+    for (int a = a0; a < ks; a += 4) {
+      const int r = ((i + a - c) >> 2) - Ilo;              // 0 ... 11
+      for (int b = b0; b < ks; b += 4) {
+        const int q = ((j + b - c) >> 2) & 63;
+        acc = fmaf(sk[a * FH_SR_KS + b], ys[r][q], acc);
+      }
+    }
+    dst[(size_t)i * 256 + j] = acc;
+  }
+}
