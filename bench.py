@@ -12,11 +12,18 @@ Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; 
 buffers (pinned y / noise -> device, final image -> host inside the timed region); `roofline` = the dominant
 kernel's algorithmic bytes / CUDA-event time; `cpu_baseline` = oracle/fh_oracle.py on a bounded sample.
 """
+import os
+import sys
+
+# The CPU legs use every host core: torchrun exports OMP_NUM_THREADS=1 for its children, which would silently time the
+# reference on one BLAS thread.  Must happen before numpy / scipy load their thread pools.
+if "reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -130,9 +137,18 @@ def cpu_reference_sample(assets, a, budget_s, threads):
     """The reference algorithm (oracle/fh_oracle.py: float64 CG, complex128 covariance state -- the reference's own
     precision) on the host cores for a BOUNDED prefix of the same workload: mechanism calls of image 0 are run until
     `budget_s` seconds are spent.  Returns per-call records so the caller can scale to images/s."""
+    import contextlib
+    import scipy.fft as sfft
     import torch
     from oracle import fh_oracle as fo
     torch.set_num_threads(threads)
+    pools = contextlib.ExitStack()
+    pools.enter_context(sfft.set_workers(threads))                 # scipy.fft (DCTs, OTF products) is 1 worker by default
+    try:
+        from threadpoolctl import threadpool_limits
+        pools.enter_context(threadpool_limits(limits=threads))     # BLAS pools, whatever OMP_NUM_THREADS said at import
+    except ImportError:
+        pass
     var = assets["dct_variance"]
     x_clean, noise, ynoise = synth_inputs(assets, a.operator, 1, 1000)
     if a.operator == "inpainting":
@@ -167,6 +183,8 @@ def cpu_reference_sample(assets, a, budget_s, threads):
         complete = True
     except Budget:
         complete = False
+    finally:
+        pools.close()
     return calls, complete, time.perf_counter() - t_begin
 
 

@@ -560,9 +560,12 @@ fh_k_mask_mul(const float* __restrict__ in, const float* __restrict__ mask, int 
 // 32x32 output tile per CTA with a halo staged in shared memory.  grid = (W/32, H/32, B*C), block (32,8).
 struct FhTaps { const int* dy; const int* dx; const float* w; int n; int ymin, ymax, xmin, xmax; };
 
+#define FH_CONV_MAX_TAPS 1024
 __global__ void __launch_bounds__(256)
 fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps taps, int H, int W, int transpose) {
   FH_DYN_SMEM(float, sm);
+  __shared__ int s_off[FH_CONV_MAX_TAPS];                  // tap offset inside the staged tile
+  __shared__ float s_w[FH_CONV_MAX_TAPS];
   // halo extents in "input offset" space: offsets o = -dy (fwd) or +dy (transpose)
   const int oy0 = transpose ? taps.ymin : -taps.ymax, oy1 = transpose ? taps.ymax : -taps.ymin;
   const int ox0 = transpose ? taps.xmin : -taps.xmax, ox1 = transpose ? taps.xmax : -taps.xmin;
@@ -572,6 +575,14 @@ fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps tap
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const size_t plane = (size_t)blockIdx.z * H * W;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const bool staged = taps.n <= FH_CONV_MAX_TAPS;
+  if (staged)
+    for (int t = tid; t < taps.n; t += 256) {
+      const int oy = transpose ? taps.dy[t] : -taps.dy[t];
+      const int ox = transpose ? taps.dx[t] : -taps.dx[t];
+      s_off[t] = (oy - oy0) * tws + (ox - ox0);
+      s_w[t] = taps.w[t];
+    }
   for (int idx = tid; idx < th * tw; idx += 256) {
     const int r = idx / tw, c = idx % tw;
     int gi = (i0 + oy0 + r) % H; if (gi < 0) gi += H;
@@ -580,15 +591,23 @@ fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps tap
   }
   __syncthreads();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t = 0; t < taps.n; ++t) {
-    const int oy = transpose ? taps.dy[t] : -taps.dy[t];
-    const int ox = transpose ? taps.dx[t] : -taps.dx[t];
-    const float wv = taps.w[t];
-    const int c = threadIdx.x + ox - ox0;
+  const float* base = tile + threadIdx.y * tws + threadIdx.x;
+  if (staged) {
+#pragma unroll 4
+    for (int t = 0; t < taps.n; ++t) {
+      const float wv = s_w[t];
+      const float* p = base + s_off[t];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = threadIdx.y + 8 * q + oy - oy0;
-      acc[q] = fmaf(wv, tile[r * tws + c], acc[q]);
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(wv, p[8 * q * tws], acc[q]);
+    }
+  } else {
+    for (int t = 0; t < taps.n; ++t) {
+      const int oy = transpose ? taps.dy[t] : -taps.dy[t];
+      const int ox = transpose ? taps.dx[t] : -taps.dx[t];
+      const float wv = taps.w[t];
+      const float* p = base + (oy - oy0) * tws + (ox - ox0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(wv, p[8 * q * tws], acc[q]);
     }
   }
 #pragma unroll
