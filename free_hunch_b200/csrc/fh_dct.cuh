@@ -24,14 +24,16 @@ struct FhDctTables {
 };
 
 #define FH_RS 264             // shared-memory row stride in floats (16-B aligned rows)
+#define FH_PAD(i) ((i) + (((i) >> 4) << 2))      // 4 float2 of padding after every 16: stage writes 16g+k land on 20g+k
+#define FH_FFT_LD 320
 #define FH_PASS_THREADS 256
 
 template <int ROWS>
 struct FhStripSmem {
   float a[ROWS * FH_RS];
   float b[ROWS * FH_RS];
-  float2 X[ROWS / 2][FH_N];
-  float2 Y[ROWS / 2][FH_N];
+  float2 X[ROWS / 2][FH_FFT_LD];      // FFT ping-pong buffers, padded (FH_PAD) so that every Stockham stage's
+  float2 Y[ROWS / 2][FH_FFT_LD];      // strided writes fall on distinct banks
   float2 tw[FH_N];
   float2 tab[FH_N];
 };
@@ -72,7 +74,7 @@ __device__ __forceinline__ void fh_strip_tables(FhStripSmem<ROWS>& sm, const FhD
 template <int SIGN, int NS>
 __device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, float2* __restrict__ out, int j, const float2* __restrict__ tw) {
   const int k = j & (NS - 1);
-  float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
+  float2 v0 = in[FH_PAD(j)], v1 = in[FH_PAD(j + 64)], v2 = in[FH_PAD(j + 128)], v3 = in[FH_PAD(j + 192)];
   if (NS > 1) {
     const int t = k * (64 / NS);                       // angle = SIGN * 2 pi k r / (4 Ns)
     v1 = fh_cmul(v1, tw[t]);
@@ -81,7 +83,7 @@ __device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, f
   }
   fh_dft4<SIGN>(v0, v1, v2, v3);
   const int j0 = ((j - k) << 2) + k;
-  out[j0] = v0; out[j0 + NS] = v1; out[j0 + 2 * NS] = v2; out[j0 + 3 * NS] = v3;
+  out[FH_PAD(j0)] = v0; out[FH_PAD(j0 + NS)] = v1; out[FH_PAD(j0 + 2 * NS)] = v2; out[FH_PAD(j0 + 3 * NS)] = v3;
 }
 
 // Transform the ROWS rows in `in` (shared, stride FH_RS) into `out` (shared, stride FH_RS; must not alias `in`).
@@ -124,7 +126,9 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
       }
     }
     fh_dft4<SIGN>(v[0], v[1], v[2], v[3]);             // stage Ns = 1 (no twiddles): out[4 j + r]
-    Y[4 * j] = v[0]; Y[4 * j + 1] = v[1]; Y[4 * j + 2] = v[2]; Y[4 * j + 3] = v[3];
+    float4* y4 = reinterpret_cast<float4*>(Y + FH_PAD(4 * j));      // 4 consecutive outputs stay inside one 16-block
+    y4[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    y4[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
   }
   __syncthreads();
   if (act) fh_fft256_stage<SIGN, 4>(Y, X, j, sm.tw);
@@ -138,8 +142,8 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int k = j + 64 * r;
-        const float2 zk = X[k];
-        const float2 zn = X[(FH_N - k) & (FH_N - 1)];
+        const float2 zk = X[FH_PAD(k)];
+        const float2 zn = X[FH_PAD((FH_N - k) & (FH_N - 1))];
         const float2 va = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         const float2 vb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
         const float2 p = sm.tab[k];
@@ -151,7 +155,7 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
       for (int r = 0; r < 4; ++r) {
         const int n = j + 64 * r;
         const int pos = (n < 128) ? 2 * n : 511 - 2 * n;
-        const float2 z = X[n];
+        const float2 z = X[FH_PAD(n)];
         oa[pos] = z.x;
         ob[pos] = z.y;
       }

@@ -564,8 +564,7 @@ struct FhTaps { const int* dy; const int* dx; const float* w; int n; int ymin, y
 __global__ void __launch_bounds__(256)
 fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps taps, int H, int W, int transpose) {
   FH_DYN_SMEM(float, sm);
-  __shared__ int s_off[FH_CONV_MAX_TAPS];                  // tap offset inside the staged tile
-  __shared__ float s_w[FH_CONV_MAX_TAPS];
+  __shared__ float2 s_tap[FH_CONV_MAX_TAPS];               // (tap offset inside the staged tile as int bits, weight)
   // halo extents in "input offset" space: offsets o = -dy (fwd) or +dy (transpose)
   const int oy0 = transpose ? taps.ymin : -taps.ymax, oy1 = transpose ? taps.ymax : -taps.ymin;
   const int ox0 = transpose ? taps.xmin : -taps.xmax, ox1 = transpose ? taps.xmax : -taps.xmin;
@@ -580,14 +579,18 @@ fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps tap
     for (int t = tid; t < taps.n; t += 256) {
       const int oy = transpose ? taps.dy[t] : -taps.dy[t];
       const int ox = transpose ? taps.dx[t] : -taps.dx[t];
-      s_off[t] = (oy - oy0) * tws + (ox - ox0);
-      s_w[t] = taps.w[t];
+      s_tap[t] = make_float2(__int_as_float((oy - oy0) * tws + (ox - ox0)), taps.w[t]);
     }
-  for (int idx = tid; idx < th * tw; idx += 256) {
-    const int r = idx / tw, c = idx % tw;
-    int gi = (i0 + oy0 + r) % H; if (gi < 0) gi += H;
-    int gj = (j0 + ox0 + c) % W; if (gj < 0) gj += W;
-    tile[r * tws + c] = in[plane + (size_t)gi * W + gj];
+  const bool pow2 = ((H & (H - 1)) | (W & (W - 1))) == 0;
+  for (int r = threadIdx.y; r < th; r += 8) {               // one warp per tile row: no per-element division
+    int gi = i0 + oy0 + r;
+    if (pow2) gi &= H - 1; else { gi %= H; if (gi < 0) gi += H; }
+    const float* srow = in + plane + (size_t)gi * W;
+    for (int c = threadIdx.x; c < tw; c += 32) {
+      int gj = j0 + ox0 + c;
+      if (pow2) gj &= W - 1; else { gj %= W; if (gj < 0) gj += W; }
+      tile[r * tws + c] = srow[gj];
+    }
   }
   __syncthreads();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -595,8 +598,9 @@ fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps tap
   if (staged) {
 #pragma unroll 4
     for (int t = 0; t < taps.n; ++t) {
-      const float wv = s_w[t];
-      const float* p = base + s_off[t];
+      const float2 tp = s_tap[t];
+      const float wv = tp.y;
+      const float* p = base + __float_as_int(tp.x);
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q] = fmaf(wv, p[8 * q * tws], acc[q]);
     }
@@ -858,7 +862,7 @@ fh_k_cg_update2(const float* __restrict__ r, float* __restrict__ p, const double
 // threads of an output row read consecutive words.  grid = (16, planes), block 256.
 __global__ void __launch_bounds__(256)
 fh_k_sr4_forward(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ psf, int ks) {
-  __shared__ float xs[37][4][65];
+  __shared__ float xs[37][4 * 65];
   __shared__ float sk[FH_SR_KS * FH_SR_KS];
   const int tid = threadIdx.x;
   const size_t plane = blockIdx.y;
@@ -866,7 +870,7 @@ fh_k_sr4_forward(const float* __restrict__ in, float* __restrict__ out, const fl
   const int c = ks / 2;
   for (int i = tid; i < FH_SR_KS * FH_SR_KS; i += 256) {
     const int a = i / FH_SR_KS, b = i % FH_SR_KS;
-    sk[i] = (a < ks && b < ks) ? psf[a * ks + b] : 0.f;
+    sk[i] = (a < ks && b < ks) ? psf[a * ks + b] : 0.f;    // zero-padded to 25 x 25: the tap loops below are fixed-size
   }
   const float* src = in + plane * 65536;
   const int nrows = 4 * 3 + 2 * c + 1;                     // rows 4 I0 - c ... 4 (I0 + 3) + c
@@ -874,18 +878,23 @@ fh_k_sr4_forward(const float* __restrict__ in, float* __restrict__ out, const fl
     const int r = idx >> 6, q4 = idx & 63;
     const int gi = (4 * I0 - c + r) & 255;
     const float4 v = *reinterpret_cast<const float4*>(src + gi * 256 + 4 * q4);
-    xs[r][0][q4] = v.x; xs[r][1][q4] = v.y; xs[r][2][q4] = v.z; xs[r][3][q4] = v.w;
+    xs[r][q4] = v.x; xs[r][65 + q4] = v.y; xs[r][130 + q4] = v.z; xs[r][195 + q4] = v.w;
   }
   __syncthreads();
   const int Il = tid >> 6, J = tid & 63;
+  // column offsets of the 25 taps for this thread's J: identical for every tap row, so computed once
+  int offb[FH_SR_KS];
+#pragma unroll
+  for (int b = 0; b < FH_SR_KS; ++b) {
+    const int col = 4 * J - b + c;                         // may be negative or >= 256: wrap
+    offb[b] = (col & 3) * 65 + ((col >> 2) & 63);
+  }
   float acc = 0.f;
   for (int a = 0; a < ks; ++a) {
-    const int r = 4 * Il + 2 * c - a;                      // image row 4 (I0 + Il) - a + c
-    for (int b = 0; b < ks; ++b) {
-      const int col = 4 * J - b + c;                       // may be negative or >= 256: wrap
-      const int ph = col & 3, q = (col >> 2) & 63;
-      acc = fmaf(sk[a * FH_SR_KS + b], xs[r][ph][q], acc);
-    }
+    const float* xr = xs[4 * Il + 2 * c - a];              // image row 4 (I0 + Il) - a + c
+    const float* kr = sk + a * FH_SR_KS;
+#pragma unroll
+    for (int b = 0; b < FH_SR_KS; ++b) acc = fmaf(kr[b], xr[offb[b]], acc);
   }
   out[plane * 4096 + (size_t)(I0 + Il) * 64 + J] = acc;
 }
@@ -895,13 +904,13 @@ fh_k_sr4_forward(const float* __restrict__ in, float* __restrict__ out, const fl
 __global__ void __launch_bounds__(256)
 fh_k_sr4_transpose(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ psf, int ks) {
   __shared__ float ys[12][64];
-  __shared__ float sk[FH_SR_KS * FH_SR_KS];
+  __shared__ float sk[FH_SR_KS * (FH_SR_KS + 3)];          // rows padded to 28 so b0 + 4 t (t < 7) never leaves the row
   const int tid = threadIdx.x;
   const size_t plane = blockIdx.y;
   const int i0 = blockIdx.x * 16;
   const int c = ks / 2;                                    // multiple of 4 (checked by the host)
-  for (int i = tid; i < FH_SR_KS * FH_SR_KS; i += 256) {
-    const int a = i / FH_SR_KS, b = i % FH_SR_KS;
+  for (int i = tid; i < FH_SR_KS * (FH_SR_KS + 3); i += 256) {
+    const int a = i / (FH_SR_KS + 3), b = i % (FH_SR_KS + 3);
     sk[i] = (a < ks && b < ks) ? psf[a * ks + b] : 0.f;
   }
   const float* src = in + plane * 4096;
@@ -913,17 +922,19 @@ fh_k_sr4_transpose(const float* __restrict__ in, float* __restrict__ out, const 
   __syncthreads();
   const int j = tid;
   const int b0 = (4 - (j & 3)) & 3;                        // first tap column with (j + b - c) % 4 == 0
+  int qt[7];                                               // y columns of the 7 candidate taps: the same for every row
+#pragma unroll
+  for (int t = 0; t < 7; ++t) qt[t] = ((j + b0 + 4 * t - c) >> 2) & 63;
   float* dst = out + plane * 65536;
   for (int il = 0; il < 16; ++il) {
     const int i = i0 + il;
     const int a0 = (4 - (i & 3)) & 3;
     float acc = 0.f;
     for (int a = a0; a < ks; a += 4) {
-      const int r = ((i + a - c) >> 2) - Ilo;              // 0 ... 11
-      for (int b = b0; b < ks; b += 4) {
-        const int q = ((j + b - c) >> 2) & 63;
-        acc = fmaf(sk[a * FH_SR_KS + b], ys[r][q], acc);
-      }
+      const float* yr = ys[((i + a - c) >> 2) - Ilo];      // 0 ... 11
+      const float* kr = sk + a * (FH_SR_KS + 3) + b0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) acc = fmaf(kr[4 * t], yr[qt[t]], acc);   // taps beyond ks are zero
     }
     dst[(size_t)i * 256 + j] = acc;
   }

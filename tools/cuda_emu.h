@@ -127,6 +127,8 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d, int
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return emu::shfl_generic(v, src); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+static inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 static inline double atomicAdd(double* p, double v) { static std::mutex m; std::lock_guard<std::mutex> g(m); double o = *p; *p = o + v; return o; }
 static inline float atomicAdd(float* p, float v) { static std::mutex m; std::lock_guard<std::mutex> g(m); float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { static std::mutex m; std::lock_guard<std::mutex> g(m); int o = *p; *p = o + v; return o; }
