@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--solver", default="heun", choices=["heun", "euler"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-unet-timing", action="store_true", help="skip the separate timing of the random-init PyTorch UNet")
     ap.add_argument("--batched", type=int, default=16, help="also report a B-images-per-GPU step (HBM-bound regime); 0 = off")
     return ap.parse_args()
 
@@ -462,6 +463,39 @@ def run_b200(a, assets):
                           "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                        "traffic": traffic_b, "avg_us": times[top] * 1e3, "algorithmic_bytes_per_launch": ab, "Z_rows": m_rows,
                                        "all_kernels_us": {k: round(v * 1e3, 2) for k, v in times.items()}}}
+    # ---- the denoiser the reference would run (random-init guided-diffusion UNet, PyTorch), timed separately
+    if not a.no_unet_timing and world == 1:
+        try:
+            from free_hunch_b200.denoiser import build_denoiser
+            den = build_denoiser("imagenet256", dev)
+            xin = torch.randn(1, 3, 256, 256, dtype=torch.float64, device=dev)
+            sig = torch.tensor(5.1405, dtype=torch.float64, device=dev)
+            w = torch.randn(1, 3, 256, 256, dtype=torch.float64, device=dev)
+
+            def call():
+                xg = xin.clone().requires_grad_()
+                d, _ = den(xg, sig)
+                return torch.autograd.grad((w * d).sum(), xg)[0]
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record()
+            for _ in range(10):
+                call()
+            u1.record(); u1.synchronize()
+            unet_ms = u0.elapsed_time(u1) / 10
+            standin_ms = phases.get("denoiser", (0, 0.0))[1]
+            step_ms = total_ms / a.steps
+            out["unet"] = {"config": "imagenet256 guided-diffusion UNet, random init, fp16 autocast, batch 1 (free_hunch_b200/denoiser.py)",
+                           "params_M": sum(p.numel() for p in den.parameters()) / 1e6, "fwd_plus_vjp_ms_per_call": unet_ms,
+                           "calls_per_image": n_calls,
+                           "images_per_s_with_unet_instead_of_stand_in": 1e3 / (step_ms - standin_ms + n_calls * unet_ms),
+                           "note": "timed separately (north-star); a random-init net is not a denoiser, so it is not put inside the "
+                                   "guided loop: the CG iteration counts it would induce are arbitrary"}
+            del den
+        except Exception as e:                                   # the UNet timing is auxiliary: never fail the bench on it
+            out["unet"] = {"error": repr(e)[:200]}
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         calls, complete, secs = cpu_reference_sample(assets, a, a.cpu_seconds, cores)

@@ -339,7 +339,7 @@ static int gram(fh_state* s, int m, FhRowPtrs xr, int nx, const float* w, void* 
   const size_t smem = (size_t)(FH_GRAM_MAXR * (FH_GRAM_TILE + 1) + FH_GRAM_TILE) * sizeof(float);
   FH_LAUNCH(fh_k_gram, dim3(FH_GRAM_CTAS, s->B), dim3(256), smem, stream, s->Z, m, xr, nx, w, c->gram_partial, s->d);
   FH_KCHECK();
-  FH_LAUNCH(fh_k_gram_reduce, dim3(s->B), dim3(256), 0, stream, c->gram_partial, FH_GRAM_CTAS, m + nx, c->gramK);
+  FH_LAUNCH(fh_k_gram_reduce, dim3(s->B, FH_GRAM_RED_CTAS), dim3(256), 0, stream, c->gram_partial, FH_GRAM_CTAS, m + nx, c->gramK);
   FH_KCHECK();
   return FH_OK;
 }

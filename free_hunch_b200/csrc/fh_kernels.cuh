@@ -183,7 +183,7 @@ fh_k_lowrank_apply(const float* __restrict__ Z, int m, const double* __restrict_
 // Weighted Gram of up to FH_MAXM+4 rows:  K[i][j] = sum_c R_i[c] R_j[c] w[c]   (w null -> 1).
 // rows 0..m-1 are Z rows, rows m..m+nx-1 come from `xrows` pointers (each (B,d)).
 // grid = (FH_GRAM_CTAS, B); each CTA strides over 128-column tiles and writes one partial matrix.
-#define FH_GRAM_CTAS 64
+#define FH_GRAM_CTAS 148        // one column slab per SM (batch 1); partial matrices are summed by fh_k_gram_reduce
 #define FH_GRAM_TILE 128
 #define FH_GRAM_MAXR (FH_MAXM + 4)          // 68 rows = 17 x 4
 #define FH_GRAM_LD (FH_GRAM_MAXR)           // leading dim of the partial / result matrices
@@ -265,15 +265,23 @@ fh_k_gram(const float* __restrict__ Z, int m, FhRowPtrs xrows, int nx, const flo
   }
 }
 
-// K[b] = sum over CTAs of partial (R x R, leading dim FH_GRAM_LD).  grid = (B), block 256.
+// K[b] = sum over CTAs of partial (R x R, leading dim FH_GRAM_LD), fixed order.  grid = (B, FH_GRAM_RED_CTAS), block 256:
+// each CTA owns a slice of the matrix entries; each thread keeps 4 independent loads in flight per entry.
+#define FH_GRAM_RED_CTAS 8
 __global__ void __launch_bounds__(256)
 fh_k_gram_reduce(const double* __restrict__ partial, int nparts, int R, double* __restrict__ K) {
   const size_t b = blockIdx.x;
-  for (int idx = threadIdx.x; idx < R * R; idx += blockDim.x) {
+  const size_t mat = (size_t)(FH_GRAM_LD * FH_GRAM_LD);
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < R * R; idx += gridDim.y * blockDim.x) {
     const int i = idx / R, j = idx % R;
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partial[(b * nparts + p) * (size_t)(FH_GRAM_LD * FH_GRAM_LD) + i * FH_GRAM_LD + j];
-    K[b * (size_t)(FH_GRAM_LD * FH_GRAM_LD) + i * FH_GRAM_LD + j] = s;
+    const double* src = partial + b * nparts * mat + i * FH_GRAM_LD + j;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4) {
+      s0 += src[(size_t)p * mat]; s1 += src[(size_t)(p + 1) * mat]; s2 += src[(size_t)(p + 2) * mat]; s3 += src[(size_t)(p + 3) * mat];
+    }
+    for (; p < nparts; ++p) s0 += src[(size_t)p * mat];
+    K[b * mat + i * FH_GRAM_LD + j] = (s0 + s1) + (s2 + s3);
   }
 }
 
