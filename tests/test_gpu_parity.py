@@ -311,6 +311,48 @@ def test_cg_batch_independent_convergence(E, ctx, assets, full_state):
     assert torch.equal(matb[0], m1[0]) and torch.equal(matb[1], m2[0])
 
 
+@pytest.mark.parametrize("which", ["gaussian_blur", "motion_blur", "inpainting", "super_resolution"])
+def test_cg_batch4_matches_single(E, ctx, assets, full_state, which):
+    """B = 4 independent images (per-image y, mu, masks and covariance state) in one call: every image bit-identical to
+    its own B = 1 solve, for the folded (mask, separable blur) and the non-folded (motion, x4 SR) operator paths; the
+    images stop at different iterations without disturbing each other."""
+    var = full_state["var"]
+    xs, sig, den = full_state["xs"], full_state["sig"], full_state["den"]
+    B = 4
+    rs = np.random.RandomState(7)
+    # four different states: same schedule, different data
+    st4 = E.CovState(ctx, B, E.BASIS_DCT)
+    st4.init(tt(var), S0 ** 2)
+    x0 = np.concatenate([xs[0] + 0.3 * b * rs.standard_normal(SHAPE) for b in range(B)])
+    x1 = np.concatenate([xs[1] + 0.3 * b * rs.standard_normal(SHAPE) for b in range(B)])
+    score = (np.concatenate([den(x0[b:b + 1], sig[0]) for b in range(B)]) - x0) / sig[0] ** 2
+    m4, _ = st4.time_update(tt(x0), tt(score), sig[0], sig[1])
+    mun = np.concatenate([den(x1[b:b + 1], sig[1]) for b in range(B)])
+    st4.space_update(m4, tt(mun), sig[1], tt(x0), tt(x1))
+    if which == "inpainting":
+        masks = (rs.uniform(size=(B, 256, 256)) > 0.7).astype(np.float32)
+        op4 = E.Operator.inpaint(ctx, masks)
+        ys = (np.clip(rs.standard_normal((B,) + SHAPE[1:]), -1, 1) + 0.1 * rs.standard_normal((B,) + SHAPE[1:])) * masks[:, None]
+    else:
+        op4, _ = _ops(E, ctx, assets, which)
+        ys = rs.standard_normal(op4.y_shape(B))
+    mus = 0.3 * rs.standard_normal((B,) + SHAPE[1:])
+    rtol = 0.5
+    mat4, info4 = E.cg_solve(st4, op4, tt(ys), tt(mus), SY2, rtol, maxiter=600)
+    for b in range(B):
+        st1 = E.CovState(ctx, 1, E.BASIS_DCT)
+        st1.init(tt(var), S0 ** 2)
+        sc1 = (den(x0[b:b + 1], sig[0]) - x0[b:b + 1]) / sig[0] ** 2
+        m1, _ = st1.time_update(tt(x0[b:b + 1]), tt(sc1), sig[0], sig[1])
+        st1.space_update(m1, tt(mun[b:b + 1]), sig[1], tt(x0[b:b + 1]), tt(x1[b:b + 1]))
+        op1 = E.Operator.inpaint(ctx, masks[b]) if which == "inpainting" else op4
+        mat1, info1 = E.cg_solve(st1, op1, tt(ys[b:b + 1]), tt(mus[b:b + 1]), SY2, rtol, maxiter=600)
+        assert info4["niter"][b] == info1["niter"][0] and info4["optimal"][b] == info1["optimal"][0], (which, b, info4, info1)
+        assert torch.equal(mat4[b], mat1[0]), (which, b)
+    record("cg_batch4", op=which, niter=info4["niter"])
+    assert len(set(info4["niter"])) > 1            # the images really stopped at different iterations
+
+
 # ---------------------------------------------------------------------------------------------- mechanism
 def _mechanism_run(assets, g, device="cuda"):
     from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
