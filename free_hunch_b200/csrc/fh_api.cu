@@ -52,7 +52,7 @@ void fh_prof_begin(const char* name, cudaStream_t stream) {
 }
 void fh_prof_end(cudaStream_t stream) {
   cudaEventRecord(g_prof_pairs.back().b, stream);
-  if (g_prof_pairs.size() >= 16384) prof_drain();
+  if (g_prof_pairs.size() >= (1u << 20)) prof_drain();      // draining stalls the host: only far beyond one bench step
 }
 extern "C" int fh_prof_enable(int on) {
   if (on && !fh_g_prof_on) g_prof_acc.clear();
@@ -110,6 +110,8 @@ struct fh_ctx {
   double *part_a, *part_b;            // (max_batch, nchunk) scalar-dot partials
   FhCgScalars* cg_sc;                 // (max_batch)
   FhCgScalars* cg_sc_host;            // pinned
+  volatile int* mirror_host;          // pinned + mapped (max_batch, 2): progress / done written by the CG kernels
+  int* mirror_dev;                    // device alias of mirror_host
   int* status;                        // device error counter (singular small matrices)
   float* cgv[6];                      // CG vectors b,x,r,p,q,t  (max_batch, d)
   double* strip_dots;                 // (max_batch, C*32, FH_MAXM) per-strip partial dots of the fused CG
@@ -187,6 +189,8 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMalloc((void**)&c->part_b, (size_t)max_batch * npart * sizeof(double)));
   FH_CUDA(cudaMalloc((void**)&c->cg_sc, (size_t)max_batch * sizeof(FhCgScalars)));
   FH_CUDA(cudaMallocHost((void**)&c->cg_sc_host, (size_t)max_batch * sizeof(FhCgScalars)));
+  FH_CUDA(cudaHostAlloc((void**)&c->mirror_host, (size_t)max_batch * 2 * sizeof(int), cudaHostAllocMapped));
+  FH_CUDA(cudaHostGetDevicePointer((void**)&c->mirror_dev, (void*)c->mirror_host, 0));
   FH_CUDA(cudaMalloc((void**)&c->status, sizeof(int)));
   FH_CUDA(cudaMemset(c->status, 0, sizeof(int)));
   FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * (FH_N / 2) * FH_MAXM * sizeof(double)));
@@ -227,7 +231,7 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
   cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
-  cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFree(c->status);
+  cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFreeHost((void*)c->mirror_host); cudaFree(c->status);
   free(c);
   return FH_OK;
 }
@@ -435,7 +439,7 @@ static FhCgFused fused_params(fh_state* s, fh_op* o, int R) {
   P.x = c->cgv[1]; P.r = c->cgv[2]; P.p = c->cgv[3]; P.q = c->cgv[4];
   P.T = c->plane_tmp; P.W = c->scratch[2];
   P.dots_partial = c->strip_dots; P.part_a = c->part_a; P.part_b = c->part_b;
-  P.sc = nullptr; P.sy2 = 0.f; P.trace = c->trace;
+  P.sc = nullptr; P.sy2 = 0.f; P.trace = c->trace; P.mirror = nullptr;
   P.tab = FhDctTables{c->tw256, c->post, c->cw};
   return P;
 }
@@ -822,23 +826,42 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   FH_ROWS_SWITCH(R, { FH_LAUNCH(fh_k_cg_r0<RR>, gy, block, 0, stream, P, (const float*)bv); });   // r0 = b - q
   FH_LAUNCH(fh_k_cg_r0_scalars, dim3(B), block, 0, stream, P, rtol, 0.0, use_stop);
   FH_KCHECK();
-  int poll = 4, since = 0;
+  // The host never synchronises inside the loop.  The kernels report (progress, done) per image into pinned mapped
+  // memory; iteration `it` is launched once every running image has executed iteration it - FH_RUNAHEAD, so the GPU
+  // always has work queued and at most FH_RUNAHEAD (+1: the stop test of iteration k runs in K1 of k+1) no-op
+  // iterations are launched after the last image has stopped.  The reference syncs twice per iteration (cg.py:250,259).
+  constexpr int FH_RUNAHEAD = 2;
+  for (int b = 0; b < B; ++b) { c->mirror_host[2 * b] = 0; c->mirror_host[2 * b + 1] = 0; }
+  P.mirror = c->mirror_dev;
+  int it_done = 0;
   for (int it = 1; it <= last; ++it) {
+    bool all = false;
+    for (long spins = 0;; ++spins) {
+      all = true;
+      bool ready = true;
+      for (int b = 0; b < B; ++b) {
+        const bool dn = c->mirror_host[2 * b + 1] != 0;
+        all = all && dn;
+        ready = ready && (dn || c->mirror_host[2 * b] >= it - FH_RUNAHEAD);
+      }
+      if (all || ready) break;
+      if (spins > 200000000L) {                                     // ~seconds: something is wrong, fall back to a hard sync
+        FH_CUDA(cudaStreamSynchronize(st));
+        break;
+      }
+    }
+    if (all) break;
     if ((rc = apply(it))) return rc;                               // (stop test of it-1,) p update, q = A_op p
     FH_ROWS_SWITCH(R, { FH_LAUNCH_PDL(fh_k_cg_xr<RR>, gy, block, 0, stream, P, it); });
     FH_KCHECK();
-    if (++since >= poll || it == last) {
-      since = 0;
-      FH_LAUNCH(fh_k_cg_finish, dim3(B), block, 0, stream, P, it + 1);   // records the stop test of iteration `it`
-      FH_KCHECK();
-      FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
-      FH_CUDA(cudaStreamSynchronize(st));
-      bool all = true;
-      for (int b = 0; b < B; ++b) all = all && c->cg_sc_host[b].done;
-      if (all) break;
-      if (poll < 32) poll *= 2;
-    }
+    it_done = it;
   }
+  FH_LAUNCH(fh_k_cg_finish, dim3(B), block, 0, stream, P, it_done + 1);   // records the stop test of the last iteration launched
+  FH_KCHECK();
+  FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+  FH_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b)
+    if (!c->cg_sc_host[b].done) FH_FAIL(FH_ESTATE, "CG loop ended with image %d still running (iteration %d of %d)", b, it_done, last);
   for (int b = 0; b < B; ++b) {
     if (niter_host) niter_host[b] = c->cg_sc_host[b].niter;
     if (optimal_host) optimal_host[b] = c->cg_sc_host[b].optimal;

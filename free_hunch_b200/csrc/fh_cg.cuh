@@ -45,6 +45,7 @@ struct FhCgFused {
   float sy2;
   int last_allowed;               // iteration limit of this solve (maxiter or the fixed iteration count)
   FhDctTables tab;
+  volatile int* mirror;           // pinned, host-mapped (B, 2) ints: [progress = last iteration whose x/r update ran, done]
   long long* trace;               // optional (FH_TRACE=1): clock64 checkpoints of CTA 0, 16 slots per kernel
 };
 
@@ -82,6 +83,10 @@ __device__ __forceinline__ bool fh_stopped_earlier(const FhCgFused& P, int b, in
 __device__ __forceinline__ void fh_set_done(FhCgScalars* sc, int tag) {
   *(volatile long long*)&sc->done = ((long long)tag << 32) | 1LL;
 }
+// Zero-copy progress report to the host (pinned, mapped): the host throttles its launches on it instead of
+// synchronising the stream, so the GPU queue never drains and no iteration is launched far past convergence.
+__device__ __forceinline__ void fh_mirror_done(const FhCgFused& P, int b) { if (P.mirror) P.mirror[2 * b + 1] = 1; }
+__device__ __forceinline__ void fh_mirror_progress(const FhCgFused& P, int b, int it) { if (P.mirror) P.mirror[2 * b] = it; }
 
 // Consumer side of the r.r reduction of iteration `it - 1` (cg.py:258-263): returns true when image b has stopped.
 // `record` (one CTA per image) stores the scalars for the host; every CTA gets beta.  Contains __syncthreads.
@@ -98,7 +103,7 @@ __device__ __forceinline__ bool fh_cg_consume_rr(const FhCgFused& P, int b, int 
     w->rr[it & 1] = rr_new;
     w->niter = it - 1;
     if (converged) w->optimal = 1;
-    if (stopped) fh_set_done(w, it);
+    if (stopped) { fh_set_done(w, it); fh_mirror_done(P, b); }
   }
   *beta_out = (float)(rr_new / rr_old);
   return stopped;
@@ -581,7 +586,7 @@ fh_k_cg_xr(FhCgFused P, int it) {
         const double pAp = fh_reduce_partials(P.part_a + (size_t)b * P.ystrips, P.ystrips, s_red);
         if (pAp <= 1e-16) {
           stopped = true;
-          if (s == b * P.ystrips && tid == 0) { P.sc[b].niter = it; fh_set_done(P.sc + b, -it); }
+          if (s == b * P.ystrips && tid == 0) { P.sc[b].niter = it; fh_set_done(P.sc + b, -it); fh_mirror_done(P, b); }
         } else {
           alpha = (float)(rr_cur / pAp);
         }
@@ -605,7 +610,10 @@ fh_k_cg_xr(FhCgFused P, int it) {
     fh_g_put<ROWS>(P.x + base, xv);
     fh_g_put<ROWS>(P.r + base, rv);
     const double tot = fh_block_sum((double)rr, s_red);
-    if (tid == 0) P.part_b[(size_t)b * P.ystrips + (s - b * P.ystrips)] = tot;
+    if (tid == 0) {
+      P.part_b[(size_t)b * P.ystrips + (s - b * P.ystrips)] = tot;
+      if (s == b * P.ystrips) fh_mirror_progress(P, b, it);
+    }
     FH_TRACE(P, 4, 2);
   }
 }

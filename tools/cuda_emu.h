@@ -142,6 +142,9 @@ static inline char* emu_dyn_smem() { return (char*)(((uintptr_t)emu::g_block->dy
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::calloc(1, n ? n : 1); return 0; }
+enum { cudaHostAllocMapped = 2 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::calloc(1, n ? n : 1); return 0; }
+static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return 0; }
 static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t = 0) { std::memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memmove(d, s, n); return 0; }
