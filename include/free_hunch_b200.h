@@ -103,8 +103,9 @@ int fh_op_apply(fh_op* op, const float* in_dev, float* out_dev, int batch, int t
  *   mat = u (inpaint) or A^T u.
  * y_dev: (B, y-shape), mu_dev/mat_out_dev: (B,C,H,W).  niter_host/optimal_host/resid_host: B entries each
  * (host memory, may be NULL).  fixed_iters>0 disables the residual test and runs exactly that many
- * iterations (test hook).  Per-image convergence is tracked on the device; the host polls a flag every
- * few iterations. */
+ * iterations (test hook).  Per-image convergence is tracked on the device; the kernels report progress into
+ * pinned mapped memory and the host keeps two iterations queued ahead (no stream sync inside the loop); the call
+ * returns after one final synchronisation of `stream`. */
 int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                 int maxiter, int fixed_iters, float* mat_out_dev, int* niter_host, int* optimal_host,
                 double* resid_host, void* stream);
