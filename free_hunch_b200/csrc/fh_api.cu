@@ -158,19 +158,25 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   fh_ctx* c = (fh_ctx*)calloc(1, sizeof(fh_ctx));
   c->device = device; c->max_batch = max_batch; c->C = channels; c->H = height; c->W = width; c->max_rank = max_rank;
   c->d = (long)channels * height * width;
-  std::vector<float2> tw(FH_N), post(FH_N), cw(FH_N);
+  std::vector<float2> tw(3 * 3 * 64), post(FH_N), cw(FH_N);
+  for (int s3 = 0; s3 < 3; ++s3) {                       // Stockham stages Ns = 4, 16, 64 (fh_dct.cuh)
+    const int Ns = 4 << (2 * s3);
+    for (int r = 1; r <= 3; ++r)
+      for (int j = 0; j < 64; ++j) {
+        const double a = -2.0 * M_PI * (double)(j % Ns) * r / (4.0 * Ns);
+        tw[(s3 * 3 + (r - 1)) * 64 + j] = make_float2((float)cos(a), (float)sin(a));
+      }
+  }
   for (int j = 0; j < FH_N; ++j) {
-    const double a = -2.0 * M_PI * j / FH_N;
-    tw[j] = make_float2((float)cos(a), (float)sin(a));
     const double th = -M_PI * j / (2.0 * FH_N);
     const double f = (j == 0) ? sqrt(1.0 / FH_N) : sqrt(2.0 / FH_N);
     post[j] = make_float2((float)(f * cos(th)), (float)(f * sin(th)));
     cw[j] = make_float2((float)cos(-th), (float)sin(-th));
   }
-  FH_CUDA(cudaMalloc((void**)&c->tw256, FH_N * sizeof(float2)));
+  FH_CUDA(cudaMalloc((void**)&c->tw256, tw.size() * sizeof(float2)));
   FH_CUDA(cudaMalloc((void**)&c->post, FH_N * sizeof(float2)));
   FH_CUDA(cudaMalloc((void**)&c->cw, FH_N * sizeof(float2)));
-  FH_CUDA(cudaMemcpy(c->tw256, tw.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
+  FH_CUDA(cudaMemcpy(c->tw256, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   FH_CUDA(cudaMemcpy(c->post, post.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
   FH_CUDA(cudaMemcpy(c->cw, cw.data(), FH_N * sizeof(float2), cudaMemcpyHostToDevice));
   const size_t vec = (size_t)max_batch * c->d * sizeof(float);

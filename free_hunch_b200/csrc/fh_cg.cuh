@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FH_PASS_THREADS)
 fh_k_cg_fwd_cols(FhCgFused P) {
   __shared__ __align__(16) FhStripSmem<ROWS> sm;
   __shared__ __align__(16) float s_taps[FH_MAX_SEP_TAPS];
-  __shared__ double s_w[FH_PASS_THREADS / 32][FH_MAXM];
+  __shared__ float s_w[FH_PASS_THREADS / 32][FH_MAXM];      // per-warp fp32 sums; added up in fp64 below
   __shared__ __align__(8) fh_mbar_t s_bar[FH_ZMAX_STAGES];
   FH_DYN_SMEM(float, zbuf);
   FH_TRACE(P, 1, 0);
@@ -304,7 +304,7 @@ fh_k_cg_fwd_cols(FhCgFused P) {
           kp += __shfl_xor_sync(0xffffffffu, kp, 4);
           kp += __shfl_xor_sync(0xffffffffu, kp, 2);
           kp += __shfl_xor_sync(0xffffffffu, kp, 1);
-          if ((lane & 7) == 0 && j * ZR + (lane >> 3) < P.m) s_w[warp][j * ZR + (lane >> 3)] = (double)kp;   // lane 8r holds row r
+          if ((lane & 7) == 0 && j * ZR + (lane >> 3) < P.m) s_w[warp][j * ZR + (lane >> 3)] = kp;   // lane 8r holds row r
         } else {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1)
@@ -313,7 +313,7 @@ fh_k_cg_fwd_cols(FhCgFused P) {
           if (lane == 0) {
 #pragma unroll
             for (int u = 0; u < ZR; ++u)
-              if (j * ZR + u < P.m) s_w[warp][j * ZR + u] = (double)acc[u];
+              if (j * ZR + u < P.m) s_w[warp][j * ZR + u] = acc[u];
           }
         }
         if (j + zs.stages < zs.nrounds) {                   // recycle this buffer for a later round
@@ -326,7 +326,7 @@ fh_k_cg_fwd_cols(FhCgFused P) {
       if (tid < P.m) {
         double t = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t += s_w[wv][tid];
+        for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t += (double)s_w[wv][tid];
         P.dots_partial[((size_t)b * P.strips_per_image + sidx) * FH_MAXM + tid] = t;
       }
       FH_TRACE(P, 1, 14);

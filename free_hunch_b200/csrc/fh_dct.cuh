@@ -18,7 +18,8 @@
 #include "fh_common.cuh"
 
 struct FhDctTables {
-  const float2* tw256;   // exp(-2 pi i j / 256), j = 0..255
+  const float2* tw256;   // Stockham stage twiddles in thread order: [stage s = 0..2 (Ns = 4, 16, 64)][r = 1..3][j = 0..63]
+                         //   = exp(-2 pi i (j mod Ns) r / (4 Ns))   (576 entries; conjugated for the inverse)
   const float2* post;    // f_k * exp(-i pi k / 512): forward post-twiddle incl. orthonormal scale
   const float2* cw;      // exp(+i pi k / 512): inverse pre-twiddle
 };
@@ -34,7 +35,7 @@ struct FhStripSmem {
   float b[ROWS * FH_RS];
   float2 X[ROWS / 2][FH_FFT_LD];      // FFT ping-pong buffers, padded (FH_PAD) so that every Stockham stage's
   float2 Y[ROWS / 2][FH_FFT_LD];      // strided writes fall on distinct banks
-  float2 tw[FH_N];
+  float2 tw[3 * 3 * 64];              // per-stage twiddles, laid out so that thread j reads entry j: conflict-free
   float2 tab[FH_N];
 };
 
@@ -63,11 +64,11 @@ __device__ __forceinline__ void fh_dft4(float2& a0, float2& a1, float2& a2, floa
 // Load the twiddle tables of one direction into the strip's shared memory (all threads; caller syncs).
 template <bool INV, int ROWS>
 __device__ __forceinline__ void fh_strip_tables(FhStripSmem<ROWS>& sm, const FhDctTables& tab) {
-  for (int i = threadIdx.x; i < FH_N; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 3 * 3 * 64; i += blockDim.x) {
     const float2 w = tab.tw256[i];
-    sm.tw[i] = INV ? make_float2(w.x, -w.y) : w;      // exp(SIGN * 2 pi i j / 256)
-    sm.tab[i] = INV ? tab.cw[i] : tab.post[i];
+    sm.tw[i] = INV ? make_float2(w.x, -w.y) : w;
   }
+  for (int i = threadIdx.x; i < FH_N; i += blockDim.x) sm.tab[i] = INV ? tab.cw[i] : tab.post[i];
 }
 
 // One Stockham radix-4 stage of a 256-point FFT for thread j in [0, 64): sub-transform length Ns -> 4 Ns.
@@ -76,10 +77,10 @@ __device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, f
   const int k = j & (NS - 1);
   float2 v0 = in[FH_PAD(j)], v1 = in[FH_PAD(j + 64)], v2 = in[FH_PAD(j + 128)], v3 = in[FH_PAD(j + 192)];
   if (NS > 1) {
-    const int t = k * (64 / NS);                       // angle = SIGN * 2 pi k r / (4 Ns)
-    v1 = fh_cmul(v1, tw[t]);
-    v2 = fh_cmul(v2, tw[2 * t]);
-    v3 = fh_cmul(v3, tw[3 * t]);
+    constexpr int S = (NS == 4) ? 0 : (NS == 16) ? 1 : 2;   // angle = SIGN * 2 pi k r / (4 Ns), tabulated per thread
+    v1 = fh_cmul(v1, tw[(S * 3 + 0) * 64 + j]);
+    v2 = fh_cmul(v2, tw[(S * 3 + 1) * 64 + j]);
+    v3 = fh_cmul(v3, tw[(S * 3 + 2) * 64 + j]);
   }
   fh_dft4<SIGN>(v0, v1, v2, v3);
   const int j0 = ((j - k) << 2) + k;
