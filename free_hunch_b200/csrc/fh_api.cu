@@ -948,7 +948,7 @@ extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* m
 }
 
 // bench.py's roofline: `reps` back-to-back launches of ONE kernel of the fused iteration at the state's current
-// rank, timed with CUDA events on `stream` (inputs are whatever the workspace holds; sizes and access pattern are
+// rank, launched exactly as in the product (programmatic dependent launch), timed with CUDA events on `stream` (inputs are whatever the workspace holds; sizes and access pattern are
 // those of a real iteration).  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols, 3 inv_rows, 4 xr.
 extern "C" int fh_cg_kernel_time(fh_state* s, fh_op* o, int which, int reps, float* ms_out, void* stream) {
 #ifdef FH_EMU
@@ -979,11 +979,11 @@ extern "C" int fh_cg_kernel_time(fh_state* s, fh_op* o, int which, int reps, flo
     if (pass) FH_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < (pass ? reps : 3); ++i) {
       FH_ROWS_SWITCH(R, {
-        if (which == 0) FH_LAUNCH(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, (const float*)nullptr, 2);
-        else if (which == 1) FH_LAUNCH(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
-        else if (which == 2) FH_LAUNCH(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
-        else if (which == 3) FH_LAUNCH(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, (const float*)nullptr, 2);
-        else FH_LAUNCH(fh_k_cg_xr<RR>, gimg, block, 0, stream, P, 2);
+        if (which == 0) FH_LAUNCH_PDL(fh_k_cg_fwd_rows<RR>, gimg, block, 0, stream, P, (const float*)nullptr, (const float*)nullptr, 2);
+        else if (which == 1) FH_LAUNCH_PDL(fh_k_cg_fwd_cols<RR>, gimg, block, zbytes, stream, P);
+        else if (which == 2) FH_LAUNCH_PDL(fh_k_cg_inv_cols<RR>, gimg, block, zbytes, stream, P);
+        else if (which == 3) FH_LAUNCH_PDL(fh_k_cg_inv_rows<RR>, gimg, block, 0, stream, P, (float*)nullptr, (const float*)nullptr, 2);
+        else FH_LAUNCH_PDL(fh_k_cg_xr<RR>, gimg, block, 0, stream, P, 2);
       });
     }
     if (pass) FH_CUDA(cudaEventRecord(e1, st));

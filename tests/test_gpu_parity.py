@@ -414,3 +414,52 @@ def test_mechanism_default_rtol_runs(assets):
     assert mech.covariance_model.vector_count == int(g["k_final"])
     assert np.all(np.abs(got_n - ref_n) <= np.maximum(5, 0.2 * ref_n)), (got_n, ref_n)
     assert ef < 5e-2
+
+
+@pytest.mark.parametrize("which,solver", [("inpainting", "heun"), ("super_resolution", "heun"), ("motion_blur", "euler")])
+def test_mechanism_other_operators_vs_oracle(assets, which, solver):
+    """The whole mechanism (Python API, batch 2) for the operators the golden run does not cover, against the float64
+    oracle mechanism on the same inputs, at a tight CG tolerance (max_rtol = 1e-5) so that the comparison is between
+    converged quantities: box-mask inpainting, x4 super-resolution (Heun) and motion blur (Euler, the config-5 solver)."""
+    from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
+    from free_hunch_b200.measurements import get_operator
+    from free_hunch_b200.sampler import AnalyticDCTGaussianDenoiser, conditional_sampler, edm_sigma_steps
+    var = assets["dct_variance"]
+    B = 2
+    t_steps = edm_sigma_steps(4, sigma_min=0.5, sigma_max=12.0).numpy()          # 12 -> 0.5 crosses the space-update window
+    x_clean = np.concatenate([synth_image(var, 31 + b) for b in range(B)])
+    noise = make_inputs(40, (B,) + SHAPE[1:])
+    kw = dict(in_shape=(B,) + SHAPE[1:], sigma_s=0.1, device="cuda")
+    if which == "inpainting":
+        np.random.seed(5)
+        masks = np.stack([fo.mask_box(256, (64, 156))[0, 0] for _ in range(B)])
+        op = get_operator("inpainting", mask=tt(masks)[:, None].repeat(1, 3, 1, 1), **kw)
+        oos = [fo.InpaintingOracle(np.broadcast_to(masks[b], SHAPE), 0.1) for b in range(B)]
+        ys = np.concatenate([(x_clean[b:b + 1] + 0.1 * make_inputs(50 + b, SHAPE)) * masks[b] for b in range(B)])
+    elif which == "super_resolution":
+        op = get_operator("super_resolution", kernel=assets["bicubic_x4"], scale_factor=4, **kw)
+        oos = [fo.SuperResolutionOracle(assets["bicubic_x4"], 0.1, 4, otf_dtype=np.complex128)] * B
+        ys = np.concatenate([oos[b].A(x_clean[b:b + 1]) + 0.1 * make_inputs(50 + b, (1, 3, 64, 64)) for b in range(B)])
+    else:
+        op = get_operator("motion_blur", kernel=assets["motion_ks61_std05"], **kw)
+        oos = [fo.MotionBlurOracle(assets["motion_ks61_std05"], 0.1, otf_dtype=np.complex128)] * B
+        ys = np.concatenate([oos[b].A(x_clean[b:b + 1]) + 0.1 * make_inputs(50 + b, SHAPE) for b in range(B)])
+    mech = choose_conditioning_mechanism("free_hunch")(
+        1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(t_steps[0] ** 2, dtype=torch.float64),
+        data_dim=3 * 256 * 256, max_vector_count=100000, dct_variance=var, image_base_covariance="dct_diagonal",
+        denoiser_mean_error_threshold=0.2, use_analytical_score_time_update=True, project_to_diagonal=False,
+        space_step_update_threshold=10.0, space_step_update_lower_threshold=1.0, max_rtol=1e-5, do_space_updates=True,
+        use_analytic_var_at_end=False, solver_type="customcuda", use_rtol_func=True, device="cuda", batch=B)
+    net = AnalyticDCTGaussianDenoiser(var, mech.covariance_model.ctx)
+    x = conditional_sampler(mech, net, tt(ys).float().cuda(), tt(noise).cuda(), t_steps, solver=solver)
+    assert bool(torch.isfinite(x).all())
+    model = fo.analytic_dct_gaussian_denoiser(var)
+    errs = []
+    for b in range(B - 1, B):                            # the float64 oracle takes ~1 min per image: check the last one
+        om = fo.FreeHunchOracle(oos[b], fo.CovarianceOracleDCT(var, t_steps[0] ** 2, var.size), max_rtol=1e-5)
+        xo = fo.conditional_sampler(om, model, ys[b:b + 1], noise[b:b + 1], t_steps, solver=solver)
+        errs.append(rel_l2(x[b:b + 1], xo))
+        assert mech.covariance_model.vector_count == om.log[-1]["k"]
+        assert [r["space_update"] for r in mech.log] == [r["space_update"] for r in om.log]
+    record("mechanism_other_ops", op=which, solver=solver, final=errs, niter=[r["niter"] for r in mech.log], k=mech.covariance_model.vector_count)
+    assert max(errs) < 1e-3, errs
