@@ -5,6 +5,7 @@
 #include "fh_dct.cuh"
 #include "fh_kernels.cuh"
 #include "fh_cg.cuh"
+#include "fh_cg_resident.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -116,6 +117,10 @@ struct fh_ctx {
   float* cgv[6];                      // CG vectors b,x,r,p,q,t  (max_batch, d)
   double* strip_dots;                 // (max_batch, C*32, FH_MAXM) per-strip partial dots of the fused CG
   int sms;                            // multiprocessors of the device (grid sizing)
+  unsigned* grid_counter;             // (max_batch) arrival counters of the resident CG kernel's grid barrier
+  int cg_mode;                        // FH_CG_AUTO / FH_CG_STREAMING / FH_CG_RESIDENT (fh_ctx_set_cg_mode)
+  int cg_last_mode;                   // path taken by the last DCT-basis fh_cg_solve
+  int res_ok;                         // the resident kernel's cooperative grid fits this device
   long long* trace;                   // FH_TRACE=1: clock64 checkpoints of the fused CG kernels (8 kernels x 16 slots)
 };
 
@@ -201,6 +206,8 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMemset(c->status, 0, sizeof(int)));
   FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * (FH_N / 2) * FH_MAXM * sizeof(double)));
   c->sms = 148;
+  FH_CUDA(cudaMalloc((void**)&c->grid_counter, (size_t)max_batch * sizeof(unsigned)));
+  c->cg_mode = FH_CG_AUTO; c->cg_last_mode = 0; c->res_ok = 1;
   c->trace = nullptr;
   if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
 #ifndef FH_EMU
@@ -217,10 +224,30 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
   FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
   FH_CUDA(cudaFuncSetAttribute(fh_k_cg_inv_cols<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_ZMAX_STAGES * FH_ZROUND_FLOATS * 4));
+  {
+    // resident CG solve: one CTA per SM holding up to FH_RES_MAXM row slices of Z; needs C*256/6 co-resident CTAs
+    const int res_smem = (int)sizeof(FhResSmem) + FH_RES_MAXM * FH_RES_SLICE * 4;
+    FH_CUDA(cudaFuncSetAttribute(fh_k_cg_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem));
+    int per_sm = 0;
+    FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fh_k_cg_resident, FH_PASS_THREADS, res_smem));
+    int coop = 0;
+    FH_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    const long rows = (long)channels * height;
+    c->res_ok = (coop && height == FH_N && width == FH_N && rows % FH_RES_ROWS == 0 && rows / FH_RES_ROWS <= (long)per_sm * c->sms) ? 1 : 0;
+  }
+#else
+  c->res_ok = (height == FH_N && width == FH_N && ((long)channels * height) % FH_RES_ROWS == 0) ? 1 : 0;
 #endif
   *out = c;
   return FH_OK;
 }
+
+extern "C" int fh_ctx_set_cg_mode(fh_ctx* c, int mode) {
+  if (!c || mode < FH_CG_AUTO || mode > FH_CG_RESIDENT) FH_FAIL(FH_EINVAL, "bad fh_ctx_set_cg_mode arguments");
+  c->cg_mode = mode;
+  return FH_OK;
+}
+extern "C" int fh_ctx_cg_last_mode(const fh_ctx* c) { return c ? c->cg_last_mode : FH_EINVAL; }
 
 // Debug: copies the 8 x 16 clock64 checkpoints recorded by CTA 0 of the fused CG kernels (FH_TRACE=1) to the host.
 extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
@@ -235,7 +262,7 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
-  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace);
+  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace); cudaFree(c->grid_counter);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
   cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFreeHost((void*)c->mirror_host); cudaFree(c->status);
   free(c);
@@ -768,6 +795,77 @@ static int apply_ASAt(fh_state* s, fh_op* o, const float* p, float* t, void* str
   return fh_op_apply(o, img, t, s->B, 0, stream);
 }
 
+// Cooperative launch of the resident CG kernel (all CTAs co-resident: the kernel has grid barriers).
+static int launch_resident(fh_ctx* c, const FhCgFused& P, const FhCgResident& R, cudaStream_t st) {
+  const dim3 grid((unsigned)P.strips_per_image), block(FH_PASS_THREADS);
+  const size_t smem = sizeof(FhResSmem) + (size_t)P.m * FH_RES_SLICE * sizeof(float);
+#ifdef FH_EMU
+  (void)c; (void)st;
+  emu::launch_coop([&] { fh_k_cg_resident(P, R); }, grid, block, smem);
+  ++fh_g_launches;
+#else
+  (void)c;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (fh_g_prof_on) fh_prof_begin("fh_k_cg_resident", st);
+  FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_resident, P, R));
+  if (fh_g_prof_on) fh_prof_end(st);
+  ++fh_g_launches;
+#endif
+  return FH_OK;
+}
+
+static bool resident_applies(const fh_state* s, const FhCgFused& P) {
+  const fh_ctx* c = s->ctx;
+  return c->res_ok && P.fuse != 0 && s->m <= FH_RES_MAXM && c->cg_mode != FH_CG_STREAMING;
+}
+
+// Whole solve in one launch per image (fh_cg_resident.cuh): Z stays in shared memory, x/r/p/q in registers.
+static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y, const float* mu, double rtol, int last,
+                             int use_stop, float* mat_out, int* niter_host, int* optimal_host, double* resid_host, void* stream) {
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->B;
+  const long n = s->d;                                    // mask and blur: measurement space == image space
+  const long hw = (long)c->H * c->W;
+  float *bv = c->cgv[0], *x = c->cgv[1], *t = c->cgv[5];
+  int rc;
+  const float* amu = mu;
+  if (o->kind != FH_OP_INPAINT) {
+    if ((rc = fh_op_apply(o, mu, t, B, 0, stream))) return rc;
+    amu = t;
+  }
+  FH_LAUNCH(fh_k_cg_rhs, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, amu, P.mask, P.mask_batch, hw, bv, x, n);
+  FH_KCHECK();
+  FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
+  FH_CUDA(cudaMemsetAsync(c->grid_counter, 0, (size_t)B * sizeof(unsigned), st));
+  P.strips_per_image = (int)(s->d / FH_RES_SLICE);
+  P.ystrips = P.strips_per_image;
+  P.last_allowed = last;
+  P.mirror = nullptr;
+  float* xout = (o->kind == FH_OP_INPAINT) ? mat_out : x;  // inpainting returns u itself
+  for (int b = 0; b < B; ++b) {
+    FhCgResident R{};
+    R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n; R.grid_counter = c->grid_counter + b;
+    R.rtol = rtol; R.atol = 0.0; R.use_stop = use_stop; R.image = b;
+    if ((rc = launch_resident(c, P, R, st))) return rc;
+  }
+  FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+  FH_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    if (!c->cg_sc_host[b].done) FH_FAIL(FH_ESTATE, "resident CG kernel did not finish image %d", b);
+    if (niter_host) niter_host[b] = c->cg_sc_host[b].niter;
+    if (optimal_host) optimal_host[b] = c->cg_sc_host[b].optimal;
+    if (resid_host) resid_host[b] = sqrt(c->cg_sc_host[b].resid2);
+  }
+  if (o->kind == FH_OP_INPAINT) return FH_OK;
+  return fh_op_apply(o, x, mat_out, B, 1, stream);
+}
+
 // DCT-basis solve: the iteration of fh_cg.cuh.  5 launches per iteration when the operator folds into the DCT passes
 // (mask, separable blur), 9 otherwise (p update, A^T, 4 passes, A, q, x/r update).
 static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
@@ -787,6 +885,13 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   const int use_stop = fixed_iters > 0 ? 0 : 1;
   const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
   P.last_allowed = last;
+  if (resident_applies(s, P)) {
+    c->cg_last_mode = FH_CG_RESIDENT;
+    return cg_solve_resident(s, o, P, y, mu, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream);
+  }
+  if (c->cg_mode == FH_CG_RESIDENT)
+    FH_FAIL(FH_EINVAL, "resident CG solve requested but not applicable (rank %d > %d, operator not foldable, or device too small)", s->m, FH_RES_MAXM);
+  c->cg_last_mode = FH_CG_STREAMING;
   const bool fusedop = P.fuse != 0;
   const dim3 block(FH_PASS_THREADS);
   const dim3 gimg = strip_grid(c, B * P.strips_per_image), gy = strip_grid(c, B * ystrips);

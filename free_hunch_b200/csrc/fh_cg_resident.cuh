@@ -1,0 +1,435 @@
+// Resident CG solve: ONE cooperative launch runs a whole solve of  (sigma_y^2 I + A Sigma A^T) u = b  for one image
+// (conditioning_utils/cg.py:230-292 with the operators of conditioning_mechanisms.py:384-419 / 489-527), for the
+// operators that fold into the DCT passes (mask, separable blur).
+//
+// Why: at one image per GPU (BASELINE configs[1], [2]) the five-kernel iteration of fh_cg.cuh is bound by launch
+// latency and by re-reading Z (m x 786 KB) from L2 twice per iteration.  Z does not change during a solve, and the
+// 148 SMs of a B200 hold 33 MB of shared memory -- more than Z at the rank a 30-step Heun run reaches (m = 32:
+// 25 MB).  So the 768 rows (3 channels x 256) of the image are cut into 128 strips of 6 rows; CTA s of a 128-CTA
+// cooperative grid
+//   * owns pixel rows [6s, 6s+6) of x, r, p, q, b, mask                       -> registers, for the whole solve
+//   * owns basis rows [6s, 6s+6) of delta (registers) and of every row of Z   -> shared memory (m x 6 KB, one TMA
+//     bulk copy per row, issued once in the prologue), for the whole solve
+// and the only global traffic of an iteration is the half-transformed plane T that has to be transposed between the
+// row pass and the column pass of the 2-D DCT (written transposed, read back after a grid barrier: 4 x 786 KB through
+// L2) plus a few KB of fp64 partial sums.  An iteration is five phases separated by five grid barriers:
+//
+//   P1  w = mask.p | row-blur^T p ; row DCT ; transposed store -> T                                   | barrier
+//   P2  T -> column blur^T ; column DCT = w_hat (registers) ; partial Z (delta w_hat) -> partials     | barrier
+//   P3  coef = Gs sum(partials) ; delta (w_hat + Z^T coef) ; column IDCT ; column blur ; T (transp.)  | barrier
+//   P4  T -> row IDCT ; row blur | mask = t ; q = sy2 p + t ; partial p.q                              | barrier
+//   P5  alpha = rr / sum ; (p.Ap <= 1e-16 -> break) ; x += alpha p ; r -= alpha q ; partial r.r        | barrier
+//       rr' = sum ; stop test ; beta = rr'/rr ; p = r + beta p
+//
+// All scalars are fixed-order sums of the same partials in every CTA (bit-identical), so every CTA takes the same
+// branch and the loop needs no flag.  The initial residual r0 = b - A_op b (x0 = b, cg.py:233-235) is iteration 0 of the
+// same loop.  Barrier waits are bounded (__trap instead of a hang).
+#pragma once
+#include "fh_cg.cuh"
+
+#define FH_RES_ROWS 6
+#define FH_RES_SLICE (FH_RES_ROWS * FH_N)          // floats per strip (1536)
+#define FH_RES_CTAS_PER_PLANE_X3 128               // 3 * 256 / 6
+#define FH_RES_MAXM 32                             // rows of Z one CTA can keep in shared memory (32 x 6 KB = 192 KB)
+#define FH_RES_TAPS (FH_MAX_SEP_TAPS + 8)
+
+struct FhResSmem {
+  float2 X[FH_RES_ROWS / 2][FH_FFT_LD];            // FFT ping-pong; X doubles as the strip's input rows (stride FH_RS),
+  float2 Y[FH_RES_ROWS / 2][FH_FFT_LD];            // Y as its output rows (see fh_dct_strip_core)
+  float2 tw[3 * 3 * 64];
+  float2 post[FH_N];
+  float2 cw[FH_N];
+  float taps[4][FH_RES_TAPS];                      // row A^T, column A^T, column A, row A (centre padded to a multiple of 4)
+  float s_w[FH_PASS_THREADS / 32][FH_RES_MAXM];
+  double s_sum[FH_RES_MAXM];
+  double s_red[34];
+  float s_c[FH_RES_MAXM];
+  fh_mbar_t bar;
+  unsigned long long pad_;
+};
+
+struct FhCgResident {
+  const float* bvec;           // (d) right-hand side b (pixel layout); x0 = b
+  float* x_out;                // (d) solution
+  unsigned* grid_counter;      // zeroed by the host before the launch
+  double rtol, atol;
+  int use_stop;                // 0: run exactly `last_allowed` iterations
+  int image;                   // which image of the batch (offsets into the state / scalars)
+};
+
+// ---- grid barrier -----------------------------------------------------------------------------------------
+#ifdef FH_EMU
+static inline void fh_grid_sync(unsigned*, unsigned&, unsigned) {
+  __syncthreads();
+  if (threadIdx.x == 0) emu::g_grid_bar.wait();
+  __syncthreads();
+}
+template <typename T> static inline T fh_ld_cg(const T* p) { return *p; }
+#else
+// All threads call it.  Thread 0 arrives with release semantics (the CTA's earlier writes, ordered by the bar.sync,
+// become visible device-wide) and polls with acquire loads until every CTA of the grid has arrived.
+__device__ __forceinline__ void fh_grid_sync(unsigned* counter, unsigned& target, unsigned nblocks) {
+  target += nblocks;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned v = 0;
+    for (unsigned spins = 0;; ++spins) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      if (spins > 20000000u) __trap();                 // seconds: a CTA is missing -> fail the launch, do not hang
+    }
+  }
+  __syncthreads();
+}
+template <typename T> __device__ __forceinline__ T fh_ld_cg(const T* p) { return __ldcg(p); }
+#endif
+
+// the thread's 6 elements of a strip as 3 float2 (#t, #t+256, #t+512), read past L1 (data written by other CTAs)
+__device__ __forceinline__ void fh_res_get_cg(const float* src, float (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const float2 v = fh_ld_cg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+
+// the thread's 6 elements of a contiguous (unpadded) 1536-float slice in shared memory: conflict-free LDS.64
+__device__ __forceinline__ void fh_strip_get_flat(const float* src, float (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+
+// transposed store of strip s (global rows 6s .. 6s+5 of the 768): T[plane][k][row] = rows[row][k].  Row pairs never
+// straddle a plane (256 is even); the strip itself may.
+__device__ __forceinline__ void fh_res_store_t(const float* sm_rows, float* __restrict__ T, int s) {
+  const int k = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int g = FH_RES_ROWS * s + 2 * h;
+    float* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
+    *reinterpret_cast<float2*>(d) = make_float2(sm_rows[(2 * h) * FH_RS + k], sm_rows[(2 * h + 1) * FH_RS + k]);
+  }
+}
+
+// In-place circular correlation along the 6 rows (register window, 8 outputs per thread, warps 0..5 active).
+// `taps`: n4 (multiple of 4) taps with centre c4 (multiple of 4).  Contains two __syncthreads.
+__device__ __forceinline__ void fh_res_conv(float* sm_rows, const float* __restrict__ taps, int n4, int c4) {
+  const int row = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool act = row < FH_RES_ROWS;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (act) {
+    const float* rr = sm_rows + row * FH_RS;
+    const int base = 8 * l - c4;
+    float4 f0 = *reinterpret_cast<const float4*>(rr + (base & (FH_N - 1)));
+    float4 f1 = *reinterpret_cast<const float4*>(rr + ((base + 4) & (FH_N - 1)));
+    for (int a0 = 0; a0 < n4; a0 += 4) {
+      const float4 f2 = *reinterpret_cast<const float4*>(rr + ((base + a0 + 8) & (FH_N - 1)));
+      const float4 tk = *reinterpret_cast<const float4*>(taps + a0);
+      const float win[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+      const float tt[4] = {tk.x, tk.y, tk.z, tk.w};
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(tt[aa], win[aa + e], acc[e]);
+      f0 = f1; f1 = f2;
+    }
+  }
+  __syncthreads();
+  if (act) {
+    float* wr = sm_rows + row * FH_RS + 8 * l;
+    *reinterpret_cast<float4*>(wr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(wr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+}
+
+// Stage one tap set: forward = 0 (A^T): t = k, centre c; forward = 1 (A): t = reversed k, centre n-1-c; then shifted
+// right by (4 - centre % 4) % 4 zeros so that the centre is a multiple of 4.  Returns (n4 << 8) | c4.  Caller syncs.
+__device__ __forceinline__ int fh_res_stage_taps(float* s_taps, const float* __restrict__ k, int n, int c, int forward) {
+  const int cen = forward ? n - 1 - c : c;
+  const int sh = (4 - (cen & 3)) & 3;
+  const int n4 = (n + sh + 3) & ~3;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int a = i - sh;
+    s_taps[i] = (a >= 0 && a < n) ? (forward ? k[n - 1 - a] : k[a]) : 0.f;
+  }
+  return (n4 << 8) | (cen + sh);
+}
+
+// Sum over the 32 lanes of 32 values per lane with 31 shuffles: afterwards lane l holds the warp total of v[l] in v[0].
+__device__ __forceinline__ float fh_warp_transpose_sum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const float send = hi ? v[k] : v[k + o];
+      const float keep = hi ? v[k + o] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// grid = C*256/6 CTAs (cooperative launch), block = 256, dynamic shared memory = sizeof(FhResSmem) + m * 6 KB.
+__global__ void __launch_bounds__(FH_PASS_THREADS, 1)
+fh_k_cg_resident(FhCgFused P, FhCgResident R) {
+  FH_DYN_SMEM(unsigned char, smem_raw);
+  FhResSmem& sm = *reinterpret_cast<FhResSmem*>(smem_raw);
+  float* Zs = reinterpret_cast<float*>(smem_raw + sizeof(FhResSmem));       // [m][1536]
+  float* rows_a = reinterpret_cast<float*>(sm.X);
+  float* rows_b = reinterpret_cast<float*>(sm.Y);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x;
+  const unsigned nblk = gridDim.x;
+  const int m = P.m;
+  const long d = (long)nblk * FH_RES_SLICE;
+  const size_t img = (size_t)R.image * d;
+  const size_t soff = (size_t)s * FH_RES_SLICE;
+  unsigned bar_target = 0;
+
+  // ---- prologue: Z slices by TMA (one 6 KB bulk copy per row), tables, taps, per-solve constants in registers ----
+  if (tid == 0) { fh_mbar_init(&sm.bar, 1); fh_mbar_fence_init(); }
+  __syncthreads();
+  if (m > 0 && warp == 0) {
+    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)m * FH_RES_SLICE * 4u);
+    __syncwarp();
+    const float* zsrc = P.Z + (size_t)R.image * FH_MAXM * d + soff;
+    for (int i = lane; i < m; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, FH_RES_SLICE * 4u, &sm.bar);
+  }
+  for (int i = tid; i < 3 * 3 * 64; i += FH_PASS_THREADS) sm.tw[i] = P.tab.tw256[i];
+  for (int i = tid; i < FH_N; i += FH_PASS_THREADS) { sm.post[i] = P.tab.post[i]; sm.cw[i] = P.tab.cw[i]; }
+  int tp[4] = {0, 0, 0, 0};
+  if (P.fuse == 2) {
+    tp[0] = fh_res_stage_taps(sm.taps[0], P.kr, P.nr, P.cr, 0);
+    tp[1] = fh_res_stage_taps(sm.taps[1], P.kc, P.nc, P.cc, 0);
+    tp[2] = fh_res_stage_taps(sm.taps[2], P.kc, P.nc, P.cc, 1);
+    tp[3] = fh_res_stage_taps(sm.taps[3], P.kr, P.nr, P.cr, 1);
+  }
+  float bv[FH_RES_ROWS], dl[FH_RES_ROWS], mk[FH_RES_ROWS];
+  fh_g_get<FH_RES_ROWS>(R.bvec + soff, bv);
+  fh_g_get<FH_RES_ROWS>(P.delta + img + soff, dl);
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e) mk[e] = 1.f;
+  if (P.fuse == 1) {
+    // the mask is one 256 x 256 plane per image, shared by the channels: global row g -> plane row g & 255
+    const float* mp = P.mask + (size_t)(P.mask_batch > 1 ? R.image : 0) * FH_N * FH_N;
+#pragma unroll
+    for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+      const int e = 2 * (tid + FH_PASS_THREADS * h);                    // element offset inside the strip
+      const int g = FH_RES_ROWS * s + (e >> 8);
+      const float2 v = *reinterpret_cast<const float2*>(mp + (size_t)(g & (FH_N - 1)) * FH_N + (e & (FH_N - 1)));
+      mk[2 * h] = v.x; mk[2 * h + 1] = v.y;
+    }
+  }
+  // coefficient stage: thread (i = tid / 8, part = tid % 8) owns Gs[i][part + 8u], u < 4
+  const int ci = tid >> 3, cpart = tid & 7;
+  double gs[4] = {0.0, 0.0, 0.0, 0.0};
+  if (ci < m) {
+    const double* g = P.Gs + ((size_t)R.image * FH_MAXM + ci) * FH_MAXM;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) gs[u] = (cpart + 8 * u < m) ? g[cpart + 8 * u] : 0.0;
+  }
+  double* dots_part = P.dots_partial + (size_t)R.image * P.strips_per_image * FH_MAXM;    // [nblk][FH_MAXM]
+  double* part_a = P.part_a + (size_t)R.image * P.ystrips;
+  double* part_b = P.part_b + (size_t)R.image * P.ystrips;
+  float* T = P.T + img;
+  __syncthreads();
+
+  float x[FH_RES_ROWS], r[FH_RES_ROWS], p[FH_RES_ROWS], q[FH_RES_ROWS];
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e) { x[e] = bv[e]; p[e] = bv[e]; r[e] = 0.f; q[e] = 0.f; }
+  double rr = 0.0, stop2 = -1.0, resid2 = 0.0;
+  int niter = 0, optimal = 0;
+  bool z_ready = (m == 0);
+
+  for (int it = 0;; ++it) {
+    // ------------------------------------------------------------------ P1: rows, forward
+    {
+      float w[FH_RES_ROWS];
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) w[e] = p[e] * mk[e];
+      fh_strip_put<FH_RES_ROWS>(rows_a, w);
+      __syncthreads();
+      if (P.fuse == 2) fh_res_conv(rows_a, sm.taps[0], tp[0] >> 8, tp[0] & 255);
+      fh_dct_strip_core<false, FH_RES_ROWS, false>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.post);
+      __syncthreads();
+      fh_res_store_t(rows_b, T, s);
+    }
+    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    // ------------------------------------------------------------------ P2: columns, forward; partial Z (delta w_hat)
+    float wh[FH_RES_ROWS];
+    {
+      float t[FH_RES_ROWS];
+      fh_res_get_cg(T + soff, t);
+      fh_strip_put<FH_RES_ROWS>(rows_a, t);
+      __syncthreads();
+      if (P.fuse == 2) fh_res_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255);
+      fh_dct_strip_core<false, FH_RES_ROWS, false>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.post);
+      __syncthreads();
+      fh_strip_get<FH_RES_ROWS>(rows_b, wh);
+    }
+    if (m > 0) {
+      if (!z_ready) { fh_mbar_wait(&sm.bar, 0); z_ready = true; }
+      float wd[FH_RES_ROWS];
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) wd[e] = wh[e] * dl[e];
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = 0.f;
+        if (i < m) {
+          float z[FH_RES_ROWS];
+          fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+#pragma unroll
+          for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fmaf(z[e], wd[e], acc[i]);
+        }
+      }
+      const float tot = fh_warp_transpose_sum32(acc);
+      sm.s_w[warp][lane] = tot;
+      __syncthreads();
+      if (tid < m) {
+        double t = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t += (double)sm.s_w[wv][tid];
+        dots_part[(size_t)s * FH_MAXM + tid] = t;
+      }
+      fh_grid_sync(R.grid_counter, bar_target, nblk);
+      // ---------------------------------------------------------------- P3: coef = Gs sum(partials); w_hat + Z^T coef
+      {
+        double t = 0.0;
+        if (ci < m) {
+          const double* col = dots_part + ci;
+          for (int k0 = cpart; k0 < (int)nblk; k0 += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + 8 * u < (int)nblk) ? fh_ld_cg(col + (size_t)(k0 + 8 * u) * FH_MAXM) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += v[u];
+          }
+        }
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        if (cpart == 0 && ci < FH_RES_MAXM) sm.s_sum[ci] = (ci < m) ? t : 0.0;
+        __syncthreads();
+        double a = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a += gs[u] * sm.s_sum[cpart + 8 * u];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (cpart == 0 && ci < FH_RES_MAXM) sm.s_c[ci] = (float)a;
+        __syncthreads();
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < m) {
+          const float c = sm.s_c[i];
+          float z[FH_RES_ROWS];
+          fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+#pragma unroll
+          for (int e = 0; e < FH_RES_ROWS; ++e) wh[e] = fmaf(c, z[e], wh[e]);
+        }
+      }
+    }
+    {
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) wh[e] *= dl[e];
+      __syncthreads();                                   // every thread has read rows_b (w_hat) / the coefficient stage
+      fh_strip_put<FH_RES_ROWS>(rows_a, wh);
+      __syncthreads();
+      fh_dct_strip_core<true, FH_RES_ROWS, true>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.cw);
+      __syncthreads();
+      if (P.fuse == 2) fh_res_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255);
+      fh_res_store_t(rows_b, T, s);
+    }
+    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    // ------------------------------------------------------------------ P4: rows, inverse; q = sy2 p + t; partial p.q
+    {
+      float t[FH_RES_ROWS];
+      fh_res_get_cg(T + soff, t);
+      fh_strip_put<FH_RES_ROWS>(rows_a, t);
+      __syncthreads();
+      fh_dct_strip_core<true, FH_RES_ROWS, true>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.cw);
+      __syncthreads();
+      if (P.fuse == 2) fh_res_conv(rows_b, sm.taps[3], tp[3] >> 8, tp[3] & 255);
+      fh_strip_get<FH_RES_ROWS>(rows_b, t);
+      float a32 = 0.f;
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) {
+        q[e] = fmaf(P.sy2, p[e], t[e] * mk[e]);
+        a32 = fmaf(p[e], q[e], a32);
+      }
+      if (it == 0) {
+        // initial residual r0 = b - A_op x0 (x0 = b); |b|^2 and |r0|^2; p1 = r0     (cg.py:233-237)
+        float rr32 = 0.f, bb32 = 0.f;
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) {
+          r[e] = bv[e] - q[e];
+          rr32 = fmaf(r[e], r[e], rr32);
+          bb32 = fmaf(bv[e], bv[e], bb32);
+          p[e] = r[e];
+        }
+        const double t1 = fh_block_sum((double)rr32, sm.s_red);
+        const double t2 = fh_block_sum((double)bb32, sm.s_red);
+        if (tid == 0) { part_a[s] = t1; part_b[s] = t2; }
+        fh_grid_sync(R.grid_counter, bar_target, nblk);
+        rr = fh_reduce_partials(part_a, (int)nblk, sm.s_red);
+        const double bb = fh_reduce_partials(part_b, (int)nblk, sm.s_red);
+        const double stop = fmax(R.rtol * sqrt(bb), R.atol);
+        stop2 = R.use_stop ? stop * stop : -1.0;
+        resid2 = rr;
+        if (s == 0 && tid == 0) { P.sc[R.image].bnorm2 = bb; P.sc[R.image].stop2 = stop2; }
+        // part_a / part_b are rewritten in P4 / P5 of iteration 1, three barriers from here
+        continue;
+      }
+      const double tot = fh_block_sum((double)a32, sm.s_red);
+      if (tid == 0) part_a[s] = tot;
+    }
+    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    // ------------------------------------------------------------------ P5: step, residual, stop test, new direction
+    {
+      const double pAp = fh_reduce_partials(part_a, (int)nblk, sm.s_red);
+      if (pAp <= 1e-16) { niter = it; break; }                           // cg.py:250
+      const float alpha = (float)(rr / pAp);
+      float rr32 = 0.f;
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) {
+        x[e] = fmaf(alpha, p[e], x[e]);
+        r[e] = fmaf(-alpha, q[e], r[e]);
+        rr32 = fmaf(r[e], r[e], rr32);
+      }
+      const double tot = fh_block_sum((double)rr32, sm.s_red);
+      if (tid == 0) part_b[s] = tot;
+      fh_grid_sync(R.grid_counter, bar_target, nblk);
+      const double rr_new = fh_reduce_partials(part_b, (int)nblk, sm.s_red);
+      resid2 = rr_new;
+      niter = it;
+      const bool converged = (stop2 >= 0.0) && (rr_new <= stop2);
+      if (converged) optimal = 1;
+      if (converged || it >= P.last_allowed) break;                      // cg.py:258-263
+      const float beta = (float)(rr_new / rr);
+      rr = rr_new;
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) p[e] = fmaf(beta, p[e], r[e]);
+    }
+  }
+  if (!z_ready) fh_mbar_wait(&sm.bar, 0);                  // never leave with bulk copies in flight
+  fh_g_put<FH_RES_ROWS>(R.x_out + soff, x);
+  if (s == 0 && tid == 0) {
+    FhCgScalars* w = P.sc + R.image;
+    w->resid2 = resid2;
+    w->rr[0] = rr; w->rr[1] = rr;
+    w->niter = niter;
+    w->optimal = optimal;
+    fh_set_done(w, niter + 1);
+  }
+}

@@ -72,15 +72,18 @@ __device__ __forceinline__ void fh_strip_tables(FhStripSmem<ROWS>& sm, const FhD
 }
 
 // One Stockham radix-4 stage of a 256-point FFT for thread j in [0, 64): sub-transform length Ns -> 4 Ns.
-template <int SIGN, int NS>
+// CONJ: the table holds the forward twiddles and the inverse transform conjugates them on the fly.
+template <int SIGN, int NS, bool CONJ = false>
 __device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, float2* __restrict__ out, int j, const float2* __restrict__ tw) {
   const int k = j & (NS - 1);
   float2 v0 = in[FH_PAD(j)], v1 = in[FH_PAD(j + 64)], v2 = in[FH_PAD(j + 128)], v3 = in[FH_PAD(j + 192)];
   if (NS > 1) {
     constexpr int S = (NS == 4) ? 0 : (NS == 16) ? 1 : 2;   // angle = SIGN * 2 pi k r / (4 Ns), tabulated per thread
-    v1 = fh_cmul(v1, tw[(S * 3 + 0) * 64 + j]);
-    v2 = fh_cmul(v2, tw[(S * 3 + 1) * 64 + j]);
-    v3 = fh_cmul(v3, tw[(S * 3 + 2) * 64 + j]);
+    float2 w1 = tw[(S * 3 + 0) * 64 + j], w2 = tw[(S * 3 + 1) * 64 + j], w3 = tw[(S * 3 + 2) * 64 + j];
+    if (CONJ) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+    v1 = fh_cmul(v1, w1);
+    v2 = fh_cmul(v2, w2);
+    v3 = fh_cmul(v3, w3);
   }
   fh_dft4<SIGN>(v0, v1, v2, v3);
   const int j0 = ((j - k) << 2) + k;
@@ -90,8 +93,13 @@ __device__ __forceinline__ void fh_fft256_stage(const float2* __restrict__ in, f
 // Transform the ROWS rows in `in` (shared, stride FH_RS) into `out` (shared, stride FH_RS; must not alias `in`).
 // COLLECTIVE: every thread of the 256-thread CTA calls it (it contains __syncthreads); `in` must be complete
 // (caller synchronised) and `out` is complete only after the caller's next __syncthreads.
-template <bool INV, int ROWS>
-__device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float* __restrict__ out, FhStripSmem<ROWS>& sm) {
+// Core with explicit buffers: Xb / Yb are the [ROWS/2][FH_FFT_LD] ping-pong buffers, tw the stage twiddles (forward
+// table conjugated on the fly when CONJ), tab the post- (forward) or pre- (inverse) twiddle table.  `in` may alias Xb
+// and `out` may alias Yb: `in` is dead after the first barrier (before any write to Xb) and Yb is dead after the last
+// one (before any write to `out`) -- the resident CG kernel (fh_cg_resident.cuh) relies on this to save 12 KB.
+template <bool INV, int ROWS, bool CONJ>
+__device__ __forceinline__ void fh_dct_strip_core(const float* in, float* out, float2 (*Xb)[FH_FFT_LD], float2 (*Yb)[FH_FFT_LD],
+                                                  const float2* __restrict__ tw, const float2* __restrict__ tab) {
   constexpr int SIGN = INV ? +1 : -1;
   const int f = threadIdx.x >> 6, j = threadIdx.x & 63;
   const bool act = f < ROWS / 2;
@@ -100,8 +108,8 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
   const float* rb = ra + FH_RS;
   float* oa = out + (2 * fc) * FH_RS;
   float* ob = oa + FH_RS;
-  float2* X = sm.X[fc];
-  float2* Y = sm.Y[fc];
+  float2* X = Xb[fc];
+  float2* Y = Yb[fc];
   if (act) {
     float2 v[4];
     if (!INV) {
@@ -123,7 +131,7 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
         const float sn = (k == 0) ? 0.f : sc1;
         const float A = ra[k] * sk + rb[kn] * sn;
         const float B = rb[k] * sk - ra[kn] * sn;
-        v[r] = fh_cmul(sm.tab[k], make_float2(A, B));
+        v[r] = fh_cmul(tab[k], make_float2(A, B));
       }
     }
     fh_dft4<SIGN>(v[0], v[1], v[2], v[3]);             // stage Ns = 1 (no twiddles): out[4 j + r]
@@ -132,11 +140,11 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
     y4[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
   }
   __syncthreads();
-  if (act) fh_fft256_stage<SIGN, 4>(Y, X, j, sm.tw);
+  if (act) fh_fft256_stage<SIGN, 4, CONJ>(Y, X, j, tw);
   __syncthreads();
-  if (act) fh_fft256_stage<SIGN, 16>(X, Y, j, sm.tw);
+  if (act) fh_fft256_stage<SIGN, 16, CONJ>(X, Y, j, tw);
   __syncthreads();
-  if (act) fh_fft256_stage<SIGN, 64>(Y, X, j, sm.tw);
+  if (act) fh_fft256_stage<SIGN, 64, CONJ>(Y, X, j, tw);
   __syncthreads();
   if (act) {
     if (!INV) {
@@ -147,7 +155,7 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
         const float2 zn = X[FH_PAD((FH_N - k) & (FH_N - 1))];
         const float2 va = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         const float2 vb = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-        const float2 p = sm.tab[k];
+        const float2 p = tab[k];
         oa[k] = p.x * va.x - p.y * va.y;
         ob[k] = p.x * vb.x - p.y * vb.y;
       }
@@ -164,14 +172,19 @@ __device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float
   }
 }
 
+template <bool INV, int ROWS>
+__device__ __forceinline__ void fh_dct_strip(const float* __restrict__ in, float* __restrict__ out, FhStripSmem<ROWS>& sm) {
+  fh_dct_strip_core<INV, ROWS, false>(in, out, sm.X, sm.Y, sm.tw, sm.tab);
+}
+
 // ---- strip movers (all 256 threads) -------------------------------------------------------------
 // A strip is ROWS*256 contiguous floats; thread t owns ROWS of them as one vector per 256*W floats:
-//   ROWS = 8: float4 #t and #t+256      ROWS = 4: float4 #t      ROWS = 2: float2 #t
-template <int ROWS> struct FhVec { static constexpr int W = (ROWS >= 4) ? 4 : 2; static constexpr int NV = ROWS / W; };
+//   ROWS = 8: float4 #t and #t+256      ROWS = 4: float4 #t      ROWS = 2: float2 #t      ROWS = 6: float2 #t, #t+256, #t+512
+template <int ROWS> struct FhVec { static constexpr int W = (ROWS % 4 == 0) ? 4 : 2; static constexpr int NV = ROWS / W; };
 
 template <int ROWS>
 __device__ __forceinline__ void fh_g_get(const float* __restrict__ src, float (&r)[ROWS]) {
-  if constexpr (ROWS >= 4) {
+  if constexpr (FhVec<ROWS>::W == 4) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
     for (int h = 0; h < ROWS / 4; ++h) {
@@ -179,18 +192,23 @@ __device__ __forceinline__ void fh_g_get(const float* __restrict__ src, float (&
       r[4 * h] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
     }
   } else {
-    const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x];
-    r[0] = v.x; r[1] = v.y;
+#pragma unroll
+    for (int h = 0; h < ROWS / 2; ++h) {
+      const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+      r[2 * h] = v.x; r[2 * h + 1] = v.y;
+    }
   }
 }
 template <int ROWS>
 __device__ __forceinline__ void fh_g_put(float* __restrict__ dst, const float (&r)[ROWS]) {
-  if constexpr (ROWS >= 4) {
+  if constexpr (FhVec<ROWS>::W == 4) {
     float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
     for (int h = 0; h < ROWS / 4; ++h) d4[threadIdx.x + FH_PASS_THREADS * h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
   } else {
-    reinterpret_cast<float2*>(dst)[threadIdx.x] = make_float2(r[0], r[1]);
+#pragma unroll
+    for (int h = 0; h < ROWS / 2; ++h)
+      reinterpret_cast<float2*>(dst)[threadIdx.x + FH_PASS_THREADS * h] = make_float2(r[2 * h], r[2 * h + 1]);
   }
 }
 // element offset (inside the strip) of the thread's vector h

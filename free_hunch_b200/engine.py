@@ -11,6 +11,7 @@ import torch
 from . import _lib
 
 BASIS_IDENTITY, BASIS_DCT = 0, 1
+CG_AUTO, CG_STREAMING, CG_RESIDENT = 0, 1, 2      # fh_ctx_set_cg_mode (include/free_hunch_b200.h)
 MAX_RANK = 64            # FH_MAXM: rows of Z (two per BFGS space update)
 
 
@@ -58,6 +59,14 @@ class Context:
         out = torch.empty_like(x)
         _lib.check(_lib.lib().fh_dct2(self._h, _ptr(x), _ptr(out), nplanes, 1 if inverse else 0, self.stream()))
         return out
+
+    def set_cg_mode(self, mode):
+        """CG_AUTO (resident kernel whenever it applies), CG_STREAMING (five launches per iteration) or CG_RESIDENT."""
+        _lib.check(_lib.lib().fh_ctx_set_cg_mode(self._h, int(mode)))
+
+    @property
+    def cg_last_mode(self):
+        return _lib.lib().fh_ctx_cg_last_mode(self._h)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -41,6 +41,17 @@ int fh_version(void);
 /* ---- context ------------------------------------------------------------------------------- */
 int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channels, int height, int width, int max_rank);
 int fh_ctx_destroy(fh_ctx* ctx);
+/* Which implementation fh_cg_solve uses in the DCT basis (same algorithm, cg.py:230-292, same results to rounding):
+ *   FH_CG_STREAMING  five launches per iteration, Z streamed from L2/HBM by TMA, any batch, any rank <= 64;
+ *   FH_CG_RESIDENT   one cooperative launch per image and solve, Z resident in shared memory (rank <= 32, operators
+ *                    that fold into the DCT passes: inpainting mask, separable blur);
+ *   FH_CG_AUTO       resident whenever it applies (default).
+ * FH_CG_RESIDENT makes fh_cg_solve fail with FH_EINVAL when the resident kernel does not apply. */
+#define FH_CG_AUTO 0
+#define FH_CG_STREAMING 1
+#define FH_CG_RESIDENT 2
+int fh_ctx_set_cg_mode(fh_ctx* ctx, int mode);
+int fh_ctx_cg_last_mode(const fh_ctx* ctx); /* FH_CG_STREAMING or FH_CG_RESIDENT: path of the last DCT-basis solve */
 
 /* Orthonormal 2-D DCT-II (inverse=0) / DCT-III (inverse=1) of `nplanes` 256x256 planes.
  * Replaces torch_dct.dct_2d / idct_2d(norm='ortho'), call sites online_update_bfgs.py:352-374. */

@@ -226,11 +226,32 @@ def _problem(full_state, oo, which):
 
 
 SY2 = float(np.float32(0.1) * np.float32(0.1))
+FOLDABLE = ("gaussian_blur", "inpainting")       # operators the resident one-launch CG kernel applies to
+
+
+@pytest.fixture(params=["auto", "streaming"])
+def cg_mode(request, E, ctx):
+    """Both CG implementations behind fh_cg_solve: `auto` takes the resident kernel (fh_cg_resident.cuh) for the
+    foldable operators, `streaming` forces the five-launch iteration (fh_cg.cuh)."""
+    ctx.set_cg_mode(E.CG_STREAMING if request.param == "streaming" else E.CG_AUTO)
+    yield request.param
+    ctx.set_cg_mode(E.CG_AUTO)
+
+
+def _check_mode(E, ctx, which, cg_mode):
+    if which not in FOLDABLE and cg_mode == "streaming":
+        pytest.skip("operator always takes the streaming path; covered by the auto run")
+
+
+def _assert_mode(E, ctx, which, cg_mode):
+    want = E.CG_RESIDENT if (which in FOLDABLE and cg_mode == "auto") else E.CG_STREAMING
+    assert ctx.cg_last_mode == want, (which, cg_mode, ctx.cg_last_mode)
 
 
 @pytest.mark.parametrize("which", ["gaussian_blur", "motion_blur", "inpainting", "super_resolution"])
-def test_cg_fixed_iterations(E, ctx, assets, full_state, which):
+def test_cg_fixed_iterations(E, ctx, assets, full_state, which, cg_mode):
     """Same iteration count on both sides: 1e-4 on the CG iterate (north-star tolerance)."""
+    _check_mode(E, ctx, which, cg_mode)
     op, oo = _ops(E, ctx, assets, which)
     y, mu = _problem(full_state, oo, which)
     st, ora, sigma_t = full_state["st"], full_state["ora"], full_state["sig"][-1]
@@ -238,14 +259,16 @@ def test_cg_fixed_iterations(E, ctx, assets, full_state, which):
         mat, info = E.cg_solve(st, op, tt(y), tt(mu), SY2, 1.0, maxiter=100, fixed_iters=iters)
         mo, io = fo.mat_solver(oo, y, mu, ora, sigma_t, fixed_iters=iters)
         e = rel_l2(mat, mo)
-        record("cg_fixed", op=which, iters=iters, err=e, niter=info["niter"][0])
+        record("cg_fixed", op=which, mode=cg_mode, iters=iters, err=e, niter=info["niter"][0])
+        _assert_mode(E, ctx, which, cg_mode)
         assert info["niter"][0] == iters
         assert e < 1e-4, (which, iters, e)
 
 
 @pytest.mark.parametrize("which", ["gaussian_blur", "motion_blur", "inpainting", "super_resolution"])
-def test_cg_reference_rtol_vs_golden(E, ctx, assets, full_state, which):
+def test_cg_reference_rtol_vs_golden(E, ctx, assets, full_state, which, cg_mode):
     """rtol = rtol_func(5.1405, 1) ~ 0.19 as in the reference run that produced the golden `mat`."""
+    _check_mode(E, ctx, which, cg_mode)
     g = full_state["g"]
     op, oo = _ops(E, ctx, assets, which)
     y, mu = _problem(full_state, oo, which)
@@ -255,7 +278,8 @@ def test_cg_reference_rtol_vs_golden(E, ctx, assets, full_state, which):
     key = {"gaussian_blur": "gaussian_blur", "motion_blur": "motion_blur", "inpainting": "inpaint_random", "super_resolution": "sr"}[which]
     ref_n = int(g[f"{key}_niter"])
     e = rel_l2(sub(mat), g[f"{key}_mat"])
-    record("cg_rtol_vs_golden", op=which, err=e, niter=info["niter"][0], ref_niter=ref_n, resid=info["residual_norm"][0])
+    _assert_mode(E, ctx, which, cg_mode)
+    record("cg_rtol_vs_golden", op=which, mode=cg_mode, err=e, niter=info["niter"][0], ref_niter=ref_n, resid=info["residual_norm"][0])
     assert info["optimal"][0]
     assert abs(info["niter"][0] - ref_n) <= max(1, round(0.03 * ref_n)), (info["niter"], ref_n)
     if info["niter"][0] == ref_n:
@@ -269,8 +293,9 @@ def test_cg_reference_rtol_vs_golden(E, ctx, assets, full_state, which):
 
 
 @pytest.mark.parametrize("which", ["gaussian_blur", "inpainting", "super_resolution"])
-def test_cg_converged(E, ctx, assets, full_state, which):
+def test_cg_converged(E, ctx, assets, full_state, which, cg_mode):
     """Tight tolerance: the solution is a well-defined quantity; fp32 must agree with float64 to 1e-4."""
+    _check_mode(E, ctx, which, cg_mode)
     op, oo = _ops(E, ctx, assets, which)
     y, mu = _problem(full_state, oo, which)
     st, ora = full_state["st"], full_state["ora"]
@@ -285,12 +310,13 @@ def test_cg_converged(E, ctx, assets, full_state, which):
     u = u.reshape(y.shape)
     mo = u if which == "inpainting" else oo.AT(u)
     e = rel_l2(mat, mo)
-    record("cg_converged", op=which, err=e, niter=info["niter"][0], ref_niter=io["niter"], optimal=info["optimal"][0])
+    _assert_mode(E, ctx, which, cg_mode)
+    record("cg_converged", op=which, mode=cg_mode, err=e, niter=info["niter"][0], ref_niter=io["niter"], optimal=info["optimal"][0])
     assert info["optimal"][0]
     assert e < 1e-4, (which, e)
 
 
-def test_cg_batch_independent_convergence(E, ctx, assets, full_state):
+def test_cg_batch_independent_convergence(E, ctx, assets, full_state, cg_mode):
     """Two images with different right-hand sides in one batch stop at their own iteration."""
     var = full_state["var"]
     st = E.CovState(ctx, 2, E.BASIS_DCT)
@@ -312,10 +338,11 @@ def test_cg_batch_independent_convergence(E, ctx, assets, full_state):
 
 
 @pytest.mark.parametrize("which", ["gaussian_blur", "motion_blur", "inpainting", "super_resolution"])
-def test_cg_batch4_matches_single(E, ctx, assets, full_state, which):
+def test_cg_batch4_matches_single(E, ctx, assets, full_state, which, cg_mode):
     """B = 4 independent images (per-image y, mu, masks and covariance state) in one call: every image bit-identical to
     its own B = 1 solve, for the folded (mask, separable blur) and the non-folded (motion, x4 SR) operator paths; the
     images stop at different iterations without disturbing each other."""
+    _check_mode(E, ctx, which, cg_mode)
     var = full_state["var"]
     xs, sig, den = full_state["xs"], full_state["sig"], full_state["den"]
     B = 4
@@ -349,8 +376,58 @@ def test_cg_batch4_matches_single(E, ctx, assets, full_state, which):
         mat1, info1 = E.cg_solve(st1, op1, tt(ys[b:b + 1]), tt(mus[b:b + 1]), SY2, rtol, maxiter=600)
         assert info4["niter"][b] == info1["niter"][0] and info4["optimal"][b] == info1["optimal"][0], (which, b, info4, info1)
         assert torch.equal(mat4[b], mat1[0]), (which, b)
-    record("cg_batch4", op=which, niter=info4["niter"])
+    _assert_mode(E, ctx, which, cg_mode)
+    record("cg_batch4", op=which, mode=cg_mode, niter=info4["niter"])
     assert len(set(info4["niter"])) > 1            # the images really stopped at different iterations
+
+
+@pytest.mark.parametrize("which", FOLDABLE)
+def test_cg_resident_matches_streaming(E, ctx, assets, full_state, which):
+    """The two implementations of the same iteration differ only in how partial sums are grouped (128 strips of 6 rows
+    vs 96 of 8): same iterate to fp32 rounding at a fixed count, same stop within one iteration at the reference rtol."""
+    op, oo = _ops(E, ctx, assets, which)
+    y, mu = _problem(full_state, oo, which)
+    st, sigma_t = full_state["st"], full_state["sig"][-1]
+    res = {}
+    for mode in (E.CG_RESIDENT, E.CG_STREAMING):
+        ctx.set_cg_mode(mode)
+        try:
+            res[mode] = (E.cg_solve(st, op, tt(y), tt(mu), SY2, 1.0, maxiter=100, fixed_iters=8),
+                         E.cg_solve(st, op, tt(y), tt(mu), SY2, fo.rtol_func(sigma_t, 1.0), maxiter=5000))
+            assert ctx.cg_last_mode == mode
+        finally:
+            ctx.set_cg_mode(E.CG_AUTO)
+    (f_r, i_fr), (c_r, i_cr) = res[E.CG_RESIDENT]
+    (f_s, i_fs), (c_s, i_cs) = res[E.CG_STREAMING]
+    e = rel_l2(f_r, f_s)
+    record("cg_resident_vs_streaming", op=which, err_fixed8=e, niter=[i_cr["niter"][0], i_cs["niter"][0]],
+           resid=[i_fr["residual_norm"][0], i_fs["residual_norm"][0]])
+    assert e < 2e-5, (which, e)
+    assert abs(i_fr["residual_norm"][0] - i_fs["residual_norm"][0]) <= 1e-3 * i_fs["residual_norm"][0]
+    assert abs(i_cr["niter"][0] - i_cs["niter"][0]) <= max(1, round(0.03 * i_cs["niter"][0]))
+    assert i_cr["optimal"][0] and i_cs["optimal"][0]
+
+
+def test_cg_resident_rank_limit(E, ctx, assets, full_state):
+    """Rank 0 (no Z at all) runs resident; forcing the resident kernel on a non-foldable operator is an error, not a
+    silent switch."""
+    var = full_state["var"]
+    st0 = E.CovState(ctx, 1, E.BASIS_DCT)
+    st0.init(tt(var), S0 ** 2)
+    ora0 = fo.CovarianceOracleDCT(var, S0 ** 2, var.size)
+    op, oo = _ops(E, ctx, assets, "gaussian_blur")
+    y, mu = _problem(full_state, oo, "gaussian_blur")
+    mat, info = E.cg_solve(st0, op, tt(y), tt(mu), SY2, 1.0, maxiter=100, fixed_iters=5)
+    assert ctx.cg_last_mode == E.CG_RESIDENT and st0.rank == 0
+    mo, _ = fo.mat_solver(oo, y, mu, ora0, S0, fixed_iters=5)
+    assert rel_l2(mat, mo) < 1e-4
+    opm, _ = _ops(E, ctx, assets, "motion_blur")
+    ctx.set_cg_mode(E.CG_RESIDENT)
+    try:
+        with pytest.raises(Exception, match="resident"):
+            E.cg_solve(st0, opm, tt(y), tt(mu), SY2, 1.0, maxiter=10, fixed_iters=2)
+    finally:
+        ctx.set_cg_mode(E.CG_AUTO)
 
 
 # ---------------------------------------------------------------------------------------------- mechanism

@@ -209,3 +209,63 @@ def test_fused_dct_basis_path(E, assets, monkeypatch):
         mat_cpu, io = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=2)
         assert info["niter"][0] == 2, name
         assert rel_l2(mat, mat_cpu) < 2e-5, (name, rel_l2(mat, mat_cpu))
+
+
+def _pid_max():
+    try:
+        return int(open("/proc/sys/kernel/pid_max").read())
+    except OSError:
+        return 0
+
+
+@pytest.mark.skipif(_pid_max() < 40000, reason="emulating the 128-CTA cooperative grid needs 32768 concurrent threads (kernel.pid_max too small)")
+def test_resident_cg_kernel(E, assets):
+    """The one-launch resident CG solve (fh_cg_resident.cuh) at 3 x 256 x 256, all 128 CTAs of its cooperative grid
+    emulated concurrently: 6-row strips that straddle channel planes, Z slices resident in shared memory, grid
+    barriers, in-kernel initial residual / step / stop logic -- vs the oracle and vs the five-launch streaming path."""
+    rs = np.random.RandomState(5)
+    var = assets["dct_variance"]
+    shape = (1,) + var.shape
+    s0, s1 = 80.2878, 8.463
+    ctx = E.Context("cpu", max_batch=1)
+    st = E.CovState(ctx, 1, E.BASIS_DCT)
+    st.init(torch.tensor(var), s0 ** 2)
+    ora = fo.CovarianceOracleDCT(var, s0 ** 2, var.size)
+    den = fo.analytic_dct_gaussian_denoiser(var)
+    x = rs.standard_normal(shape) * s0
+    mu = den(x, s0)[0] + 0.02 * np.tanh(x)
+    score = (mu - x) / s0 ** 2
+    m_gpu, _ = st.time_update(torch.tensor(x), torch.tensor(score), s0, s1)
+    m_cpu, _ = ora.update_time_step(x, s0, s1, score)
+    xn = x + (s1 - s0) * (x - mu) / s0
+    mun = den(xn, s1)[0] + 0.02 * np.tanh(xn)
+    st.space_update(torch.tensor(m_cpu), torch.tensor(mun), s1, torch.tensor(x), torch.tensor(xn))
+    ora.update_space_step(m_cpu, mun, s1, x, xn)
+    assert st.rank == 2
+    xc = np.clip(rs.standard_normal(shape), -1, 1)
+    mu0 = 0.3 * xc
+    sy2 = float(np.float32(0.1) * np.float32(0.1))
+    mask = (rs.uniform(size=(256, 256)) > 0.7).astype(np.float32)
+    cases = [
+        ("inpainting", E.Operator.inpaint(ctx, mask), fo.InpaintingOracle(np.broadcast_to(mask, shape), 0.1)),
+        ("gaussian", E.Operator.conv(ctx, assets["gaussian_ks61_std3"], 1), fo.GaussianBlurOracle(assets["gaussian_ks61_std3"], 0.1, otf_dtype=np.complex128)),
+    ]
+    for name, op, oo in cases:
+        if name == "inpainting":
+            y = (xc + 0.1 * rs.standard_normal(shape)) * mask
+        else:
+            ay = oo.A(xc)
+            y = ay + 0.1 * rs.standard_normal(ay.shape)
+        ctx.set_cg_mode(E.CG_RESIDENT)
+        mat, info = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, 1.0, maxiter=50, fixed_iters=2)
+        assert ctx.cg_last_mode == E.CG_RESIDENT
+        mat_cpu, io = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=2)
+        assert info["niter"][0] == 2, name
+        assert rel_l2(mat, mat_cpu) < 2e-5, (name, rel_l2(mat, mat_cpu))
+        if name == "inpainting":
+            ctx.set_cg_mode(E.CG_STREAMING)
+            mat2, info2 = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, 1.0, maxiter=50, fixed_iters=2)
+            assert ctx.cg_last_mode == E.CG_STREAMING
+            assert rel_l2(mat, mat2) < 1e-5
+            assert abs(info["residual_norm"][0] - info2["residual_norm"][0]) <= 1e-4 * info2["residual_norm"][0]
+    ctx.set_cg_mode(E.CG_AUTO)

@@ -2,10 +2,12 @@
 // free_hunch_b200/csrc WITHOUT a GPU (this container has none).  TEST INFRASTRUCTURE ONLY: the product
 // library is built by nvcc for sm_100a and never includes this file.
 //
-// Model: blocks run one after another; the threads of a block are real std::threads that meet at
+// Model (emu::launch): blocks run one after another; the threads of a block are real std::threads that meet at
 // __syncthreads()/__syncwarp() barriers; warp shuffles exchange through a per-warp mailbox.  Static
 // `__shared__` variables become `static` (safe because blocks are sequential); dynamic shared memory is a
 // per-launch buffer.  Device memory is host memory; cudaMalloc/cudaMemcpy are thin wrappers.
+// emu::launch_coop runs ALL blocks of a grid concurrently (one BlockCtx each, small thread stacks) for kernels with
+// grid barriers; such kernels must not use static __shared__ variables.
 #pragma once
 #include <algorithm>
 #include <atomic>
@@ -17,6 +19,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -70,7 +73,8 @@ struct BlockCtx {
 };
 extern thread_local uint3_ t_threadIdx, t_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
-extern BlockCtx* g_block;
+extern thread_local BlockCtx* g_block;
+extern Barrier g_grid_bar;
 extern thread_local int t_linear;
 inline void launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem) {
   BlockCtx ctx;
@@ -81,7 +85,7 @@ inline void launch(const std::function<void()>& body, dim3 grid, dim3 block, siz
   for (int w = 0; w < nwarps; ++w) ctx.warp_bar[w].reset(std::min(32, nthreads - 32 * w));
   ctx.mailbox.assign(nwarps * 32, 0);
   ctx.dyn_smem.assign(smem + 16, 0);
-  g_block = &ctx; g_blockDim = block; g_gridDim = grid;
+  g_blockDim = block; g_gridDim = grid;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -89,6 +93,7 @@ inline void launch(const std::function<void()>& body, dim3 grid, dim3 block, siz
         ts.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t)
           ts.emplace_back([&, t] {
+            g_block = &ctx;
             t_linear = t;
             t_threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y), unsigned(t / (block.x * block.y))};
             t_blockIdx = {bx, by, bz};
@@ -96,7 +101,40 @@ inline void launch(const std::function<void()>& body, dim3 grid, dim3 block, siz
           });
         for (auto& th : ts) th.join();
       }
-  g_block = nullptr;
+}
+// Cooperative launch: every block of the (1-D) grid runs at the same time; fh_grid_sync meets at g_grid_bar.
+inline void launch_coop(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem) {
+  const int nthreads = block.x * block.y * block.z, nwarps = (nthreads + 31) / 32, nblocks = grid.x;
+  std::vector<BlockCtx> ctxs(nblocks);
+  for (auto& ctx : ctxs) {
+    ctx.bar.reset(nthreads);
+    ctx.warp_bar = std::vector<Barrier>(nwarps);
+    for (int w = 0; w < nwarps; ++w) ctx.warp_bar[w].reset(std::min(32, nthreads - 32 * w));
+    ctx.mailbox.assign(nwarps * 32, 0);
+    ctx.dyn_smem.assign(smem + 16, 0);
+  }
+  g_blockDim = block; g_gridDim = grid;
+  g_grid_bar.reset(nblocks);
+  pthread_attr_t attr, saved;
+  pthread_attr_init(&attr); pthread_attr_init(&saved);
+  pthread_getattr_default_np(&saved);
+  pthread_attr_setstacksize(&attr, 256 * 1024);
+  pthread_attr_setguardsize(&attr, 0);         // one mapping per thread: 32768 threads stay under vm.max_map_count
+  pthread_setattr_default_np(&attr);
+  std::vector<std::thread> ts;
+  ts.reserve((size_t)nblocks * nthreads);
+  for (int b = 0; b < nblocks; ++b)
+    for (int t = 0; t < nthreads; ++t)
+      ts.emplace_back([&, b, t] {
+        g_block = &ctxs[b];
+        t_linear = t;
+        t_threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y), unsigned(t / (block.x * block.y))};
+        t_blockIdx = {unsigned(b), 0u, 0u};
+        body();
+      });
+  for (auto& th : ts) th.join();
+  pthread_setattr_default_np(&saved);
+  pthread_attr_destroy(&attr); pthread_attr_destroy(&saved);
 }
 template <typename T>
 inline T shfl_generic(T v, int src_lane) {
@@ -161,6 +199,7 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
   namespace emu {                                               \
   thread_local uint3_ t_threadIdx, t_blockIdx;                  \
   dim3 g_blockDim, g_gridDim;                                   \
-  BlockCtx* g_block = nullptr;                                  \
+  thread_local BlockCtx* g_block = nullptr;                     \
+  Barrier g_grid_bar;                                           \
   thread_local int t_linear = 0;                                \
   }
