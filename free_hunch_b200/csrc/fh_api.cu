@@ -118,6 +118,9 @@ struct fh_ctx {
   double* strip_dots;                 // (max_batch, C*32, FH_MAXM) per-strip partial dots of the fused CG
   int sms;                            // multiprocessors of the device (grid sizing)
   unsigned* grid_counter;             // (max_batch) arrival counters of the resident CG kernel's grid barrier
+  uint4* res_ll;                      // exchange slots of the resident CG kernel (fh_cg_resident.cuh): T, T', dots, p.q, r.r
+  size_t res_ll_bytes;
+  unsigned res_seq;                   // sequence numbers handed out so far (every flag in res_ll is <= res_seq)
   int cg_mode;                        // FH_CG_AUTO / FH_CG_STREAMING / FH_CG_RESIDENT (fh_ctx_set_cg_mode)
   int cg_last_mode;                   // path taken by the last DCT-basis fh_cg_solve
   int res_ok;                         // the resident kernel's cooperative grid fits this device
@@ -207,6 +210,13 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMalloc((void**)&c->strip_dots, (size_t)max_batch * channels * (FH_N / 2) * FH_MAXM * sizeof(double)));
   c->sms = 148;
   FH_CUDA(cudaMalloc((void**)&c->grid_counter, (size_t)max_batch * sizeof(unsigned)));
+  {
+    const size_t nblk = (size_t)(c->d / FH_RES_SLICE) + 1;
+    c->res_ll_bytes = ((size_t)c->d + FH_RES_MAXM * nblk + (FH_RES_MAXM + 2 * nblk) * FH_LL_SPREAD) * sizeof(uint4);   // 2 x d/2, dots, sums, a, b
+    FH_CUDA(cudaMalloc((void**)&c->res_ll, c->res_ll_bytes));
+    FH_CUDA(cudaMemset(c->res_ll, 0, c->res_ll_bytes));
+    c->res_seq = 0;
+  }
   c->cg_mode = FH_CG_AUTO; c->cg_last_mode = 0; c->res_ok = 1;
   c->trace = nullptr;
   if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
@@ -262,7 +272,7 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
-  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace); cudaFree(c->grid_counter);
+  cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace); cudaFree(c->res_ll); cudaFree(c->grid_counter);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
   cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFreeHost((void*)c->mirror_host); cudaFree(c->status);
   free(c);
@@ -796,8 +806,25 @@ static int apply_ASAt(fh_state* s, fh_op* o, const float* p, float* t, void* str
 }
 
 // Cooperative launch of the resident CG kernel (all CTAs co-resident: the kernel has grid barriers).
-static int launch_resident(fh_ctx* c, const FhCgFused& P, const FhCgResident& R, cudaStream_t st) {
+static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaStream_t st) {
   const dim3 grid((unsigned)P.strips_per_image), block(FH_PASS_THREADS);
+  {
+    // exchange buffers and a fresh range of sequence numbers (launches on one ctx are stream-ordered)
+    const size_t nblk = grid.x, half = (size_t)c->d / 2;
+    R.ll_T[0] = c->res_ll; R.ll_T[1] = c->res_ll + half;
+    R.ll_dots = c->res_ll + 2 * half;
+    R.ll_sum = R.ll_dots + FH_RES_MAXM * nblk;
+    R.ll_a = R.ll_sum + FH_RES_MAXM * FH_LL_SPREAD; R.ll_b = R.ll_a + nblk * FH_LL_SPREAD;
+    const unsigned need = (unsigned)P.last_allowed + 2u;
+    if (c->res_seq > 0xffffffffu - need - 1u) {
+      FH_CUDA(cudaMemsetAsync(c->res_ll, 0, c->res_ll_bytes, st));
+      c->res_seq = 0;
+    }
+    R.seq_base = c->res_seq;
+    c->res_seq += need;
+    R.grid_counter = c->grid_counter + R.image;
+    FH_CUDA(cudaMemsetAsync(R.grid_counter, 0, sizeof(unsigned), st));
+  }
   const size_t smem = sizeof(FhResSmem) + (size_t)P.m * FH_RES_SLICE * sizeof(float);
 #ifdef FH_EMU
   (void)c; (void)st;
@@ -842,7 +869,6 @@ static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y,
   FH_LAUNCH(fh_k_cg_rhs, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, amu, P.mask, P.mask_batch, hw, bv, x, n);
   FH_KCHECK();
   FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
-  FH_CUDA(cudaMemsetAsync(c->grid_counter, 0, (size_t)B * sizeof(unsigned), st));
   P.strips_per_image = (int)(s->d / FH_RES_SLICE);
   P.ystrips = P.strips_per_image;
   P.last_allowed = last;
@@ -850,7 +876,7 @@ static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y,
   float* xout = (o->kind == FH_OP_INPAINT) ? mat_out : x;  // inpainting returns u itself
   for (int b = 0; b < B; ++b) {
     FhCgResident R{};
-    R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n; R.grid_counter = c->grid_counter + b;
+    R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n;
     R.rtol = rtol; R.atol = 0.0; R.use_stop = use_stop; R.image = b;
     if ((rc = launch_resident(c, P, R, st))) return rc;
   }
@@ -1098,6 +1124,55 @@ extern "C" int fh_cg_kernel_time(fh_state* s, fh_op* o, int which, int reps, flo
   float ms = 0.f;
   FH_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_out = ms / reps;
+  return FH_OK;
+#endif
+}
+
+// bench.py's roofline for the resident solve: `reps` launches of exactly `iters` CG iterations (+ the initial residual)
+// on image 0, at the state's current rank, right-hand side = whatever the last solve left in the workspace; average
+// device time per LAUNCH (ms) between two CUDA events on `stream`.
+extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, float* ms_out, void* stream) {
+#ifdef FH_EMU
+  (void)s; (void)o; (void)iters; (void)reps; (void)ms_out; (void)stream;
+  FH_FAIL(FH_EINVAL, "not available in the emulation build");
+#else
+  if (!s || !o || !ms_out || reps < 1 || iters < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_resident_time arguments");
+  if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_EINVAL, "resident kernel needs the DCT basis");
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  FhCgFused P = fused_params(s, o, 8);
+  const int saved_mode = c->cg_mode;
+  c->cg_mode = FH_CG_AUTO;
+  const bool ok = resident_applies(s, P);
+  c->cg_mode = saved_mode;
+  if (!ok) FH_FAIL(FH_EINVAL, "resident kernel does not apply to this state / operator");
+  P.sc = c->cg_sc; P.sy2 = 0.01f; P.last_allowed = iters;
+  P.strips_per_image = (int)(s->d / FH_RES_SLICE); P.ystrips = P.strips_per_image;
+  FhCgResident R{};
+  R.bvec = c->cgv[0]; R.x_out = c->cgv[5]; R.rtol = 1.0; R.atol = 0.0; R.use_stop = 0; R.image = 0;
+  R.timing = 1;                         // a converged workspace must not end the run early (the arithmetic is the same)
+  cudaEvent_t e0, e1;
+  FH_CUDA(cudaEventCreate(&e0)); FH_CUDA(cudaEventCreate(&e1));
+  int rc = FH_OK;
+  for (int pass = 0; pass < 2 && rc == FH_OK; ++pass) {              // pass 0 warms up
+    if (pass) FH_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < (pass ? reps : 1) && rc == FH_OK; ++i) {
+      FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, sizeof(FhCgScalars), st));
+      rc = launch_resident(c, P, R, st);
+    }
+    if (pass) FH_CUDA(cudaEventRecord(e1, st));
+  }
+  if (rc) return rc;
+  FH_KCHECK();
+  FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+  FH_CUDA(cudaEventSynchronize(e1));
+  FH_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  FH_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (c->cg_sc_host[0].niter != iters)
+    FH_FAIL(FH_ESTATE, "timing run broke off after %d of %d iterations (workspace holds no usable right-hand side)", c->cg_sc_host[0].niter, iters);
   *ms_out = ms / reps;
   return FH_OK;
 #endif

@@ -12,18 +12,25 @@
 //     bulk copy per row, issued once in the prologue), for the whole solve
 // and the only global traffic of an iteration is the half-transformed plane T that has to be transposed between the
 // row pass and the column pass of the 2-D DCT (written transposed, read back after a grid barrier: 4 x 786 KB through
-// L2) plus a few KB of fp64 partial sums.  An iteration is five phases separated by five grid barriers:
+// L2) plus a few KB of fp64 partial sums.  An iteration is five phases with five all-to-all exchanges between them:
 //
-//   P1  w = mask.p | row-blur^T p ; row DCT ; transposed store -> T                                   | barrier
-//   P2  T -> column blur^T ; column DCT = w_hat (registers) ; partial Z (delta w_hat) -> partials     | barrier
-//   P3  coef = Gs sum(partials) ; delta (w_hat + Z^T coef) ; column IDCT ; column blur ; T (transp.)  | barrier
-//   P4  T -> row IDCT ; row blur | mask = t ; q = sy2 p + t ; partial p.q                              | barrier
-//   P5  alpha = rr / sum ; (p.Ap <= 1e-16 -> break) ; x += alpha p ; r -= alpha q ; partial r.r        | barrier
+//   P1  w = mask.p | row-blur^T p ; row DCT ; transposed store -> T                                   | exchange T
+//   P2  T -> column blur^T ; column DCT = w_hat (registers) ; partial Z (delta w_hat) -> partials     | exchange dots
+//   P3  coef = Gs sum(partials) ; delta (w_hat + Z^T coef) ; column IDCT ; column blur ; T' (transp.) | exchange T'
+//   P4  T' -> row IDCT ; row blur | mask = t ; q = sy2 p + t ; partial p.q                             | exchange p.q
+//   P5  alpha = rr / sum ; (p.Ap <= 1e-16 -> break) ; x += alpha p ; r -= alpha q ; partial r.r        | exchange r.r
 //       rr' = sum ; stop test ; beta = rr'/rr ; p = r + beta p
 //
+// Exchanges use a flag-in-data protocol instead of grid barriers (the first version had five barriers per iteration:
+// release fence + atomic + acquire polling cost 1.1-1.7 us each, 7 of 20 us): every 16-byte slot carries two 32-bit
+// payload words and two copies of a sequence number (= iteration + 1), written with ONE vector store; the consumer
+// polls the slot itself until both flags match.  Payload and flag arrive together, so there is no fence, no atomic and
+// no separate barrier round trip, and a consumer starts as soon as ITS inputs are there.  Reuse of a slot is safe
+// without further synchronisation because every exchange is all-to-all: a CTA can only pass exchange k once every CTA
+// has produced its part of k, i.e. has finished reading exchange k-1 (see the hazard notes in the kernel).
 // All scalars are fixed-order sums of the same partials in every CTA (bit-identical), so every CTA takes the same
 // branch and the loop needs no flag.  The initial residual r0 = b - A_op b (x0 = b, cg.py:233-235) is iteration 0 of the
-// same loop.  Barrier waits are bounded (__trap instead of a hang).
+// same loop.  Polls are bounded (__trap instead of a hang).
 #pragma once
 #include "fh_cg.cuh"
 
@@ -51,13 +58,84 @@ struct FhResSmem {
 struct FhCgResident {
   const float* bvec;           // (d) right-hand side b (pixel layout); x0 = b
   float* x_out;                // (d) solution
-  unsigned* grid_counter;      // zeroed by the host before the launch
+  uint4* ll_T[2];              // (d/2) slots each: half-transformed plane, forward / inverse (slot = 2 floats + 2 flags)
+  uint4* ll_dots;              // [FH_RES_MAXM][grid] slots: per-CTA partial of (Z (delta w_hat))_i as a double
+  uint4* ll_sum;               // [FH_RES_MAXM] slots, FH_LL_SPREAD apart: (Z (delta w_hat))_i summed over the grid by row i's owner CTA
+  uint4* ll_a;                 // [grid] slots, FH_LL_SPREAD apart: per-CTA partial of p.q  (iteration 0: |r0|^2)
+  uint4* ll_b;                 // [grid] slots, FH_LL_SPREAD apart: per-CTA partial of r.r  (iteration 0: |b|^2)
+  unsigned* grid_counter;      // arrival counter of the grid barrier, zeroed by the host before the launch
+  unsigned seq_base;           // sequence numbers of this launch are seq_base + 1 ... ; every flag in the buffers is
+                               // <= seq_base (the host hands out increasing ranges and zeroes the buffers on wrap-around)
   double rtol, atol;
   int use_stop;                // 0: run exactly `last_allowed` iterations
   int image;                   // which image of the batch (offsets into the state / scalars)
+  int timing;                  // fh_cg_resident_time only: keep iterating through the p.Ap <= 1e-16 break
 };
 
-// ---- grid barrier -----------------------------------------------------------------------------------------
+// ---- flag-in-data exchange ---------------------------------------------------------------------------------
+// slot = {payload0, seq, payload1, seq}: one 16-byte vector store / load (each 8-byte half carries its own flag, so
+// the protocol holds even if the memory system splits the access).
+#define FH_LL_SPIN_LIMIT 8000000u
+#ifdef FH_EMU
+#include <atomic>
+static inline void fh_ll_store(uint4* p, unsigned a, unsigned b, unsigned seq) {
+  volatile unsigned* q = reinterpret_cast<volatile unsigned*>(p);
+  q[0] = a; q[2] = b;
+  std::atomic_thread_fence(std::memory_order_release);
+  q[1] = seq; q[3] = seq;
+}
+static inline uint4 fh_ll_load(const uint4* p) {
+  volatile const unsigned* q = reinterpret_cast<volatile const unsigned*>(p);
+  uint4 v;
+  v.y = q[1]; v.w = q[3];
+  std::atomic_thread_fence(std::memory_order_acquire);
+  v.x = q[0]; v.z = q[2];
+  return v;
+}
+static inline void fh_ll_relax() { std::this_thread::yield(); }
+static inline void fh_ll_fail() { std::abort(); }
+static inline unsigned fh_f2u(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float fh_u2f(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline void fh_d2u(double d, unsigned& lo, unsigned& hi) { unsigned long long b; std::memcpy(&b, &d, 8); lo = (unsigned)b; hi = (unsigned)(b >> 32); }
+static inline double fh_u2d(unsigned lo, unsigned hi) { unsigned long long b = ((unsigned long long)hi << 32) | lo; double d; std::memcpy(&d, &b, 8); return d; }
+#else
+__device__ __forceinline__ void fh_ll_store(uint4* p, unsigned a, unsigned b, unsigned seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(seq), "r"(b), "r"(seq) : "memory");
+}
+__device__ __forceinline__ uint4 fh_ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fh_ll_relax() {}
+__device__ __forceinline__ void fh_ll_fail() { __trap(); }
+__device__ __forceinline__ unsigned fh_f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float fh_u2f(unsigned u) { return __uint_as_float(u); }
+__device__ __forceinline__ void fh_d2u(double d, unsigned& lo, unsigned& hi) { lo = (unsigned)__double2loint(d); hi = (unsigned)__double2hiint(d); }
+__device__ __forceinline__ double fh_u2d(unsigned lo, unsigned hi) { return __hiloint2double((int)hi, (int)lo); }
+#endif
+
+// N slots p[0], p[stride], ... : all loads are issued before the first flag is looked at; slots that are not there
+// yet are re-polled one by one (bounded).
+template <int N>
+__device__ __forceinline__ void fh_ll_wait(const uint4* p, int stride, unsigned seq, uint4 (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = fh_ll_load(p + (size_t)i * stride);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    unsigned spins = 0;
+    while (v[i].y != seq || v[i].w != seq) {
+      if (++spins > FH_LL_SPIN_LIMIT) fh_ll_fail();     // seconds: a producer is missing -> fail the launch, do not hang
+      fh_ll_relax();
+      v[i] = fh_ll_load(p + (size_t)i * stride);
+    }
+  }
+}
+
+// ---- grid barrier (used for the two plane exchanges when FH_RES_T_LL == 0) ---------------------------------------
+#ifndef FH_RES_T_LL
+#define FH_RES_T_LL 0
+#endif
 #ifdef FH_EMU
 static inline void fh_grid_sync(unsigned*, unsigned&, unsigned) {
   __syncthreads();
@@ -77,21 +155,70 @@ __device__ __forceinline__ void fh_grid_sync(unsigned* counter, unsigned& target
     for (unsigned spins = 0;; ++spins) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (v >= target) break;
-      if (spins > 20000000u) __trap();                 // seconds: a CTA is missing -> fail the launch, do not hang
+      if (spins > FH_LL_SPIN_LIMIT) __trap();          // seconds: a CTA is missing -> fail the launch, do not hang
     }
   }
   __syncthreads();
 }
 template <typename T> __device__ __forceinline__ T fh_ld_cg(const T* p) { return __ldcg(p); }
 #endif
-
-// the thread's 6 elements of a strip as 3 float2 (#t, #t+256, #t+512), read past L1 (data written by other CTAs)
+// plain (flag-less) variants of the plane exchange: float2 per row pair, read past L1 after the grid barrier
 __device__ __forceinline__ void fh_res_get_cg(const float* src, float (&r)[FH_RES_ROWS]) {
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
     const float2 v = fh_ld_cg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
   }
+}
+__device__ __forceinline__ void fh_res_store_t(const float* sm_rows, float* __restrict__ T, int s) {
+  const int k = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int g = FH_RES_ROWS * s + 2 * h;
+    float* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
+    *reinterpret_cast<float2*>(d) = make_float2(sm_rows[(2 * h) * FH_RS + k], sm_rows[(2 * h + 1) * FH_RS + k]);
+  }
+}
+
+// The thread's 6 elements (3 pairs: slots #t, #t+256, #t+512) of its strip of an exchanged plane.
+__device__ __forceinline__ void fh_res_get_ll(const uint4* strip, unsigned seq, float (&r)[FH_RES_ROWS]) {
+  uint4 v[FH_RES_ROWS / 2];
+  fh_ll_wait<FH_RES_ROWS / 2>(strip + threadIdx.x, FH_PASS_THREADS, seq, v);
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) { r[2 * h] = fh_u2f(v[h].x); r[2 * h + 1] = fh_u2f(v[h].z); }
+}
+
+// Transposed store of strip s (global rows 6s .. 6s+5 of the 768) into the exchange plane: element (row g, column k)
+// goes to row (plane(g), k), column g & 255 of the transposed plane; the pair (g, g+1) is one slot.  Row pairs never
+// straddle a plane (256 is even); the strip itself may.
+__device__ __forceinline__ void fh_res_store_t_ll(const float* sm_rows, uint4* T, int s, unsigned seq) {
+  const int k = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int g = FH_RES_ROWS * s + 2 * h;
+    uint4* d = T + ((size_t)(g >> 8) * FH_N + k) * (FH_N / 2) + ((g & (FH_N - 1)) >> 1);
+    fh_ll_store(d, fh_f2u(sm_rows[(2 * h) * FH_RS + k]), fh_f2u(sm_rows[(2 * h + 1) * FH_RS + k]), seq);
+  }
+}
+
+// Sum of one double per CTA over the grid: thread t < nblk polls slot t, fixed-order block sum (bit-identical in
+// every CTA).  Contains __syncthreads.
+// Slots that many CTAs poll at once sit FH_LL_SPREAD slots (128 bytes) apart, so that they land in different L2 slices:
+// with 2 KB of contiguous slots polled by 16 384 threads one slice serialises everything (measured: 10 us per exchange).
+#define FH_LL_SPREAD 8
+__device__ __forceinline__ double fh_ll_reduce(const uint4* slots, int nblk, unsigned seq, double* s_red) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += FH_PASS_THREADS) {
+    uint4 w[1];
+    fh_ll_wait<1>(slots + (size_t)i * FH_LL_SPREAD, 0, seq, w);
+    v += fh_u2d(w[0].x, w[0].z);
+  }
+  return fh_block_sum(v, s_red);
+}
+__device__ __forceinline__ void fh_ll_put_double(uint4* slot, double v, unsigned seq) {
+  unsigned lo, hi;
+  fh_d2u(v, lo, hi);
+  fh_ll_store(slot, lo, hi, seq);
 }
 
 // the thread's 6 elements of a contiguous (unpadded) 1536-float slice in shared memory: conflict-free LDS.64
@@ -100,18 +227,6 @@ __device__ __forceinline__ void fh_strip_get_flat(const float* src, float (&r)[F
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
     const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
-  }
-}
-
-// transposed store of strip s (global rows 6s .. 6s+5 of the 768): T[plane][k][row] = rows[row][k].  Row pairs never
-// straddle a plane (256 is even); the strip itself may.
-__device__ __forceinline__ void fh_res_store_t(const float* sm_rows, float* __restrict__ T, int s) {
-  const int k = threadIdx.x;
-#pragma unroll
-  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-    const int g = FH_RES_ROWS * s + 2 * h;
-    float* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
-    *reinterpret_cast<float2*>(d) = make_float2(sm_rows[(2 * h) * FH_RS + k], sm_rows[(2 * h + 1) * FH_RS + k]);
   }
 }
 
@@ -184,6 +299,8 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   FH_DYN_SMEM(unsigned char, smem_raw);
   FhResSmem& sm = *reinterpret_cast<FhResSmem*>(smem_raw);
   float* Zs = reinterpret_cast<float*>(smem_raw + sizeof(FhResSmem));       // [m][1536]
+  // rows_a aliases the FFT buffer X and rows_b aliases Y: a strip is put into rows_a only after the barrier that follows
+  // the last read of X, and Y is rewritten by the next transform only after the barrier that follows the put.
   float* rows_a = reinterpret_cast<float*>(sm.X);
   float* rows_b = reinterpret_cast<float*>(sm.Y);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,7 +310,6 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   const long d = (long)nblk * FH_RES_SLICE;
   const size_t img = (size_t)R.image * d;
   const size_t soff = (size_t)s * FH_RES_SLICE;
-  unsigned bar_target = 0;
 
   // ---- prologue: Z slices by TMA (one 6 KB bulk copy per row), tables, taps, per-solve constants in registers ----
   if (tid == 0) { fh_mbar_init(&sm.bar, 1); fh_mbar_fence_init(); }
@@ -237,10 +353,10 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) gs[u] = (cpart + 8 * u < m) ? g[cpart + 8 * u] : 0.0;
   }
-  double* dots_part = P.dots_partial + (size_t)R.image * P.strips_per_image * FH_MAXM;    // [nblk][FH_MAXM]
-  double* part_a = P.part_a + (size_t)R.image * P.ystrips;
-  double* part_b = P.part_b + (size_t)R.image * P.ystrips;
-  float* T = P.T + img;
+  unsigned bar_target = 0;
+  float* Tp = P.T + img;                                                   // plain plane (FH_RES_T_LL == 0)
+  const uint4* my_T0 = R.ll_T[0] + (size_t)s * (FH_RES_SLICE / 2);          // this CTA's strip of the exchanged planes
+  const uint4* my_T1 = R.ll_T[1] + (size_t)s * (FH_RES_SLICE / 2);
   __syncthreads();
 
   float x[FH_RES_ROWS], r[FH_RES_ROWS], p[FH_RES_ROWS], q[FH_RES_ROWS];
@@ -250,8 +366,14 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   int niter = 0, optimal = 0;
   bool z_ready = (m == 0);
 
+#define FH_RTRACE(slot) do { if (it == 3) FH_TRACE(P, 5, slot); } while (0)
   for (int it = 0;; ++it) {
+    const unsigned seq = R.seq_base + (unsigned)it + 1u;
+    // Slot reuse: T (forward) is rewritten in P1 of it+1, after this CTA has passed the r.r exchange of `it`, which every
+    // CTA joins only after its own P2 read of T; likewise T' (P3 / P4, p.q exchange), the dot slots (P2 / P3, then p.q and
+    // r.r), ll_a (P4 / P5, r.r) and ll_b (P5, then the dot exchange of it+1).
     // ------------------------------------------------------------------ P1: rows, forward
+    FH_RTRACE(0);
     {
       float w[FH_RES_ROWS];
 #pragma unroll
@@ -261,14 +383,26 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
       if (P.fuse == 2) fh_res_conv(rows_a, sm.taps[0], tp[0] >> 8, tp[0] & 255);
       fh_dct_strip_core<false, FH_RES_ROWS, false>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.post);
       __syncthreads();
-      fh_res_store_t(rows_b, T, s);
+#if FH_RES_T_LL
+      fh_res_store_t_ll(rows_b, R.ll_T[0], s, seq);
+#else
+      fh_res_store_t(rows_b, Tp, s);
+#endif
     }
+    FH_RTRACE(1);
+#if !FH_RES_T_LL
     fh_grid_sync(R.grid_counter, bar_target, nblk);
+#endif
     // ------------------------------------------------------------------ P2: columns, forward; partial Z (delta w_hat)
     float wh[FH_RES_ROWS];
     {
       float t[FH_RES_ROWS];
-      fh_res_get_cg(T + soff, t);
+#if FH_RES_T_LL
+      fh_res_get_ll(my_T0, seq, t);
+#else
+      fh_res_get_cg(Tp + soff, t);
+#endif
+      FH_RTRACE(2);
       fh_strip_put<FH_RES_ROWS>(rows_a, t);
       __syncthreads();
       if (P.fuse == 2) fh_res_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255);
@@ -276,6 +410,7 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
       __syncthreads();
       fh_strip_get<FH_RES_ROWS>(rows_b, wh);
     }
+    FH_RTRACE(3);
     if (m > 0) {
       if (!z_ready) { fh_mbar_wait(&sm.bar, 0); z_ready = true; }
       float wd[FH_RES_ROWS];
@@ -299,26 +434,47 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         double t = 0.0;
 #pragma unroll
         for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t += (double)sm.s_w[wv][tid];
-        dots_part[(size_t)s * FH_MAXM + tid] = t;
+        fh_ll_put_double(R.ll_dots + (size_t)tid * nblk + s, t, seq);
       }
-      fh_grid_sync(R.grid_counter, bar_target, nblk);
+      FH_RTRACE(4);
       // ---------------------------------------------------------------- P3: coef = Gs sum(partials); w_hat + Z^T coef
       {
-        double t = 0.0;
-        if (ci < m) {
-          const double* col = dots_part + ci;
-          for (int k0 = cpart; k0 < (int)nblk; k0 += 64) {
-            double v[8];
+        // Two hops, each a few KB: row i's partials (one slot per CTA, contiguous) are summed in a fixed order by warp 0
+        // of its owner CTA (i * grid / 32: spread over the chip), which publishes the total; then warp 0 of EVERY CTA
+        // fetches the m totals.  (One hop -- every CTA summing all grid x m partials itself -- moves 8 MB through L2 per
+        // iteration and took 2.2 us.)
+        const int own_step = (int)nblk / FH_RES_MAXM > 0 ? (int)nblk / FH_RES_MAXM : 1;
+        if (warp == 0) {
+          if (s % own_step == 0 && s / own_step < m) {
+            const int i = s / own_step;
+            const uint4* col = R.ll_dots + (size_t)i * nblk;
+            double t = 0.0;
+            for (int k0 = lane; k0 < (int)nblk; k0 += 128) {
+              if (k0 + 96 < (int)nblk) {
+                uint4 v[4];
+                fh_ll_wait<4>(col + k0, 32, seq, v);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (k0 + 8 * u < (int)nblk) ? fh_ld_cg(col + (size_t)(k0 + 8 * u) * FH_MAXM) : 0.0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t += v[u];
+                for (int u = 0; u < 4; ++u) t += fh_u2d(v[u].x, v[u].z);
+              } else {
+                for (int k = k0; k < (int)nblk; k += 32) {
+                  uint4 v[1];
+                  fh_ll_wait<1>(col + k, 0, seq, v);
+                  t += fh_u2d(v[0].x, v[0].z);
+                }
+              }
+            }
+            t = fh_warp_sum(t);
+            if (lane == 0) fh_ll_put_double(R.ll_sum + (size_t)i * FH_LL_SPREAD, t, seq);
           }
+          double tot = 0.0;
+          if (lane < m) {
+            uint4 v[1];
+            fh_ll_wait<1>(R.ll_sum + (size_t)lane * FH_LL_SPREAD, 0, seq, v);
+            tot = fh_u2d(v[0].x, v[0].z);
+          }
+          sm.s_sum[lane] = tot;
         }
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-        t += __shfl_xor_sync(0xffffffffu, t, 4);
-        if (cpart == 0 && ci < FH_RES_MAXM) sm.s_sum[ci] = (ci < m) ? t : 0.0;
+        FH_RTRACE(5);
         __syncthreads();
         double a = 0.0;
 #pragma unroll
@@ -329,6 +485,7 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         if (cpart == 0 && ci < FH_RES_MAXM) sm.s_c[ci] = (float)a;
         __syncthreads();
       }
+      FH_RTRACE(6);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         if (i < m) {
@@ -340,22 +497,34 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         }
       }
     }
+    FH_RTRACE(7);
     {
 #pragma unroll
       for (int e = 0; e < FH_RES_ROWS; ++e) wh[e] *= dl[e];
-      __syncthreads();                                   // every thread has read rows_b (w_hat) / the coefficient stage
       fh_strip_put<FH_RES_ROWS>(rows_a, wh);
       __syncthreads();
       fh_dct_strip_core<true, FH_RES_ROWS, true>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.cw);
       __syncthreads();
       if (P.fuse == 2) fh_res_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255);
-      fh_res_store_t(rows_b, T, s);
+#if FH_RES_T_LL
+      fh_res_store_t_ll(rows_b, R.ll_T[1], s, seq);
+#else
+      fh_res_store_t(rows_b, Tp, s);
+#endif
     }
+    FH_RTRACE(8);
+#if !FH_RES_T_LL
     fh_grid_sync(R.grid_counter, bar_target, nblk);
+#endif
     // ------------------------------------------------------------------ P4: rows, inverse; q = sy2 p + t; partial p.q
     {
       float t[FH_RES_ROWS];
-      fh_res_get_cg(T + soff, t);
+#if FH_RES_T_LL
+      fh_res_get_ll(my_T1, seq, t);
+#else
+      fh_res_get_cg(Tp + soff, t);
+#endif
+      FH_RTRACE(9);
       fh_strip_put<FH_RES_ROWS>(rows_a, t);
       __syncthreads();
       fh_dct_strip_core<true, FH_RES_ROWS, true>(rows_a, rows_b, sm.X, sm.Y, sm.tw, sm.cw);
@@ -380,25 +549,24 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         }
         const double t1 = fh_block_sum((double)rr32, sm.s_red);
         const double t2 = fh_block_sum((double)bb32, sm.s_red);
-        if (tid == 0) { part_a[s] = t1; part_b[s] = t2; }
-        fh_grid_sync(R.grid_counter, bar_target, nblk);
-        rr = fh_reduce_partials(part_a, (int)nblk, sm.s_red);
-        const double bb = fh_reduce_partials(part_b, (int)nblk, sm.s_red);
+        if (tid == 0) { fh_ll_put_double(R.ll_a + (size_t)s * FH_LL_SPREAD, t1, seq); fh_ll_put_double(R.ll_b + (size_t)s * FH_LL_SPREAD, t2, seq); }
+        rr = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red);
+        const double bb = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red);
         const double stop = fmax(R.rtol * sqrt(bb), R.atol);
         stop2 = R.use_stop ? stop * stop : -1.0;
         resid2 = rr;
         if (s == 0 && tid == 0) { P.sc[R.image].bnorm2 = bb; P.sc[R.image].stop2 = stop2; }
-        // part_a / part_b are rewritten in P4 / P5 of iteration 1, three barriers from here
         continue;
       }
       const double tot = fh_block_sum((double)a32, sm.s_red);
-      if (tid == 0) part_a[s] = tot;
+      if (tid == 0) fh_ll_put_double(R.ll_a + (size_t)s * FH_LL_SPREAD, tot, seq);
     }
-    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    FH_RTRACE(10);
     // ------------------------------------------------------------------ P5: step, residual, stop test, new direction
     {
-      const double pAp = fh_reduce_partials(part_a, (int)nblk, sm.s_red);
-      if (pAp <= 1e-16) { niter = it; break; }                           // cg.py:250
+      const double pAp = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red);
+      FH_RTRACE(12);
+      if (pAp <= 1e-16 && !R.timing) { niter = it; break; }              // cg.py:250
       const float alpha = (float)(rr / pAp);
       float rr32 = 0.f;
 #pragma unroll
@@ -408,9 +576,10 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         rr32 = fmaf(r[e], r[e], rr32);
       }
       const double tot = fh_block_sum((double)rr32, sm.s_red);
-      if (tid == 0) part_b[s] = tot;
-      fh_grid_sync(R.grid_counter, bar_target, nblk);
-      const double rr_new = fh_reduce_partials(part_b, (int)nblk, sm.s_red);
+      if (tid == 0) fh_ll_put_double(R.ll_b + (size_t)s * FH_LL_SPREAD, tot, seq);
+      FH_RTRACE(13);
+      const double rr_new = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red);
+      FH_RTRACE(15);
       resid2 = rr_new;
       niter = it;
       const bool converged = (stop2 >= 0.0) && (rr_new <= stop2);

@@ -250,6 +250,15 @@ def kernel_profile():
 
 
 CG_KERNELS = ("fh_k_cg_fwd_rows", "fh_k_cg_fwd_cols", "fh_k_cg_inv_cols", "fh_k_cg_inv_rows", "fh_k_cg_xr")
+CG_RESIDENT_KERNEL = "fh_k_cg_resident"
+
+
+def cg_resident_time(state, op, iters=200, reps=5):
+    """Average device time in ms of one launch of the resident CG kernel running exactly `iters` iterations of image 0
+    at the state's current rank (bench.py's roofline)."""
+    ms = ctypes.c_float()
+    _lib.check(_lib.lib().fh_cg_resident_time(state._h, op._h, int(iters), int(reps), ctypes.byref(ms), state.ctx.stream()))
+    return float(ms.value)
 
 
 def cg_kernel_time(state, op, which, reps=200):

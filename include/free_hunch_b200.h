@@ -124,6 +124,9 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
  * iteration at the state's current rank, CUDA events on `stream`.  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols,
  * 3 inv_rows, 4 xr.  Only for operators that fold into the DCT passes (inpainting, separable blur). */
 int fh_cg_kernel_time(fh_state* st, fh_op* op, int which, int reps, float* ms_out, void* stream);
+/* The same for the resident solve (FH_CG_RESIDENT): average device time (ms) of `reps` launches that each run exactly
+ * `iters` CG iterations of image 0 at the state's current rank. */
+int fh_cg_resident_time(fh_state* st, fh_op* op, int iters, int reps, float* ms_out, void* stream);
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 long long fh_launch_count(int reset);
 /* Per-kernel device timing for bench.py: while enabled every launch is bracketed by a cudaEvent pair on its
