@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-unet-timing", action="store_true", help="skip the separate timing of the random-init PyTorch UNet")
+    ap.add_argument("--blocking-host-reads", action="store_true",
+                    help="run the mechanism with the reference's per-call host reads (allclose / std / CG flags) instead of deferring them")
     ap.add_argument("--batched", type=int, default=16, help="also report a B-images-per-GPU step (HBM-bound regime); 0 = off")
     return ap.parse_args()
 
@@ -96,12 +98,18 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples taken before this call (nvidia-smi start-up, warm-up steps) are not reported."""
+        self.first = len(self.rows)
 
     def start(self):
+        if os.environ.get("FH_BENCH_NO_CLOCKS"):          # diagnostics only: measure the sampler's own interference
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "250"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -119,7 +127,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             if len(r) < 8:
                 continue
             try:
@@ -296,13 +304,36 @@ def run_b200(a, assets):
             data_dim=3 * 256 * 256, max_vector_count=100000, dct_variance=var, image_base_covariance="dct_diagonal",
             denoiser_mean_error_threshold=0.2, use_analytical_score_time_update=True, project_to_diagonal=False,
             space_step_update_threshold=10.0, space_step_update_lower_threshold=1.0, max_rtol=1.0, do_space_updates=True,
-            use_analytic_var_at_end=False, solver_type="customcuda", use_rtol_func=True, device=dev, batch=B, timer=timer)
+            use_analytic_var_at_end=False, solver_type="customcuda", use_rtol_func=True, device=dev, batch=B, timer=timer,
+            defer_host_reads=not a.blocking_host_reads)
 
     nets = {}
 
+    host_trace = []
+
     def sample(op, y_dev, noise_dev, timer=None):
         B = y_dev.shape[0]
+        t_mk = time.perf_counter()
         mech = make_mechanism(op, B, timer)
+        if os.environ.get("FH_BENCH_TRACE_HOST"):            # diagnostics: host seconds per mechanism call
+            inner = mech.x0_mean_update
+            host_trace.clear()
+            host_trace.append(("make_mechanism", time.perf_counter() - t_mk))
+
+            def traced(*args, **kw):
+                t0 = time.perf_counter()
+                out = inner(*args, **kw)
+                host_trace.append((f"call{len(host_trace)}", time.perf_counter() - t0))
+                return out
+            mech.x0_mean_update = traced
+            fin = mech.finalize
+
+            def traced_fin():
+                t0 = time.perf_counter()
+                out = fin()
+                host_trace.append(("finalize", time.perf_counter() - t0))
+                return out
+            mech.finalize = traced_fin
         ctx = mech.covariance_model.ctx
         if id(ctx) not in nets:
             nets[id(ctx)] = AnalyticDCTGaussianDenoiser(var, ctx)
@@ -321,19 +352,30 @@ def run_b200(a, assets):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    import gc
     B = a.batch
     n_iter = a.warmup + a.steps + 2                # warm-up, timed steps (both arms sample the same images), phase-timed step, kernel-profiled step
     problems = [make_problem(s, B) for s in range(n_iter)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # 256 MiB > 126 MB L2
     it = 0
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML attach, ~1-3 s) stalls the GPU for whole seconds when it
+    # falls into a timed step; only samples taken after clocks.mark() are reported
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(a.warmup):
         op, y, noise = problems[it]; it += 1
         sample(op, torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev))
     # ---- device-resident arm: inputs already in HBM, CUDA events per step, L2 flushed between steps
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    if rank == 0 and not clocks.rows:
+        time.sleep(2.0)                                   # make sure the sampler is past its start-up
+    # a cyclic-GC pass over the interpreter's objects is tens of ms of host time in the middle of a 80 ms step: collect
+    # now, then keep the collector off while steps are being timed
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     barrier()
+    clocks.mark()
     E.launch_count(reset=True)
     ms_steps, cg_iters, ranks_k = [], [], []
     for _ in range(a.steps):
@@ -342,11 +384,21 @@ def run_b200(a, assets):
         flush.fill_(1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dbg = PhaseTimer(True) if os.environ.get("FH_BENCH_TRACE_PHASES") else None
         e0.record()
-        x, mech = sample(op, y_dev, noise_dev)
+        x, mech = sample(op, y_dev, noise_dev, dbg)
         e1.record()
         e1.synchronize()
         ms_steps.append(e0.elapsed_time(e1))
+        if host_trace:
+            top = sorted(host_trace, key=lambda kv: -kv[1])[:4]
+            print(f"[host] step {len(ms_steps)} {ms_steps[-1]:.1f} ms; host total {sum(v for _, v in host_trace) * 1e3:.1f} ms; top {[(n, round(v * 1e3, 2)) for n, v in top]}", file=sys.stderr, flush=True)
+        if dbg is not None:                                  # diagnostics: where did a slow step spend its time?
+            torch.cuda.synchronize()
+            durs = sorted(((p0_.elapsed_time(p1_), nm, i) for i, (nm, p0_, p1_) in enumerate(dbg.pairs)), reverse=True)
+            gaps = sorted(((dbg.pairs[i][2].elapsed_time(dbg.pairs[i + 1][1]), dbg.pairs[i][0] + "->" + dbg.pairs[i + 1][0], i) for i in range(len(dbg.pairs) - 1)), reverse=True)
+            print(f"[phases] step {len(ms_steps)} {ms_steps[-1]:.1f} ms; longest phases {[(round(d, 2), n, i) for d, n, i in durs[:4]]}; "
+                  f"longest gaps {[(round(d, 2), n, i) for d, n, i in gaps[:4]]}", file=sys.stderr, flush=True)
         cg_iters.append(sum(max(r["niter"]) for r in mech.log))
         ranks_k.append(mech.covariance_model.vector_count)
         assert bool(torch.isfinite(x).all()), "non-finite sample"
@@ -367,6 +419,7 @@ def run_b200(a, assets):
         out_pin.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    gc.enable()
     e2e_total = reduce_max(float(sum(e2e_ms)))
     clk = clocks.stop() if rank == 0 else None
     e2e_value = world * B * a.steps / (e2e_total * 1e-3)
@@ -467,13 +520,14 @@ def run_b200(a, assets):
                                  "L2 / SM latency rather than HBM; `batched` has the HBM-bound regime" if B < 4 else "HBM-bound regime")})
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / a.steps, "ms_steps": [round(v, 3) for v in ms_steps], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (f64 reductions and k x k algebra)", "data": "synthetic",
         "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (PyTorch + library DCT); the UNet is outside the hot path",
                    "l2": "256 MiB flush between steps; every step samples new images", "mechanism_calls": n_calls,
-                   "cg_iterations_per_image": float(np.mean(cg_iters)), "final_bfgs_pairs": ranks_k[-1]},
+                   "host_reads": "per call (reference behaviour)" if a.blocking_host_reads else "deferred: one synchronisation per sampled image (FreeHunch.finalize)",
+                   "cg_iterations_per_image": float(np.mean(cg_iters)), "cg_iterations_steps": cg_iters, "final_bfgs_pairs": ranks_k[-1]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_total / a.steps},
+                "ms_per_step": e2e_total / a.steps, "ms_steps": [round(v, 3) for v in e2e_ms]},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

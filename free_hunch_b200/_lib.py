@@ -16,6 +16,8 @@ _SIGNATURES = {
     "fh_version": (c_int, []),
     "fh_launch_count": (c_long, [c_int]),
     "fh_cg_kernel_time": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_void_p]),
+    "fh_cg_solve_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p]),
     "fh_cg_resident_time": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_void_p]),
     "fh_trace_read": (c_int, [c_void_p, c_void_p]),
     "fh_prof_enable": (c_int, [c_int]),

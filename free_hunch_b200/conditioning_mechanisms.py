@@ -94,7 +94,7 @@ def rtol_func(sigma, rtol_max=1e0, rtol_min=1e-14):
 
 def choose_solver(operator_name, operator, y, x0_mean, theta0_var=None, covariance_model=None, method="customcuda",
                   max_rtol=1, ortho_tf=None, sigma_t=None, use_rtol_func=False, maxiter=5000, return_info=False,
-                  fixed_iters=0):
+                  fixed_iters=0, defer=False):
     """conditioning_mechanisms.py:562-600 for method='customcuda' (the reference default, config.yaml:121): returns
     mat = A^T (A Sigma A^T + sigma_y^2 I)^-1 (y - A x0_mean) from the CG solve with x0 = b and
     rtol = rtol_func(sigma_t, max_rtol).  The scipy paths of the reference are CPU baselines and are not provided."""
@@ -103,14 +103,28 @@ def choose_solver(operator_name, operator, y, x0_mean, theta0_var=None, covarian
     if method != "customcuda":
         raise ValueError(f"solver_type '{method}' is a CPU path of the reference; free_hunch_b200 provides 'customcuda' only")
     # sigma_s is a 1-element float32 tensor; clip and square in float32 like the reference (:387,:491,:642)
-    sig = operator.sigma_s.detach().to(torch.float32).cpu().clip(min=0.001)
-    if operator_name == "super_resolution":
-        sig = sig.clip(min=1e-2)
-    sy2 = float((sig ** 2).item())
-    mat, info = engine.cg_solve(covariance_model.state, operator.op, y, x0_mean, sy2, rtol_func(sigma_t, max_rtol),
-                                maxiter=maxiter, fixed_iters=fixed_iters)
-    if any(n >= maxiter for n in info["niter"]):
-        warn("CG not converge.")
+    sy2 = getattr(operator, "_fh_sy2", None)
+    if sy2 is None or operator._fh_sy2_src is not operator.sigma_s:
+        sig = operator.sigma_s.detach().to(torch.float32).cpu().clip(min=0.001)        # one device read per operator, not per call
+        if operator_name == "super_resolution":
+            sig = sig.clip(min=1e-2)
+        sy2 = float((sig ** 2).item())
+        try:
+            operator._fh_sy2, operator._fh_sy2_src = sy2, operator.sigma_s
+        except AttributeError:
+            pass
+    res = None
+    if defer:
+        # no host read-back: info is an engine.DeferredCgInfo (decoded by FreeHunch.finalize); None = not available here
+        res = engine.cg_solve_async(covariance_model.state, operator.op, y, x0_mean, sy2, rtol_func(sigma_t, max_rtol),
+                                    maxiter=maxiter, fixed_iters=fixed_iters)
+    if res is not None:
+        mat, info = res
+    else:
+        mat, info = engine.cg_solve(covariance_model.state, operator.op, y, x0_mean, sy2, rtol_func(sigma_t, max_rtol),
+                                    maxiter=maxiter, fixed_iters=fixed_iters)
+        if any(n >= maxiter for n in info["niter"]):
+            warn("CG not converge.")
     mat = mat.to(x0_mean.dtype)
     return (mat, info) if return_info else mat
 
@@ -134,6 +148,9 @@ class FreeHunch(ConditioningMechanism):
         argv.setdefault("space_step_update_threshold", 10.0)
         argv.setdefault("space_step_update_lower_threshold", 1.0)
         argv.setdefault("use_analytic_var_at_end", False)
+        # defer_host_reads: run x0_mean_update without any host synchronisation (see x0_mean_update); the caller must
+        # call finalize() after the last step.  Off by default: direct callers get the reference's blocking behaviour.
+        argv.setdefault("defer_host_reads", False)
         if argv["use_analytic_var_at_end"]:
             raise ValueError("use_analytic_var_at_end (scipy baseline branch, conditioning_mechanisms.py:273-278) is not provided")
         self.argv = argv
@@ -168,11 +185,14 @@ class FreeHunch(ConditioningMechanism):
         self.space_step_update_lower_threshold = argv["space_step_update_lower_threshold"]
         self.log = []
         self.timer = argv.get("timer") or PhaseTimer(False)
+        self.defer = bool(argv["defer_host_reads"])
+        self._deferred = []                   # (log record, DeferredCgInfo | None, same-x flag | None, fallback flag | None)
 
     def mat_solver(self, y, x0_mean, covariance_model=None, sigma_t=None, return_info=False):
         return choose_solver(self.forward_operator.name, self.forward_operator, y, x0_mean, None,
                              covariance_model or self.covariance_model, self.argv["solver_type"], self.argv["max_rtol"],
-                             None, sigma_t, use_rtol_func=self.argv["use_rtol_func"], return_info=return_info)
+                             None, sigma_t, use_rtol_func=self.argv["use_rtol_func"], return_info=return_info,
+                             defer=self.defer)
 
     def update_time_step(self, x_t, sigma_t, sigma_tnext, score_t):
         self.covariance_model.update_time_step(x_t, sigma_t, sigma_tnext, score_t)
@@ -181,7 +201,14 @@ class FreeHunch(ConditioningMechanism):
         self.covariance_model.update_space_step(denoiser_mean_at_x, denoiser_mean_at_xnext, sigma_t, x, xnext)
 
     def x0_mean_update(self, x_t, model, y, sigma):
-        """conditioning_mechanisms.py:237-294."""
+        """conditioning_mechanisms.py:237-294.
+
+        The reference reads three device values on the host in every call: `torch.allclose(x_t, xs[-1])` (:250), the
+        `.std() > threshold` fallback test (:283) and the CG loop's convergence flags.  With `defer_host_reads` the call
+        queues its work without waiting for any of them: the fallback is selected on the device (both candidates are
+        computed, `torch.where` picks), the CG outcome stays in device memory, and the x-changed test is ASSUMED true
+        (a sampler never evaluates the mechanism twice at the same point) and verified in finalize(), which raises if
+        the assumption was wrong.  The arithmetic is the same in both modes."""
         sigma_f = float(sigma.item()) if torch.is_tensor(sigma) else float(sigma)
         x_t = x_t.requires_grad_()
         with self.timer("denoiser"):
@@ -197,7 +224,15 @@ class FreeHunch(ConditioningMechanism):
                 rec["time_update"] = True
             elif len(self.sigmas) != 0:                                                                  # :248-249
                 prev_mean_at_sigma = self.denoiser_means[-1]
-            if len(self.xs) != 0 and not torch.allclose(x_t.detach(), self.xs[-1]):                     # :250
+            same_x = None
+            if len(self.xs) != 0:
+                if self.defer:
+                    same_x = torch.isclose(x_t.detach(), self.xs[-1]).all()       # device flag, checked in finalize()
+                    x_changed = True
+                else:
+                    x_changed = not torch.allclose(x_t.detach(), self.xs[-1])
+            rec["_same_x"] = same_x
+            if len(self.xs) != 0 and x_changed:                                                          # :250
                 if not self.use_analytical_score_time_update:                                            # :252-254
                     with torch.no_grad():
                         prev_mean_at_sigma, _ = model(self.xs[-1], sigma)
@@ -216,7 +251,12 @@ class FreeHunch(ConditioningMechanism):
         s2 = sigma_f ** 2
         with self.timer("denoiser"):
             p_y_xt_grad = torch.autograd.grad((mat.detach() * x_0_mean).sum(), x_t)[0]                   # :280
-        if (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold:                                # :283-285
+        if self.defer:
+            use_cov = (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold                      # :283, stays on device
+            alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
+            p_y_xt_grad = torch.where(use_cov, alt, p_y_xt_grad * self.cond_scaling)
+            rec["fallback"] = use_cov
+        elif (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold:                              # :283-285
             p_y_xt_grad = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
             rec["fallback"] = True
         else:                                                                                            # :287-288
@@ -227,10 +267,32 @@ class FreeHunch(ConditioningMechanism):
         self.sigmas.append(sigma_f)
         self.xs = [x_t.detach()]
         self.denoiser_means = [x_0_mean.detach()]
-        rec["niter"] = info["niter"]
+        rec["niter"] = info["niter"] if isinstance(info, dict) else info
         rec["k"] = cov.vector_count
         self.log.append(rec)
         return x_0_mean_new
+
+    def finalize(self):
+        """Deferred mode: ONE synchronisation for the whole run -- decode the CG outcomes and device-side flags into the
+        log, warn about unconverged solves and verify the x-changed assumption.  No-op otherwise."""
+        pending = [r for r in self.log if not isinstance(r.get("niter"), list) or torch.is_tensor(r.get("fallback"))
+                   or r.get("_same_x") is not None]
+        if not pending:
+            return self.log
+        maxiter = 5000
+        for r in pending:
+            if not isinstance(r["niter"], list):
+                info = r["niter"].fetch()
+                r["niter"] = info["niter"]
+                if any(n >= maxiter for n in info["niter"]):
+                    warn("CG not converge.")
+            if torch.is_tensor(r.get("fallback")):
+                r["fallback"] = bool(r["fallback"].item())
+            same = r.pop("_same_x", None)
+            if same is not None and bool(same.item()):
+                raise RuntimeError("defer_host_reads: the mechanism was evaluated twice at the same x_t (sigma = "
+                                   f"{r['sigma']}); the reference skips the space update there -- rerun with defer_host_reads=False")
+        return self.log
 
 
 # the reference's name for the same class

@@ -124,6 +124,9 @@ struct fh_ctx {
   int cg_mode;                        // FH_CG_AUTO / FH_CG_STREAMING / FH_CG_RESIDENT (fh_ctx_set_cg_mode)
   int cg_last_mode;                   // path taken by the last DCT-basis fh_cg_solve
   int res_ok;                         // the resident kernel's cooperative grid fits this device
+  // Device buffers of destroyed states, kept for the next fh_state_create of the same batch: a sampler builds one state
+  // per image, and cudaMalloc / cudaFree of its ~60 MB synchronise the device (measured: sporadic 10-100 ms stalls).
+  struct fh_state* state_pool[4];
   long long* trace;                   // FH_TRACE=1: clock64 checkpoints of the fused CG kernels (8 kernels x 16 slots)
 };
 
@@ -269,6 +272,11 @@ extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
 
 extern "C" int fh_ctx_destroy(fh_ctx* c) {
   if (!c) return FH_OK;
+  for (int i = 0; i < 4; ++i)
+    if (fh_state* p = c->state_pool[i]) {
+      cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs);
+      free(p);
+    }
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
@@ -351,6 +359,16 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
   fh_state* s = (fh_state*)calloc(1, sizeof(fh_state));
   s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0; s->sig2 = 1.0;
   const size_t vec = (size_t)batch * s->d * sizeof(float);
+  for (int i = 0; i < 4; ++i) {
+    fh_state* p = c->state_pool[i];
+    if (p && p->B == batch) {                               // reuse the buffers of a destroyed state (no cudaMalloc)
+      c->state_pool[i] = nullptr;
+      s->pi = p->pi; s->delta = p->delta; s->Z = p->Z; s->Gz = p->Gz; s->Gs = p->Gs;
+      free(p);
+      *out = s;
+      return FH_OK;
+    }
+  }
   FH_CUDA(cudaMalloc((void**)&s->pi, vec));
   FH_CUDA(cudaMalloc((void**)&s->delta, vec));
   FH_CUDA(cudaMalloc((void**)&s->Z, (size_t)batch * c->max_rank * s->d * sizeof(float) + 16));
@@ -361,6 +379,12 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
 }
 extern "C" int fh_state_destroy(fh_state* s) {
   if (!s) return FH_OK;
+  if (s->ctx)
+    for (int i = 0; i < 4; ++i)
+      if (!s->ctx->state_pool[i]) {                         // park the buffers; work queued on them is stream-ordered
+        s->ctx->state_pool[i] = s;                          // before whatever the next owner queues
+        return FH_OK;
+      }
   cudaFree(s->pi); cudaFree(s->delta); cudaFree(s->Z); cudaFree(s->Gz); cudaFree(s->Gs);
   free(s);
   return FH_OK;
@@ -853,7 +877,8 @@ static bool resident_applies(const fh_state* s, const FhCgFused& P) {
 
 // Whole solve in one launch per image (fh_cg_resident.cuh): Z stays in shared memory, x/r/p/q in registers.
 static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y, const float* mu, double rtol, int last,
-                             int use_stop, float* mat_out, int* niter_host, int* optimal_host, double* resid_host, void* stream) {
+                             int use_stop, float* mat_out, int* niter_host, int* optimal_host, double* resid_host, void* stream,
+                             FhCgInfo* info_dev = nullptr) {
   fh_ctx* c = s->ctx;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B;
@@ -878,7 +903,12 @@ static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y,
     FhCgResident R{};
     R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n;
     R.rtol = rtol; R.atol = 0.0; R.use_stop = use_stop; R.image = b;
+    R.info_out = info_dev ? info_dev + b : nullptr;
     if ((rc = launch_resident(c, P, R, st))) return rc;
+  }
+  if (info_dev) {                                          // asynchronous: the outcome stays on the device
+    if (o->kind == FH_OP_INPAINT) return FH_OK;
+    return fh_op_apply(o, x, mat_out, B, 1, stream);
   }
   FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
   FH_CUDA(cudaStreamSynchronize(st));
@@ -1009,6 +1039,24 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
     return FH_OK;
   }
   return fh_op_apply(o, x, mat_out, B, 1, stream);
+}
+
+// Fully asynchronous solve: nothing is read back, the call returns as soon as the work is queued on `stream`.  Only
+// where the resident kernel applies (the streaming path needs the host to follow the iteration count).
+extern "C" int fh_cg_solve_async(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
+                                 int maxiter, int fixed_iters, float* mat_out, fh_cg_info* info_dev, void* stream) {
+  if (!s || !o || !y || !mu || !mat_out || !info_dev || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve_async arguments");
+  if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_ESTATE, "asynchronous solve needs the DCT basis");
+  fh_ctx* c = s->ctx;
+  FhCgFused P = fused_params(s, o, 8);
+  if (!resident_applies(s, P)) FH_FAIL(FH_ESTATE, "asynchronous solve needs the resident kernel (rank %d, operator kind %d)", s->m, o->kind);
+  P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
+  const int use_stop = fixed_iters > 0 ? 0 : 1;
+  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
+  c->cg_last_mode = FH_CG_RESIDENT;
+  static_assert(sizeof(FhCgInfo) == sizeof(fh_cg_info), "device record layout");
+  return cg_solve_resident(s, o, P, y, mu, rtol, last, use_stop, mat_out, nullptr, nullptr, nullptr, stream, reinterpret_cast<FhCgInfo*>(info_dev));
 }
 
 extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,

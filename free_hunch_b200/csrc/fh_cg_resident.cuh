@@ -55,6 +55,8 @@ struct FhResSmem {
   unsigned long long pad_;
 };
 
+struct FhCgInfo { double residual_norm; int niter; int optimal; };      // == fh_cg_info of include/free_hunch_b200.h
+
 struct FhCgResident {
   const float* bvec;           // (d) right-hand side b (pixel layout); x0 = b
   float* x_out;                // (d) solution
@@ -69,6 +71,7 @@ struct FhCgResident {
   double rtol, atol;
   int use_stop;                // 0: run exactly `last_allowed` iterations
   int image;                   // which image of the batch (offsets into the state / scalars)
+  FhCgInfo* info_out;          // optional device record of the outcome (fh_cg_solve_async); written by CTA 0 at the end
   int timing;                  // fh_cg_resident_time only: keep iterating through the p.Ap <= 1e-16 break
 };
 
@@ -600,5 +603,6 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
     w->niter = niter;
     w->optimal = optimal;
     fh_set_done(w, niter + 1);
+    if (R.info_out) { R.info_out->residual_norm = sqrt(resid2); R.info_out->niter = niter; R.info_out->optimal = optimal; }
   }
 }

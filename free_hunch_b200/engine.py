@@ -155,7 +155,9 @@ class CovState:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib().fh_state_destroy(self._h)
+            # the library parks the state's buffers in its context for reuse: never hand it a state whose context is gone
+            if getattr(self.ctx, "_h", None):
+                _lib.lib().fh_state_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -226,6 +228,35 @@ def cg_solve(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
                                       int(fixed_iters), _ptr(mat), niter, optimal, resid, ctx.stream()))
     info = {"niter": list(niter), "optimal": [bool(o) for o in optimal], "residual_norm": list(resid)}
     return mat, info
+
+
+class DeferredCgInfo:
+    """Outcome records of asynchronous solves, still on the device; `fetch()` synchronises once and decodes them."""
+
+    def __init__(self, buf, batch):
+        self.buf, self.batch = buf, batch
+
+    def fetch(self):
+        raw = self.buf.cpu().numpy().tobytes()
+        rec = np.frombuffer(raw, dtype=np.dtype([("residual_norm", "<f8"), ("niter", "<i4"), ("optimal", "<i4")]), count=self.batch)
+        return {"niter": [int(v) for v in rec["niter"]], "optimal": [bool(v) for v in rec["optimal"]],
+                "residual_norm": [float(v) for v in rec["residual_norm"]]}
+
+
+def cg_solve_async(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
+    """(mat, DeferredCgInfo) with no host synchronisation, or None where the resident kernel does not apply
+    (fh_cg_solve_async returns FH_ESTATE: the caller uses cg_solve)."""
+    ctx = state.ctx
+    y = ctx.prep(y, op.y_shape(state.B))
+    mu = ctx.prep(mu, state.shape)
+    mat = torch.empty_like(mu)
+    info = torch.zeros(16 * state.B, dtype=torch.uint8, device=ctx.device)
+    rc = _lib.lib().fh_cg_solve_async(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
+                                      int(fixed_iters), _ptr(mat), _ptr(info), ctx.stream())
+    if rc == -4:                       # FH_ESTATE
+        return None
+    _lib.check(rc)
+    return mat, DeferredCgInfo(info, state.B)
 
 
 def launch_count(reset=False):

@@ -39,20 +39,25 @@ def conditional_sampler(mechanism, net, y, noise, t_steps, solver="heun"):
     t_steps = [float(t) for t in t_steps]
     x_next = noise.to(torch.float64) * t_steps[0]
     n = len(t_steps) - 1
+    # sigma goes to the mechanism as a 0-dim float64 HOST tensor: the mechanism and the denoiser wrapper read it with
+    # .item(), which on a device tensor is a full synchronisation per call
+    sig = lambda t: torch.tensor(t, dtype=torch.float64)
     for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
         x_hat = x_next
         h = t_next - t_cur
         with torch.enable_grad():
-            den = mechanism(x_hat.detach().clone().requires_grad_(), net, y, torch.tensor(t_cur, dtype=torch.float64, device=noise.device)).detach()
+            den = mechanism(x_hat.detach().clone().requires_grad_(), net, y, sig(t_cur)).detach()
         d_cur = (x_hat - den) / t_cur
         x_prime = x_hat + h * d_cur
         if solver == "euler" or i == n - 1:
             x_next = x_hat + h * d_cur
         else:
             with torch.enable_grad():
-                den2 = mechanism(x_prime.detach().clone().requires_grad_(), net, y, torch.tensor(t_next, dtype=torch.float64, device=noise.device)).detach()
+                den2 = mechanism(x_prime.detach().clone().requires_grad_(), net, y, sig(t_next)).detach()
             d_prime = x_prime / t_next - den2 / t_next
             x_next = x_hat + h * (0.5 * d_cur + 0.5 * d_prime)
+    if hasattr(mechanism, "finalize"):
+        mechanism.finalize()                       # deferred host reads (one synchronisation), no-op otherwise
     return x_next
 
 

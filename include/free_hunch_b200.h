@@ -120,6 +120,13 @@ int fh_op_apply(fh_op* op, const float* in_dev, float* out_dev, int batch, int t
 int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                 int maxiter, int fixed_iters, float* mat_out_dev, int* niter_host, int* optimal_host,
                 double* resid_host, void* stream);
+/* The same solve without any host read-back: returns once the work is queued on `stream`; the outcome of image b is
+ * written to info_dev[b] (device memory) when its solve ends.  This is what lets a sampler run the whole guided loop
+ * without a host synchronisation (the reference synchronises twice per CG iteration, cg.py:250,259).  Available where
+ * the resident kernel applies (DCT basis, rank <= 32, mask or separable blur); otherwise FH_ESTATE -- use fh_cg_solve. */
+typedef struct { double residual_norm; int niter; int optimal; } fh_cg_info;
+int fh_cg_solve_async(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
+                      int maxiter, int fixed_iters, float* mat_out_dev, fh_cg_info* info_dev, void* stream);
 /* bench.py's roofline: average device time (ms) of `reps` back-to-back launches of ONE kernel of the fused CG
  * iteration at the state's current rank, CUDA events on `stream`.  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols,
  * 3 inv_rows, 4 xr.  Only for operators that fold into the DCT passes (inpainting, separable blur). */

@@ -493,6 +493,57 @@ def test_mechanism_default_rtol_runs(assets):
     assert ef < 5e-2
 
 
+def test_mechanism_deferred_host_reads_identical(assets):
+    """defer_host_reads=True (no host synchronisation inside the sampling loop: CG outcome kept on the device, fallback
+    chosen with torch.where, x-changed test verified at the end) gives bit-identical samples and the same log as the
+    blocking mode, for a foldable operator (asynchronous resident CG) and a non-foldable one (blocking CG inside)."""
+    from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
+    from free_hunch_b200.measurements import get_operator
+    from free_hunch_b200.sampler import AnalyticDCTGaussianDenoiser, conditional_sampler, edm_sigma_steps
+    dev = torch.device("cuda")
+    var = assets["dct_variance"]
+    t_steps = edm_sigma_steps(12)
+    rs = np.random.RandomState(11)
+    x_clean = synth_image(var, 21)
+    noise = torch.from_numpy(rs.standard_normal(SHAPE)).to(dev)
+    for name, key in (("gaussian_blur", "gaussian_ks61_std3"), ("motion_blur", "motion_ks61_std05")):
+        op = get_operator(name, kernel=assets[key], scale_factor=1, in_shape=SHAPE, sigma_s=0.1, device=dev)
+        y = op.A(tt(x_clean).float().to(dev)) + 0.1 * torch.from_numpy(rs.standard_normal(SHAPE)).float().to(dev)
+        outs, logs = [], []
+        for defer in (False, True):
+            mech = choose_conditioning_mechanism("free_hunch")(
+                1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(float(t_steps[0]) ** 2, dtype=torch.float64),
+                data_dim=3 * 256 * 256, dct_variance=var, image_base_covariance="dct_diagonal", device=dev, defer_host_reads=defer)
+            net = AnalyticDCTGaussianDenoiser(var, mech.covariance_model.ctx)
+            outs.append(conditional_sampler(mech, net, y, noise, t_steps, solver="heun"))
+            logs.append([(r["sigma"], r["time_update"], r["space_update"], r["fallback"], tuple(r["niter"]), r["k"]) for r in mech.log])
+        assert torch.equal(outs[0], outs[1]), name
+        assert logs[0] == logs[1], name
+        assert all(isinstance(r[3], bool) for r in logs[1])
+        record("mechanism_deferred", op=name, calls=len(logs[1]), cg_iterations=sum(max(r[4]) for r in logs[1]))
+
+
+def test_mechanism_deferred_detects_repeated_point(assets):
+    """The one assumption of the deferred mode (x_t differs from the previous call) is verified, not trusted."""
+    from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
+    from free_hunch_b200.measurements import get_operator
+    from free_hunch_b200.sampler import AnalyticDCTGaussianDenoiser
+    dev = torch.device("cuda")
+    var = assets["dct_variance"]
+    op = get_operator("gaussian_blur", kernel=assets["gaussian_ks61_std3"], scale_factor=1, in_shape=SHAPE, sigma_s=0.1, device=dev)
+    mech = choose_conditioning_mechanism("free_hunch")(
+        1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(80.0 ** 2, dtype=torch.float64),
+        data_dim=3 * 256 * 256, dct_variance=var, image_base_covariance="dct_diagonal", device=dev, defer_host_reads=True)
+    net = AnalyticDCTGaussianDenoiser(var, mech.covariance_model.ctx)
+    x = torch.from_numpy(make_inputs(4, SHAPE) * 80.0).to(dev)
+    y = op.A(tt(synth_image(var, 3)).float().to(dev))
+    with torch.enable_grad():
+        mech(x.clone().requires_grad_(), net, y, torch.tensor(80.0, dtype=torch.float64))
+        mech(x.clone().requires_grad_(), net, y, torch.tensor(5.0, dtype=torch.float64))       # same x, new sigma
+    with pytest.raises(RuntimeError, match="same x_t"):
+        mech.finalize()
+
+
 @pytest.mark.parametrize("which,solver", [("inpainting", "heun"), ("super_resolution", "heun"), ("motion_blur", "euler")])
 def test_mechanism_other_operators_vs_oracle(assets, which, solver):
     """The whole mechanism (Python API, batch 2) for the operators the golden run does not cover, against the float64
