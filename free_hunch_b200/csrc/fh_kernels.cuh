@@ -200,11 +200,24 @@ fh_k_gram(const float* __restrict__ Z, int m, FhRowPtrs xrows, int nx, const flo
   const size_t b = blockIdx.y;
   const int R = m + nx;
   const int nb = (R + 3) / 4;                // 4x4 register blocks per dimension
-  // thread -> block (bi, bj); threads beyond nb*nb idle in compute
-  const int bi = tid / 17, bj = tid % 17;    // 17*17 = 289 > 256: loop twice over block ids
-  double acc[2][16];
+  // thread = (column part, block slot): the 128 columns of a tile are split over 4 groups of 64 threads, each thread
+  // owns up to 3 of the nb (nb + 1) / 2 <= 153 upper-triangular 4x4 blocks (the first version gave one block to one
+  // thread over all 128 columns: at m = 32 only 45 threads of the CTA computed and the kernel took 100 us)
+  const int part = tid >> 6, slot = tid & 63;
+  const int nblk2 = nb * (nb + 1) / 2;
+  int bpi[3], bpj[3];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int h = 0; h < 3; ++h) {
+    int blk = slot + 64 * h, pi_ = 0;
+    bpi[h] = -1; bpj[h] = 0;
+    if (blk < nblk2) {
+      while (blk >= nb - pi_) { blk -= nb - pi_; ++pi_; }       // row pi_ of the triangle holds nb - pi_ blocks
+      bpi[h] = pi_; bpj[h] = pi_ + blk;
+    }
+  }
+  double acc[3][16];
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[h][e] = 0.0;
   const long ntile = (d + FH_GRAM_TILE - 1) / FH_GRAM_TILE;
@@ -223,16 +236,16 @@ fh_k_gram(const float* __restrict__ Z, int m, FhRowPtrs xrows, int nx, const flo
     if (tid < FH_GRAM_TILE) wt[tid] = (c0 + tid < d) ? (w ? w[b * d + c0 + tid] : 1.f) : 0.f;
     __syncthreads();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int blk = tid + 256 * h;
-      const int pi_ = blk / 17, pj_ = blk % 17;
-      if (pi_ < nb && pj_ < nb && pj_ >= pi_) {        // upper triangle of blocks only
+    for (int h = 0; h < 3; ++h) {
+      if (bpi[h] >= 0) {
         float a32[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) a32[e] = 0.f;
-        const float* ri = tile + (4 * pi_) * (FH_GRAM_TILE + 1);
-        const float* rj = tile + (4 * pj_) * (FH_GRAM_TILE + 1);
-        for (int c = 0; c < FH_GRAM_TILE; ++c) {
+        const float* ri = tile + (4 * bpi[h]) * (FH_GRAM_TILE + 1);
+        const float* rj = tile + (4 * bpj[h]) * (FH_GRAM_TILE + 1);
+        const int cb = part * (FH_GRAM_TILE / 4);
+#pragma unroll 4
+        for (int c = cb; c < cb + FH_GRAM_TILE / 4; ++c) {
           const float wv = wt[c];
           float x[4], y[4];
 #pragma unroll
@@ -247,18 +260,25 @@ fh_k_gram(const float* __restrict__ Z, int m, FhRowPtrs xrows, int nx, const flo
       }
     }
   }
-  (void)bi; (void)bj;
+  // sum the 4 column parts (fixed order) through shared memory, 64 slots x 16 doubles per part and round
+  double* red = reinterpret_cast<double*>(sm);
   double* P = partial + (b * gridDim.x + blockIdx.x) * (size_t)(FH_GRAM_LD * FH_GRAM_LD);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int blk = tid + 256 * h;
-    const int pi_ = blk / 17, pj_ = blk % 17;
-    if (pi_ < nb && pj_ < nb && pj_ >= pi_) {
+  for (int h = 0; h < 3; ++h) {
+    __syncthreads();
+    if (part > 0) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) red[((part - 1) * 64 + slot) * 16 + e] = acc[h][e];
+    }
+    __syncthreads();
+    if (part == 0 && bpi[h] >= 0) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[h][e] = ((acc[h][e] + red[slot * 16 + e]) + red[(64 + slot) * 16 + e]) + red[(128 + slot) * 16 + e];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          const int i = 4 * pi_ + q, j = 4 * pj_ + s;
+          const int i = 4 * bpi[h] + q, j = 4 * bpj[h] + s;
           if (i < R && j < R) { P[i * FH_GRAM_LD + j] = acc[h][4 * q + s]; P[j * FH_GRAM_LD + i] = acc[h][4 * q + s]; }
         }
     }

@@ -45,7 +45,9 @@ int fh_ctx_destroy(fh_ctx* ctx);
  *   FH_CG_STREAMING  five launches per iteration, Z streamed from L2/HBM by TMA, any batch, any rank <= 64;
  *   FH_CG_RESIDENT   one cooperative launch per image and solve, Z resident in shared memory (rank <= 32, operators
  *                    that fold into the DCT passes: inpainting mask, separable blur);
- *   FH_CG_AUTO       resident whenever it applies (default).
+ *   FH_CG_AUTO       resident where it applies and the batch is at most 4 images (the resident kernel takes the images
+ *                    one after the other; from 5 images on the streaming iteration is faster per image) (default).
+ * Results are bit-identical across batch sizes within one implementation, not between the two.
  * FH_CG_RESIDENT makes fh_cg_solve fail with FH_EINVAL when the resident kernel does not apply. */
 #define FH_CG_AUTO 0
 #define FH_CG_STREAMING 1
