@@ -50,7 +50,10 @@ def build(args):
         xn = x + (s - s_prev) * (x - mu_prev) / s_prev + 0.02 * s * torch.randn(shape, device="cuda", generator=g)
         mun = den(xn, s)
         e[2].record()
-        st.space_update(mean, mun, s, x, xn)
+        # secant pair from the denoiser itself at the new sigma (dx.de > 0: a positive-definite state; with the time
+        # update's own prediction `mean` the pair carries the model error and the synthetic state can go indefinite,
+        # which ends CG through the p.Ap <= 1e-16 break after a handful of iterations)
+        st.space_update(den(x, s), mun, s, x, xn)
         e3 = torch.cuda.Event(enable_timing=True)
         e3.record()
         torch.cuda.synchronize()
