@@ -62,7 +62,10 @@ def parse_args():
 
 
 def workload_name(a):
-    return (f"configs[1]: {a.operator} sigma_y=0.1 ks=61, Free Hunch (dct_diagonal, space updates 1<sigma<10), "
+    cfg = {("gaussian_blur", "heun", 30, 1): "configs[1]", ("inpainting", "heun", 30, 1): "configs[2] (one of the 8 shards)",
+           ("super_resolution", "heun", 30, 16): "configs[3] (memory-efficient update)",
+           ("motion_blur", "euler", 100, 1): "configs[4] (one image of the sweep)"}.get((a.operator, a.solver, a.num_steps, a.batch), "variant")
+    return (f"{cfg}: {a.operator} sigma_y=0.1 ks=61, Free Hunch (dct_diagonal, space updates 1<sigma<10), "
             f"{a.num_steps}-step {a.solver}, 3x256x256, micro-batch {a.batch}/GPU")
 
 
@@ -93,23 +96,56 @@ def random_mask(seed):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  In-process NVML (nvidia_ml_py) from a thread when it is
+    importable: the `nvidia-smi -lms` loop it replaces stalled the GPU for tens of ms per sample on this pool (and for
+    whole seconds while starting up), which is a large fraction of an 80 ms step.  Falls back to nvidia-smi."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.1):
         self.index, self.rows, self.proc, self.first = index, [], None, 0
+        self.period, self.how, self._stop, self._thread = period_s, None, threading.Event(), None
 
     def mark(self):
-        """Samples taken before this call (nvidia-smi start-up, warm-up steps) are not reported."""
+        """Samples taken before this call (start-up, warm-up steps) are not reported."""
         self.first = len(self.rows)
+
+    def _nvml_loop(self, nv, h):
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        names = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except AttributeError:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(self.index), str(sm), str(smax), ""] + ["Active" if mask & bit else "Not Active" for _, bit in names])
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
         if os.environ.get("FH_BENCH_NO_CLOCKS"):          # diagnostics only: measure the sampler's own interference
             return
+        if not os.environ.get("FH_BENCH_NVIDIA_SMI"):
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+                self.how = "nvml"
+                self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+                self._thread.start()
+                return
+            except Exception:
+                self.how = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "250"], stdout=subprocess.PIPE, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -119,13 +155,17 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, smax, reasons = [], None, set()
         for r in self.rows[self.first:]:
             if len(r) < 8:
@@ -138,7 +178,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampler": self.how}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -408,8 +448,8 @@ def run_b200(a, assets):
     value = world * B * a.steps / (total_ms * 1e-3)
     # ---- end-to-end arm: pinned host buffers in, host image out, wall clock of the user-facing call
     e2e_ms = []
-    for k in range(a.steps):
-        op, y, noise = problems[a.warmup + k]                  # the same images as the device-resident arm
+    for k in range(-1, a.steps):                               # k = -1: one untimed pass over the pinned-memory path
+        op, y, noise = problems[a.warmup + max(k, 0)]          # the same images as the device-resident arm
         y_pin, n_pin = torch.from_numpy(y).pin_memory(), torch.from_numpy(noise).pin_memory()
         out_pin = torch.empty((B, 3, 256, 256), dtype=torch.float64).pin_memory()
         flush.fill_(1)
@@ -418,7 +458,8 @@ def run_b200(a, assets):
         x, _ = sample(op, y_pin.to(dev, non_blocking=True), n_pin.to(dev, non_blocking=True))
         out_pin.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
-        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        if k >= 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
     gc.enable()
     e2e_total = reduce_max(float(sum(e2e_ms)))
     clk = clocks.stop() if rank == 0 else None

@@ -227,7 +227,12 @@ class FreeHunch(ConditioningMechanism):
             same_x = None
             if len(self.xs) != 0:
                 if self.defer:
-                    same_x = torch.isclose(x_t.detach(), self.xs[-1]).all()       # device flag, checked in finalize()
+                    # the test only decides whether the space update below runs: outside its sigma window (and with the
+                    # analytical score transfer) nothing depends on it -- at small sigma consecutive Euler iterates DO
+                    # agree to allclose's tolerance, exactly as in the reference
+                    in_window = self.space_step_update_lower_threshold < sigma_f < self.space_step_update_threshold
+                    if in_window or not self.use_analytical_score_time_update:
+                        same_x = torch.isclose(x_t.detach(), self.xs[-1]).all()   # device flag, checked in finalize()
                     x_changed = True
                 else:
                     x_changed = not torch.allclose(x_t.detach(), self.xs[-1])

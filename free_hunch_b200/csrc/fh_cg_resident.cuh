@@ -49,7 +49,7 @@ struct FhResSmem {
   float taps[4][FH_RES_TAPS];                      // row A^T, column A^T, column A, row A (centre padded to a multiple of 4)
   float s_w[FH_PASS_THREADS / 32][FH_RES_MAXM];
   double s_sum[FH_RES_MAXM];
-  double s_red[34];
+  double s_red[36];                                // [0..32] fh_block_sum scratch, [33], [34] broadcast slots of fh_ll_reduce
   float s_c[FH_RES_MAXM];
   fh_mbar_t bar;
   unsigned long long pad_;
@@ -204,12 +204,13 @@ __device__ __forceinline__ void fh_res_store_t_ll(const float* sm_rows, uint4* T
   }
 }
 
-// Sum of one double per CTA over the grid: thread t < nblk polls slot t, fixed-order block sum (bit-identical in
-// every CTA).  Contains __syncthreads.
 // Slots that many CTAs poll at once sit FH_LL_SPREAD slots (128 bytes) apart, so that they land in different L2 slices:
 // with 2 KB of contiguous slots polled by 16 384 threads one slice serialises everything (measured: 10 us per exchange).
 #define FH_LL_SPREAD 8
-__device__ __forceinline__ double fh_ll_reduce(const uint4* slots, int nblk, unsigned seq, double* s_red) {
+// Sum of one double per CTA over the grid: thread t < nblk polls slot t, fixed-order block sum (bit-identical in
+// every CTA).  Contains __syncthreads.  (Polling with warp 0 only -- 4 slots per lane, shuffle reduce, one barrier --
+// measured slower: 20.0 instead of 18.7 us per iteration.)
+__device__ __forceinline__ double fh_ll_reduce(const uint4* slots, int nblk, unsigned seq, double* s_red, int /*which*/) {
   double v = 0.0;
   for (int i = threadIdx.x; i < nblk; i += FH_PASS_THREADS) {
     uint4 w[1];
@@ -553,8 +554,8 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         const double t1 = fh_block_sum((double)rr32, sm.s_red);
         const double t2 = fh_block_sum((double)bb32, sm.s_red);
         if (tid == 0) { fh_ll_put_double(R.ll_a + (size_t)s * FH_LL_SPREAD, t1, seq); fh_ll_put_double(R.ll_b + (size_t)s * FH_LL_SPREAD, t2, seq); }
-        rr = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red);
-        const double bb = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red);
+        rr = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red, 0);
+        const double bb = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red, 1);
         const double stop = fmax(R.rtol * sqrt(bb), R.atol);
         stop2 = R.use_stop ? stop * stop : -1.0;
         resid2 = rr;
@@ -567,7 +568,7 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
     FH_RTRACE(10);
     // ------------------------------------------------------------------ P5: step, residual, stop test, new direction
     {
-      const double pAp = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red);
+      const double pAp = fh_ll_reduce(R.ll_a, (int)nblk, seq, sm.s_red, 0);
       FH_RTRACE(12);
       if (pAp <= 1e-16 && !R.timing) { niter = it; break; }              // cg.py:250
       const float alpha = (float)(rr / pAp);
@@ -581,7 +582,7 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
       const double tot = fh_block_sum((double)rr32, sm.s_red);
       if (tid == 0) fh_ll_put_double(R.ll_b + (size_t)s * FH_LL_SPREAD, tot, seq);
       FH_RTRACE(13);
-      const double rr_new = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red);
+      const double rr_new = fh_ll_reduce(R.ll_b, (int)nblk, seq, sm.s_red, 1);
       FH_RTRACE(15);
       resid2 = rr_new;
       niter = it;
