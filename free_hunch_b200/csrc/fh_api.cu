@@ -215,7 +215,7 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   FH_CUDA(cudaMalloc((void**)&c->grid_counter, (size_t)max_batch * sizeof(unsigned)));
   {
     const size_t nblk = (size_t)(c->d / FH_RES_SLICE) + 1;
-    c->res_ll_bytes = ((size_t)c->d + FH_RES_MAXM * nblk + (FH_RES_MAXM + 2 * nblk) * FH_LL_SPREAD) * sizeof(uint4);   // 2 x d/2, dots, sums, a, b
+    c->res_ll_bytes = ((size_t)c->d + FH_MAXM * nblk + (FH_MAXM + 2 * nblk) * FH_LL_SPREAD) * sizeof(uint4);   // 2 x d/2, dots, sums, a, b
     FH_CUDA(cudaMalloc((void**)&c->res_ll, c->res_ll_bytes));
     FH_CUDA(cudaMemset(c->res_ll, 0, c->res_ll_bytes));
     c->res_seq = 0;
@@ -240,9 +240,12 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
   {
     // resident CG solve: one CTA per SM holding up to FH_RES_MAXM row slices of Z; needs C*256/6 co-resident CTAs
     const int res_smem = (int)sizeof(FhResSmem) + FH_RES_MAXM * FH_RES_SLICE * 4;
-    FH_CUDA(cudaFuncSetAttribute(fh_k_cg_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem));
-    int per_sm = 0;
-    FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fh_k_cg_resident, FH_PASS_THREADS, res_smem));
+    FH_CUDA(cudaFuncSetAttribute(fh_k_cg_resident<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem));
+    FH_CUDA(cudaFuncSetAttribute(fh_k_cg_resident<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem));
+    int per_sm = 0, per_sm_big = 0;
+    FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fh_k_cg_resident<false>, FH_PASS_THREADS, res_smem));
+    FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_big, fh_k_cg_resident<true>, FH_PASS_THREADS, res_smem));
+    per_sm = std::min(per_sm, per_sm_big);
     int coop = 0;
     FH_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     const long rows = (long)channels * height;
@@ -837,8 +840,8 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
     const size_t nblk = grid.x, half = (size_t)c->d / 2;
     R.ll_T[0] = c->res_ll; R.ll_T[1] = c->res_ll + half;
     R.ll_dots = c->res_ll + 2 * half;
-    R.ll_sum = R.ll_dots + FH_RES_MAXM * nblk;
-    R.ll_a = R.ll_sum + FH_RES_MAXM * FH_LL_SPREAD; R.ll_b = R.ll_a + nblk * FH_LL_SPREAD;
+    R.ll_sum = R.ll_dots + FH_MAXM * nblk;
+    R.ll_a = R.ll_sum + FH_MAXM * FH_LL_SPREAD; R.ll_b = R.ll_a + nblk * FH_LL_SPREAD;
     const unsigned need = (unsigned)P.last_allowed + 2u;
     if (c->res_seq > 0xffffffffu - need - 1u) {
       FH_CUDA(cudaMemsetAsync(c->res_ll, 0, c->res_ll_bytes, st));
@@ -849,10 +852,12 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
     R.grid_counter = c->grid_counter + R.image;
     FH_CUDA(cudaMemsetAsync(R.grid_counter, 0, sizeof(unsigned), st));
   }
-  const size_t smem = sizeof(FhResSmem) + (size_t)P.m * FH_RES_SLICE * sizeof(float);
+  const bool big = P.m > FH_RES_MAXM;                      // rows above 32 are re-read from L2 (fh_k_cg_resident<true>)
+  const size_t smem = sizeof(FhResSmem) + (size_t)std::min(P.m, FH_RES_MAXM) * FH_RES_SLICE * sizeof(float);
 #ifdef FH_EMU
   (void)c; (void)st;
-  emu::launch_coop([&] { fh_k_cg_resident(P, R); }, grid, block, smem);
+  if (big) emu::launch_coop([&] { fh_k_cg_resident<true>(P, R); }, grid, block, smem);
+  else emu::launch_coop([&] { fh_k_cg_resident<false>(P, R); }, grid, block, smem);
   ++fh_g_launches;
 #else
   (void)c;
@@ -863,7 +868,8 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (fh_g_prof_on) fh_prof_begin("fh_k_cg_resident", st);
-  FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_resident, P, R));
+  if (big) FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_resident<true>, P, R));
+  else FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_resident<false>, P, R));
   if (fh_g_prof_on) fh_prof_end(st);
   ++fh_g_launches;
 #endif
@@ -875,7 +881,7 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
 #define FH_RES_AUTO_MAX_BATCH 4
 static bool resident_applies(const fh_state* s, const FhCgFused& P) {
   const fh_ctx* c = s->ctx;
-  if (!(c->res_ok && P.fuse != 0 && s->m <= FH_RES_MAXM) || c->cg_mode == FH_CG_STREAMING) return false;
+  if (!(c->res_ok && P.fuse != 0 && s->m <= FH_MAXM) || c->cg_mode == FH_CG_STREAMING) return false;
   return c->cg_mode == FH_CG_RESIDENT || s->B <= FH_RES_AUTO_MAX_BATCH;
 }
 
@@ -950,7 +956,7 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
     return cg_solve_resident(s, o, P, y, mu, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream);
   }
   if (c->cg_mode == FH_CG_RESIDENT)
-    FH_FAIL(FH_EINVAL, "resident CG solve requested but not applicable (rank %d > %d, operator not foldable, or device too small)", s->m, FH_RES_MAXM);
+    FH_FAIL(FH_EINVAL, "resident CG solve requested but not applicable (operator does not fold into the DCT passes, or the device cannot hold the cooperative grid)");
   c->cg_last_mode = FH_CG_STREAMING;
   const bool fusedop = P.fuse != 0;
   const dim3 block(FH_PASS_THREADS);

@@ -47,10 +47,10 @@ struct FhResSmem {
   float2 post[FH_N];
   float2 cw[FH_N];
   float taps[4][FH_RES_TAPS];                      // row A^T, column A^T, column A, row A (centre padded to a multiple of 4)
-  float s_w[FH_PASS_THREADS / 32][FH_RES_MAXM];
-  double s_sum[FH_RES_MAXM];
+  float s_w[FH_PASS_THREADS / 32][FH_MAXM];
+  double s_sum[FH_MAXM];
   double s_red[36];                                // [0..32] fh_block_sum scratch, [33], [34] broadcast slots of fh_ll_reduce
-  float s_c[FH_RES_MAXM];
+  float s_c[FH_MAXM];
   fh_mbar_t bar;
   unsigned long long pad_;
 };
@@ -61,8 +61,8 @@ struct FhCgResident {
   const float* bvec;           // (d) right-hand side b (pixel layout); x0 = b
   float* x_out;                // (d) solution
   uint4* ll_T[2];              // (d/2) slots each: half-transformed plane, forward / inverse (slot = 2 floats + 2 flags)
-  uint4* ll_dots;              // [FH_RES_MAXM][grid] slots: per-CTA partial of (Z (delta w_hat))_i as a double
-  uint4* ll_sum;               // [FH_RES_MAXM] slots, FH_LL_SPREAD apart: (Z (delta w_hat))_i summed over the grid by row i's owner CTA
+  uint4* ll_dots;              // [FH_MAXM][grid] slots: per-CTA partial of (Z (delta w_hat))_i as a double
+  uint4* ll_sum;               // [FH_MAXM] slots, FH_LL_SPREAD apart: (Z (delta w_hat))_i summed over the grid by row i's owner CTA
   uint4* ll_a;                 // [grid] slots, FH_LL_SPREAD apart: per-CTA partial of p.q  (iteration 0: |r0|^2)
   uint4* ll_b;                 // [grid] slots, FH_LL_SPREAD apart: per-CTA partial of r.r  (iteration 0: |b|^2)
   unsigned* grid_counter;      // arrival counter of the grid barrier, zeroed by the host before the launch
@@ -297,7 +297,24 @@ __device__ __forceinline__ float fh_warp_transpose_sum32(float (&v)[32]) {
   return v[0];
 }
 
-// grid = C*256/6 CTAs (cooperative launch), block = 256, dynamic shared memory = sizeof(FhResSmem) + m * 6 KB.
+// the thread's 6 elements of a Z row slice that is NOT resident: straight from global memory (L2), read-only path
+__device__ __forceinline__ void fh_strip_get_global(const float* __restrict__ src, float (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+#ifdef FH_EMU
+    const float2 v = reinterpret_cast<const float2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+#else
+    const float2 v = __ldg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+#endif
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+
+// grid = C*256/6 CTAs (cooperative launch), block = 256, dynamic shared memory = sizeof(FhResSmem) + min(m, 32) * 6 KB.
+// BIG = false: m <= 32, every row of Z resident.  BIG = true: 32 < m <= 64 (a 100-step Euler run reaches 56): rows
+// 0..31 resident, rows 32..m-1 re-read from L2 in the two low-rank phases of every iteration (their slices are only
+// read, each by one CTA: plain read-only loads, 12 in flight per thread, no staging).
+template <bool BIG>
 __global__ void __launch_bounds__(FH_PASS_THREADS, 1)
 fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   FH_DYN_SMEM(unsigned char, smem_raw);
@@ -311,6 +328,7 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   const int s = blockIdx.x;
   const unsigned nblk = gridDim.x;
   const int m = P.m;
+  const int mr = BIG ? FH_RES_MAXM : m;                  // rows of Z resident in shared memory
   const long d = (long)nblk * FH_RES_SLICE;
   const size_t img = (size_t)R.image * d;
   const size_t soff = (size_t)s * FH_RES_SLICE;
@@ -318,11 +336,11 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
   // ---- prologue: Z slices by TMA (one 6 KB bulk copy per row), tables, taps, per-solve constants in registers ----
   if (tid == 0) { fh_mbar_init(&sm.bar, 1); fh_mbar_fence_init(); }
   __syncthreads();
+  const float* zsrc = P.Z + (size_t)R.image * FH_MAXM * d + soff;        // this CTA's slice of row 0 of Z
   if (m > 0 && warp == 0) {
-    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)m * FH_RES_SLICE * 4u);
+    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)mr * FH_RES_SLICE * 4u);
     __syncwarp();
-    const float* zsrc = P.Z + (size_t)R.image * FH_MAXM * d + soff;
-    for (int i = lane; i < m; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, FH_RES_SLICE * 4u, &sm.bar);
+    for (int i = lane; i < mr; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, FH_RES_SLICE * 4u, &sm.bar);
   }
   for (int i = tid; i < 3 * 3 * 64; i += FH_PASS_THREADS) sm.tw[i] = P.tab.tw256[i];
   for (int i = tid; i < FH_N; i += FH_PASS_THREADS) { sm.post[i] = P.tab.post[i]; sm.cw[i] = P.tab.cw[i]; }
@@ -349,13 +367,17 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
       mk[2 * h] = v.x; mk[2 * h + 1] = v.y;
     }
   }
-  // coefficient stage: thread (i = tid / 8, part = tid % 8) owns Gs[i][part + 8u], u < 4
-  const int ci = tid >> 3, cpart = tid & 7;
-  double gs[4] = {0.0, 0.0, 0.0, 0.0};
+  // coefficient stage: thread (i = tid / CP, part = tid % CP) owns Gs[i][part + CP u], u < NG  (32 rows x 8 parts x 4
+  // columns, or 64 rows x 4 parts x 16 columns)
+  constexpr int CP = BIG ? 4 : 8, NG = BIG ? 16 : 4, CROWS = FH_PASS_THREADS / CP;
+  const int ci = tid / CP, cpart = tid % CP;
+  double gs[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) gs[u] = 0.0;
   if (ci < m) {
     const double* g = P.Gs + ((size_t)R.image * FH_MAXM + ci) * FH_MAXM;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) gs[u] = (cpart + 8 * u < m) ? g[cpart + 8 * u] : 0.0;
+    for (int u = 0; u < NG; ++u) gs[u] = (cpart + CP * u < m) ? g[cpart + CP * u] : 0.0;
   }
   unsigned bar_target = 0;
   float* Tp = P.T + img;                                                   // plain plane (FH_RES_T_LL == 0)
@@ -420,19 +442,39 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
       float wd[FH_RES_ROWS];
 #pragma unroll
       for (int e = 0; e < FH_RES_ROWS; ++e) wd[e] = wh[e] * dl[e];
-      float acc[32];
+      {
+        float acc[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = 0.f;
-        if (i < m) {
-          float z[FH_RES_ROWS];
-          fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+        for (int i = 0; i < 32; ++i) {
+          acc[i] = 0.f;
+          if (i < mr) {
+            float z[FH_RES_ROWS];
+            fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
 #pragma unroll
-          for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fmaf(z[e], wd[e], acc[i]);
+            for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fmaf(z[e], wd[e], acc[i]);
+          }
         }
+        sm.s_w[warp][lane] = fh_warp_transpose_sum32(acc);
       }
-      const float tot = fh_warp_transpose_sum32(acc);
-      sm.s_w[warp][lane] = tot;
+      if (BIG) {
+        float acc[32];
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 4) {                 // 4 rows = 12 independent 8-byte loads in flight per thread
+          float z[4][FH_RES_ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (mr + i0 + u < m) fh_strip_get_global(zsrc + (size_t)(mr + i0 + u) * d, z[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[i0 + u] = 0.f;
+            if (mr + i0 + u < m) {
+#pragma unroll
+              for (int e = 0; e < FH_RES_ROWS; ++e) acc[i0 + u] = fmaf(z[u][e], wd[e], acc[i0 + u]);
+            }
+          }
+        }
+        sm.s_w[warp][32 + lane] = fh_warp_transpose_sum32(acc);
+      }
       __syncthreads();
       if (tid < m) {
         double t = 0.0;
@@ -447,7 +489,8 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
         // of its owner CTA (i * grid / 32: spread over the chip), which publishes the total; then warp 0 of EVERY CTA
         // fetches the m totals.  (One hop -- every CTA summing all grid x m partials itself -- moves 8 MB through L2 per
         // iteration and took 2.2 us.)
-        const int own_step = (int)nblk / FH_RES_MAXM > 0 ? (int)nblk / FH_RES_MAXM : 1;
+        constexpr int OROWS = BIG ? FH_MAXM : FH_RES_MAXM;
+        const int own_step = (int)nblk / OROWS > 0 ? (int)nblk / OROWS : 1;
         if (warp == 0) {
           if (s % own_step == 0 && s / own_step < m) {
             const int i = s / own_step;
@@ -470,34 +513,55 @@ fh_k_cg_resident(FhCgFused P, FhCgResident R) {
             t = fh_warp_sum(t);
             if (lane == 0) fh_ll_put_double(R.ll_sum + (size_t)i * FH_LL_SPREAD, t, seq);
           }
-          double tot = 0.0;
-          if (lane < m) {
-            uint4 v[1];
-            fh_ll_wait<1>(R.ll_sum + (size_t)lane * FH_LL_SPREAD, 0, seq, v);
-            tot = fh_u2d(v[0].x, v[0].z);
+#pragma unroll
+          for (int g = 0; g < (BIG ? 2 : 1); ++g) {
+            const int row = lane + 32 * g;
+            double tot = 0.0;
+            if (row < m) {
+              uint4 v[1];
+              fh_ll_wait<1>(R.ll_sum + (size_t)row * FH_LL_SPREAD, 0, seq, v);
+              tot = fh_u2d(v[0].x, v[0].z);
+            }
+            sm.s_sum[row] = tot;
           }
-          sm.s_sum[lane] = tot;
         }
         FH_RTRACE(5);
         __syncthreads();
         double a = 0.0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a += gs[u] * sm.s_sum[cpart + 8 * u];
+        for (int u = 0; u < NG; ++u) a += gs[u] * sm.s_sum[cpart + CP * u];
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (cpart == 0 && ci < FH_RES_MAXM) sm.s_c[ci] = (float)a;
+        if (!BIG) a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (cpart == 0 && ci < CROWS) sm.s_c[ci] = (float)a;
         __syncthreads();
       }
       FH_RTRACE(6);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        if (i < m) {
+        if (i < mr) {
           const float c = sm.s_c[i];
           float z[FH_RES_ROWS];
           fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
 #pragma unroll
           for (int e = 0; e < FH_RES_ROWS; ++e) wh[e] = fmaf(c, z[e], wh[e]);
+        }
+      }
+      if (BIG) {
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+          float z[4][FH_RES_ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (mr + i0 + u < m) fh_strip_get_global(zsrc + (size_t)(mr + i0 + u) * d, z[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (mr + i0 + u < m) {
+              const float c = sm.s_c[mr + i0 + u];
+#pragma unroll
+              for (int e = 0; e < FH_RES_ROWS; ++e) wh[e] = fmaf(c, z[u][e], wh[e]);
+            }
+          }
         }
       }
     }

@@ -408,6 +408,47 @@ def test_cg_resident_matches_streaming(E, ctx, assets, full_state, which):
     assert i_cr["optimal"][0] and i_cs["optimal"][0]
 
 
+def test_cg_resident_rank_above_32(E, ctx, assets, full_state):
+    """Rank 48 (24 BFGS pairs; a 100-step Euler run reaches 56): the resident kernel keeps 32 rows of Z in shared memory and
+    re-reads the rest from L2 (fh_k_cg_resident<true>).  Against the oracle, against the streaming iteration, and through
+    the asynchronous entry point."""
+    var, den = full_state["var"], full_state["den"]
+    s0, s1 = S0, 6.5
+    st = E.CovState(ctx, 1, E.BASIS_DCT)
+    st.init(tt(var), s0 ** 2)
+    ora = fo.CovarianceOracleDCT(var, s0 ** 2, var.size)
+    st.time_update(None, None, s0, s1, only_covariance=True)
+    ora.update_time_step(np.zeros(SHAPE), s0, s1, np.zeros(SHAPE), only_covariance=True)
+    rs = np.random.RandomState(31)
+    x = synth_image(var, 41) + s1 * rs.standard_normal(SHAPE)
+    for i in range(24):
+        xn = x + 0.3 * s1 * rs.standard_normal(SHAPE)
+        m0, m1 = den(x, s1), den(xn, s1)
+        st.space_update(tt(m0), tt(m1), s1, tt(x), tt(xn))
+        ora.update_space_step(m0, m1, s1, x, xn)
+        x = xn
+    assert st.rank == 48
+    w = make_inputs(5, SHAPE)
+    assert rel_l2(st.cov_dot(tt(w)), ora.denoiser_cov_vector_dot(w)) < 1e-4
+    for which in FOLDABLE:
+        op, oo = _ops(E, ctx, assets, which)
+        y, mu = _problem(full_state, oo, which)
+        res = {}
+        for mode in (E.CG_RESIDENT, E.CG_STREAMING):
+            ctx.set_cg_mode(mode)
+            try:
+                res[mode] = E.cg_solve(st, op, tt(y), tt(mu), SY2, 1.0, maxiter=100, fixed_iters=8)
+                assert ctx.cg_last_mode == mode
+            finally:
+                ctx.set_cg_mode(E.CG_AUTO)
+        mo, _ = fo.mat_solver(oo, y, mu, ora, s1, fixed_iters=8)
+        e_or, e_rs = rel_l2(res[E.CG_RESIDENT][0], mo), rel_l2(res[E.CG_RESIDENT][0], res[E.CG_STREAMING][0])
+        mat_a, info_a = E.cg_solve_async(st, op, tt(y), tt(mu), SY2, 1.0, maxiter=100, fixed_iters=8)
+        record("cg_rank48", op=which, err_vs_oracle=e_or, err_vs_streaming=e_rs, niter=res[E.CG_RESIDENT][1]["niter"][0])
+        assert e_or < 1e-4 and e_rs < 2e-5, (which, e_or, e_rs)
+        assert torch.equal(mat_a, res[E.CG_RESIDENT][0]) and info_a.fetch()["niter"] == [8]
+
+
 def test_cg_resident_rank_limit(E, ctx, assets, full_state):
     """Rank 0 (no Z at all) runs resident; forcing the resident kernel on a non-foldable operator is an error, not a
     silent switch."""
