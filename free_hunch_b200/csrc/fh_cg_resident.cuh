@@ -95,7 +95,7 @@ static inline uint4 fh_ll_load(const uint4* p) {
   v.x = q[0]; v.z = q[2];
   return v;
 }
-static inline void fh_ll_relax() { std::this_thread::yield(); }
+static inline void fh_ll_relax() { emu::relax(); }
 static inline void fh_ll_fail() { std::abort(); }
 static inline unsigned fh_f2u(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline float fh_u2f(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -43,8 +43,8 @@ int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channels, int hei
 int fh_ctx_destroy(fh_ctx* ctx);
 /* Which implementation fh_cg_solve uses in the DCT basis (same algorithm, cg.py:230-292, same results to rounding):
  *   FH_CG_STREAMING  five launches per iteration, Z streamed from L2/HBM by TMA, any batch, any rank <= 64;
- *   FH_CG_RESIDENT   one cooperative launch per image and solve, Z resident in shared memory (rank <= 32, operators
- *                    that fold into the DCT passes: inpainting mask, separable blur);
+ *   FH_CG_RESIDENT   one cooperative launch per image and solve, up to 32 rows of Z resident in shared memory (the rest
+ *                    re-read from L2), for operators that fold into the DCT passes: inpainting mask, separable blur;
  *   FH_CG_AUTO       resident where it applies and the batch is at most 4 images (the resident kernel takes the images
  *                    one after the other; from 5 images on the streaming iteration is faster per image) (default).
  * Results are bit-identical across batch sizes within one implementation, not between the two.
@@ -125,7 +125,8 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
 /* The same solve without any host read-back: returns once the work is queued on `stream`; the outcome of image b is
  * written to info_dev[b] (device memory) when its solve ends.  This is what lets a sampler run the whole guided loop
  * without a host synchronisation (the reference synchronises twice per CG iteration, cg.py:250,259).  Available where
- * the resident kernel applies (DCT basis, rank <= 32, mask or separable blur); otherwise FH_ESTATE -- use fh_cg_solve. */
+ * the resident kernel applies (DCT basis, mask or separable blur, batch <= 4 unless FH_CG_RESIDENT is set); otherwise
+ * FH_ESTATE -- use fh_cg_solve. */
 typedef struct { double residual_norm; int niter; int optimal; } fh_cg_info;
 int fh_cg_solve_async(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                       int maxiter, int fixed_iters, float* mat_out_dev, fh_cg_info* info_dev, void* stream);

@@ -211,17 +211,9 @@ def test_fused_dct_basis_path(E, assets, monkeypatch):
         assert rel_l2(mat, mat_cpu) < 2e-5, (name, rel_l2(mat, mat_cpu))
 
 
-def _pid_max():
-    try:
-        return int(open("/proc/sys/kernel/pid_max").read())
-    except OSError:
-        return 0
-
-
-@pytest.mark.skipif(_pid_max() < 40000, reason="emulating the 128-CTA cooperative grid needs 32768 concurrent threads (kernel.pid_max too small)")
 def test_resident_cg_kernel(E, assets):
     """The one-launch resident CG solve (fh_cg_resident.cuh) at 3 x 256 x 256, all 128 CTAs of its cooperative grid
-    emulated concurrently: 6-row strips that straddle channel planes, Z slices resident in shared memory, grid
+    emulated concurrently (32 768 fibers, tools/cuda_emu.h): 6-row strips that straddle channel planes, Z slices resident in shared memory, grid
     barriers, in-kernel initial residual / step / stop logic -- vs the oracle and vs the five-launch streaming path."""
     rs = np.random.RandomState(5)
     var = assets["dct_variance"]
@@ -268,4 +260,40 @@ def test_resident_cg_kernel(E, assets):
             assert ctx.cg_last_mode == E.CG_STREAMING
             assert rel_l2(mat, mat2) < 1e-5
             assert abs(info["residual_norm"][0] - info2["residual_norm"][0]) <= 1e-4 * info2["residual_norm"][0]
+    ctx.set_cg_mode(E.CG_AUTO)
+
+
+def test_resident_cg_kernel_rank_above_32(E, assets):
+    """fh_k_cg_resident<true>: rank 34 (17 BFGS pairs) -- 32 rows of Z resident, two re-read from global memory, 64-row
+    coefficient stage and owner mapping -- one CG iteration against the oracle, Gaussian blur folded in."""
+    rs = np.random.RandomState(9)
+    var = assets["dct_variance"]
+    shape = (1,) + var.shape
+    s0, s1 = 80.2878, 6.5
+    ctx = E.Context("cpu", max_batch=1)
+    st = E.CovState(ctx, 1, E.BASIS_DCT)
+    st.init(torch.tensor(var), s0 ** 2)
+    ora = fo.CovarianceOracleDCT(var, s0 ** 2, var.size)
+    st.time_update(None, None, s0, s1, only_covariance=True)
+    ora.update_time_step(np.zeros(shape), s0, s1, np.zeros(shape), only_covariance=True)
+    den = lambda x: fo.idct2(var.astype(np.float64) / (var + s1 ** 2) * fo.dct2(x)) + 0.02 * np.tanh(x)
+    x = np.clip(rs.standard_normal(shape), -1, 1) + s1 * rs.standard_normal(shape)
+    for _ in range(17):
+        xn = x + 0.3 * s1 * rs.standard_normal(shape)
+        m0, m1 = den(x), den(xn)
+        st.space_update(torch.tensor(m0), torch.tensor(m1), s1, torch.tensor(x), torch.tensor(xn))
+        ora.update_space_step(m0, m1, s1, x, xn)
+        x = xn
+    assert st.rank == 34
+    op = E.Operator.conv(ctx, assets["gaussian_ks61_std3"], 1)
+    oo = fo.GaussianBlurOracle(assets["gaussian_ks61_std3"], 0.1, otf_dtype=np.complex128)
+    xc = np.clip(rs.standard_normal(shape), -1, 1)
+    y = oo.A(xc) + 0.1 * rs.standard_normal(shape)
+    mu0 = 0.3 * xc
+    sy2 = float(np.float32(0.1) * np.float32(0.1))
+    ctx.set_cg_mode(E.CG_RESIDENT)
+    mat, info = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, 1.0, maxiter=50, fixed_iters=1)
+    assert ctx.cg_last_mode == E.CG_RESIDENT and info["niter"][0] == 1
+    mat_cpu, _ = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=1)
+    assert rel_l2(mat, mat_cpu) < 2e-5, rel_l2(mat, mat_cpu)
     ctx.set_cg_mode(E.CG_AUTO)
