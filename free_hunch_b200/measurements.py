@@ -130,11 +130,69 @@ class MotionBlurOperator(_ConvOperator):
         self.out_shape = self.in_shape
 
 
+def _cubic(t):
+    a = t.abs()
+    return torch.where(a <= 1, (1.5 * a - 2.5) * a * a + 1, torch.where(a <= 2, ((-0.5 * a + 2.5) * a - 4) * a + 2, torch.zeros_like(a)))
+
+
+class Resizer(torch.nn.Module):
+    """measurement_utils/resizer.py:8-76 for kernel='cubic' over the last two axes: antialiased bicubic resampling with
+    reflected borders.  Each dimension is one dense (n_out, n_in) matrix built once in float64 from the definition
+    (tap positions, scaled Keys kernel, normalisation, mirror indices: resizer.py:104-165) and applied as a matrix
+    product, instead of the reference's gather + broadcast-multiply + sum per dimension.  Once per image."""
+
+    def __init__(self, in_shape, scale_factor=None, output_shape=None, kernel=None, antialiasing=True):
+        super().__init__()
+        if kernel not in (None, "cubic"):
+            raise ValueError("free_hunch_b200.Resizer provides the 'cubic' kernel (the one measurements.py:91 uses)")
+        if scale_factor is None:
+            scale_factor = [o / i for o, i in zip(output_shape[-2:], in_shape[-2:])]
+        if not isinstance(scale_factor, (list, tuple)):
+            scale_factor = [scale_factor, scale_factor]
+        self.scales = [float(s) for s in scale_factor[-2:]]
+        for name, n, sc in zip(("rh", "rw"), in_shape[-2:], self.scales):
+            self.register_buffer(name, self._matrix(int(n), sc, antialiasing))
+
+    @staticmethod
+    def _matrix(n_in, scale, antialiasing):
+        n_out = int(np.ceil(n_in * scale))
+        aa = bool(antialiasing) and scale < 1
+        width = 4.0 / scale if aa else 4.0
+        u = torch.arange(1, n_out + 1, dtype=torch.float64) - (n_out - n_in * scale) / 2.0
+        c = u / scale + 0.5 * (1.0 - 1.0 / scale)
+        taps = int(np.ceil(width)) + 2
+        idx = torch.floor(c - width / 2.0)[:, None] + torch.arange(taps, dtype=torch.float64)[None, :] - 1
+        t = c[:, None] - idx - 1.0
+        w = scale * _cubic(scale * t) if aa else _cubic(t)
+        tot = w.sum(dim=1, keepdim=True)
+        w = (w / torch.where(tot == 0, torch.ones_like(tot), tot)).to(torch.float32)      # float32 weights like the reference
+        idx = torch.remainder(idx.to(torch.int64), 2 * n_in)
+        idx = torch.where(idx >= n_in, 2 * n_in - 1 - idx, idx)
+        R = torch.zeros(n_out, n_in, dtype=torch.float32)
+        R.index_put_((torch.arange(n_out)[:, None].expand_as(idx), idx), w, accumulate=True)
+        return R
+
+    def forward(self, in_tensor):
+        x = in_tensor
+        rh, rw = self.rh.to(x.dtype), self.rw.to(x.dtype)
+        return torch.matmul(torch.matmul(rh, x), rw.transpose(0, 1))
+
+
 @register_operator(name="super_resolution")
 class SuperResolutionOperator(_ConvOperator):
     """measurements.py:87-123.  A = downsample_sf . (k (*)) is the operator the solver uses
-    (conditioning_mechanisms.py:641-675) and is what forward() applies here; the reference synthesises y with
-    a bicubic `Resizer` instead (measurements.py:105), a once-per-image step listed under SURVEY.md 8(f) N3."""
+    (conditioning_mechanisms.py:641-675, `A` / `AT` / `transpose` here); `forward` synthesises the measurement with the
+    antialiased bicubic `Resizer` exactly like the reference (measurements.py:91,105) -- a different map from A."""
+
+    def forward(self, data, flatten=False, noiseless=False):
+        y = self.down_sample(data)
+        if not noiseless:
+            y = y + self.sigma_s.to(y.dtype) * torch.randn_like(y)
+        FB, FBC, F2B = self._otf(y)
+        self.pre_calculated = (FB, FBC, F2B, None)
+        if flatten:
+            return y, y.reshape(y.shape[0], -1)
+        return y
 
     def __init__(self, in_shape, scale_factor=4, sigma_s=0.1, device=None, kernel=None, kernel_dir=None, **kwargs):
         self._setup(in_shape, sigma_s, device)
@@ -145,6 +203,7 @@ class SuperResolutionOperator(_ConvOperator):
             k_index = scale_factor - 2 if scale_factor < 5 else 2
             kernel = kernels[0, k_index].astype(np.float64)
         self._make(kernel, sf=scale_factor)
+        self.down_sample = Resizer(self.in_shape, 1 / scale_factor).to(self.device)
         out = tuple(int(s / scale_factor) for s in self.in_shape[-2:])
         self.out_shape = (1, self.in_shape[-3], *out)
 

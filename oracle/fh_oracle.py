@@ -417,6 +417,48 @@ class SuperResolutionOracle(_FFTOperator):
         return super().AT(upsample(y, self.scale_factor))
 
 
+# ---- measurement synthesis for super-resolution: the bicubic `Resizer` --------------------------
+def _cubic(t):
+    """Keys cubic (a = -0.5), measurement_utils/resizer.py:171-176."""
+    a = np.abs(t)
+    return np.where(a <= 1, (1.5 * a - 2.5) * a * a + 1, np.where(a <= 2, ((-0.5 * a + 2.5) * a - 4) * a + 2, 0.0))
+
+
+def resizer_matrix(n_in: int, scale: float, antialiasing: bool = True) -> np.ndarray:
+    """Dense (n_out, n_in) matrix of one dimension of Resizer(kernel='cubic') -- resizer.py:104-165: output pixel u
+    (1-based) sits at c = u'/scale + (1 - 1/scale)/2 with u' = u - (n_out - n_in*scale)/2 (:117-130); with antialiasing
+    (downscaling only, :27) the kernel is scale*cubic(scale*t), 4/scale wide (:112-113); ceil(width)+2 candidate taps
+    start at floor(c - width/2) - 1 (:133-143), weights are normalised to sum 1 (:151-153) and indices are reflected at
+    the borders (:156-157).  Weights are rounded to float32 like the reference's weight tensors (:44)."""
+    n_out = int(np.ceil(n_in * scale))                                    # :98
+    aa = antialiasing and scale < 1
+    width = 4.0 / scale if aa else 4.0
+    kern = (lambda t: scale * _cubic(scale * t)) if aa else _cubic
+    u = np.arange(1, n_out + 1) - (n_out - n_in * scale) / 2.0
+    c = u / scale + 0.5 * (1.0 - 1.0 / scale)
+    left = np.floor(c - width / 2.0)
+    taps = int(np.ceil(width)) + 2
+    idx = (left[:, None] + np.arange(taps)[None, :] - 1).astype(np.int64)          # 0-based input index, may be out of range
+    w = kern(c[:, None] - idx - 1.0)
+    tot = w.sum(axis=1)
+    tot[tot == 0] = 1.0
+    w = (w / tot[:, None]).astype(np.float32).astype(np.float64)
+    idx = np.mod(idx, 2 * n_in)
+    idx = np.where(idx >= n_in, 2 * n_in - 1 - idx, idx)                             # mirror
+    R = np.zeros((n_out, n_in))
+    np.add.at(R, (np.repeat(np.arange(n_out), taps), idx.reshape(-1)), w.reshape(-1))
+    return R
+
+
+def bicubic_downsample(x, scale_factor: int):
+    """y = Resizer(in_shape, 1/scale_factor)(x) over the last two axes (measurements.py:91,105): the measurement the
+    reference synthesises for super-resolution (NOT the operator A its solver uses)."""
+    x = np.asarray(x, np.float64)
+    Rh = resizer_matrix(x.shape[-2], 1.0 / scale_factor)
+    Rw = resizer_matrix(x.shape[-1], 1.0 / scale_factor)
+    return np.einsum("oh,...hw,pw->...op", Rh, x, Rw)
+
+
 def mask_random(image_size: int, prob_range: Tuple[float, float], rng=np.random) -> np.ndarray:
     """measurements.py:287-299.  Consumes the *global* numpy RNG exactly like the reference:
     one uniform() then one choice(replace=False).  Returns (1,3,H,W) float32 of {0,1}, 1 = observed."""
