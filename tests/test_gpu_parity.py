@@ -180,8 +180,14 @@ def test_sr_operator(E, ctx, assets):
     e = dict(A=rel_l2(Ax, oo.A(x)), AT=rel_l2(ATy, oo.AT(yv)))
     lhs, rhs = float((Ax.double() * tt(yv).cuda()).sum()), float((tt(x).cuda() * ATy.double()).sum())
     e["adjoint"] = abs(lhs - rhs) / abs(lhs)
+    # measurement synthesis (the reference's forward(): antialiased bicubic Resizer, not A) on the device
+    from free_hunch_b200.measurements import get_operator
+    sr = get_operator("super_resolution", kernel=assets["bicubic_x4"], scale_factor=4, in_shape=SHAPE, sigma_s=0.1, device=torch.device("cuda"))
+    y = sr.forward(tt(x).cuda(), noiseless=True)
+    e["forward_resizer"] = rel_l2(y, fo.bicubic_downsample(x, 4))
     record("op_sr", **e)
-    assert e["A"] < 1e-6 and e["AT"] < 1e-6 and e["adjoint"] < 1e-5
+    assert y.shape == (1, 3, 64, 64) and y.dtype == torch.float64 and sr.pre_calculated[0] is not None
+    assert e["A"] < 1e-6 and e["AT"] < 1e-6 and e["adjoint"] < 1e-5 and e["forward_resizer"] < 1e-6
 
 
 @pytest.mark.parametrize("mtype", ["random", "box"])

@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from free_hunch_b200.outputs import aggregate_mean, decode_uint8, image_filename, psnr_uint8
 from free_hunch_b200.sharding import gather_images, image_seed, shard_indices
 
 
@@ -46,7 +47,8 @@ def _worker(rank, world, port, n, q):
     imgs = torch.stack([torch.from_numpy(np.random.RandomState(image_seed(0, i)).standard_normal((3, 4, 4))) for i in idx]) \
         if idx else torch.zeros((0, 3, 4, 4), dtype=torch.float64)
     out = gather_images(imgs, idx, n)
-    q.put((rank, out.numpy()))
+    agg = aggregate_mean(10.0 + rank)                 # per-rank means 10 and 11 -> 10.5 on every rank
+    q.put((rank, out.numpy(), agg))
     dist.destroy_process_group()
 
 
@@ -58,7 +60,9 @@ def test_gather_world2_gloo(n):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in procs)
+    got = [q.get(timeout=120) for _ in procs]
+    res = {r: a for r, a, _ in got}
+    assert all(abs(g - 10.5) < 1e-6 for _, _, g in got)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -71,3 +75,15 @@ def test_gather_single_process():
     imgs = torch.arange(3 * 2, dtype=torch.float32).reshape(3, 2)
     out = gather_images(imgs, [2, 0, 1], 3)
     assert torch.equal(out, imgs[[1, 2, 0]])
+
+
+def test_output_side_helpers():
+    """decode (encoders.py:72-73: scale, clip, truncate), file names, PSNR (skimage definition)."""
+    x = torch.tensor([-1.5, -1.0, -0.999, 0.0, 0.5, 0.999, 1.0, 2.0])
+    assert decode_uint8(x).tolist() == [0, 0, 0, 128, 191, 255, 255, 255] and decode_uint8(x.double()).dtype == torch.uint8
+    assert image_filename(17, 3) == "000017_000003.png"
+    a = torch.zeros(3, 8, 8, dtype=torch.uint8)
+    b = a.clone(); b[0, 0, 0] = 16
+    assert psnr_uint8(a, a) == float("inf")
+    assert abs(psnr_uint8(a, b) - 10 * np.log10(255.0 ** 2 / (256.0 / 192))) < 1e-9
+    assert aggregate_mean(3.25) == 3.25                # no process group: the value itself
