@@ -148,6 +148,7 @@ struct fh_op {
   int* t_dy; int* t_dx; float* t_w; int nt, ymin, ymax, xmin, xmax;
   float *kr, *kc; int nr, nc, cr, cc;
   float* psf_dense; int ks;           // dense PSF on the device (fast x4 super-resolution kernels)
+  int4* runs; float *run_wf, *run_wt; int nruns, nrun_taps;   // the PSF as one dense vertical run per column (fh_k_conv_runs)
 };
 
 static inline dim3 ew_grid(long d, int B) { return dim3((unsigned)fh_nchunks(d), (unsigned)B, 1); }
@@ -724,6 +725,29 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
   FH_CUDA(cudaMemcpy(o->t_dy, dy.data(), w.size() * sizeof(int), cudaMemcpyHostToDevice));
   FH_CUDA(cudaMemcpy(o->t_dx, dx.data(), w.size() * sizeof(int), cudaMemcpyHostToDevice));
   FH_CUDA(cudaMemcpy(o->t_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    // one dense vertical run per PSF column (fh_k_conv_runs): weights in window order for both directions, every run
+    // padded to a multiple of 4 with zeros
+    std::vector<int4> runs; std::vector<float> wf, wt;
+    for (int b = 0; b < ks; ++b) {
+      int lo = -1, hi = -1;
+      for (int a = 0; a < ks; ++a) if (psf[a * ks + b] != 0.f) { if (lo < 0) lo = a; hi = a; }
+      if (lo < 0) continue;
+      const int L = hi - lo + 1, Lp = (L + 3) & ~3;
+      runs.push_back(make_int4(b - cen, lo - cen, L, (int)wf.size()));
+      for (int k = 0; k < Lp; ++k) {
+        wf.push_back(k < L ? psf[(hi - k) * ks + b] : 0.f);      // forward: the window starts at the LAST tap of the run
+        wt.push_back(k < L ? psf[(lo + k) * ks + b] : 0.f);
+      }
+    }
+    o->nruns = (int)runs.size(); o->nrun_taps = (int)wf.size();
+    FH_CUDA(cudaMalloc((void**)&o->runs, runs.size() * sizeof(int4)));
+    FH_CUDA(cudaMalloc((void**)&o->run_wf, wf.size() * sizeof(float)));
+    FH_CUDA(cudaMalloc((void**)&o->run_wt, wt.size() * sizeof(float)));
+    FH_CUDA(cudaMemcpy(o->runs, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    FH_CUDA(cudaMemcpy(o->run_wf, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FH_CUDA(cudaMemcpy(o->run_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   // rank-1 test on the support box: psf == col (x) row exactly (to 1e-7 of the peak) -> separable path
   o->separable = false;
   if (sf == 1) {
@@ -758,6 +782,7 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
 extern "C" int fh_op_destroy(fh_op* o) {
   if (!o) return FH_OK;
   cudaFree(o->t_dy); cudaFree(o->t_dx); cudaFree(o->t_w); cudaFree(o->kr); cudaFree(o->kc); cudaFree(o->psf_dense);
+  cudaFree(o->runs); cudaFree(o->run_wf); cudaFree(o->run_wt);
   free(o);
   return FH_OK;
 }
@@ -782,6 +807,15 @@ extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int
       const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
       const size_t smem = (size_t)(th * tw + th * 33) * sizeof(float);
       FH_LAUNCH(fh_k_conv_sep, grid, block, smem, stream, in, out, k, c->H, c->W, transpose);
+    } else if (c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
+               (size_t)(64 + o->ymax - o->ymin + FH_CONV_PAD_ROWS) * ((32 + o->xmax - o->xmin) | 1) * sizeof(float) <= 40 * 1024) {
+      // (a PSF whose columns are mostly gaps -- more than half of the run taps zero -- stays on the tap list)
+      FhRuns r{o->runs, o->run_wf, o->run_wt, o->nruns, o->nrun_taps, o->ymin, o->ymax, o->xmin, o->xmax};
+      const int tile_h = planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms ? 64 : 32;      // few planes: smaller tiles, more CTAs
+      const int th = tile_h + (o->ymax - o->ymin) + FH_CONV_PAD_ROWS, tw = (32 + (o->xmax - o->xmin)) | 1;
+      const size_t smem = (size_t)th * tw * sizeof(float);
+      if (tile_h == 64) FH_LAUNCH(fh_k_conv_runs<64>, dim3(c->W / 32, c->H / 64, planes), dim3(32, 8), smem, stream, in, out, r, c->H, c->W, transpose);
+      else FH_LAUNCH(fh_k_conv_runs<32>, dim3(c->W / 32, c->H / 32, planes), dim3(32, 4), smem, stream, in, out, r, c->H, c->W, transpose);
     } else {
       FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
       const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;

@@ -646,6 +646,86 @@ fh_k_conv_taps(const float* __restrict__ in, float* __restrict__ out, FhTaps tap
   for (int q = 0; q < 4; ++q) out[plane + (size_t)(i0 + threadIdx.y + 8 * q) * W + j0 + threadIdx.x] = acc[q];
 }
 
+// The same convolution organised by COLUMNS of the PSF: column dx of the PSF is one dense vertical run (dy0 .. dy0+L-1,
+// zeros inside kept), and a thread produces 8 consecutive output rows of one image column from a rolling 8-register
+// window over the input column: a run costs 8 + L shared-memory loads for 8 L FMAs, where the tap list
+// (fh_k_conv_taps) spends one load and ~4 instructions per FMA and is issue-bound (ncu: 85 % issue-active, 22 % of the
+// instructions FMAs).  The motion-blur PSF of the reference (217 taps in a 56 x 16 box, measurements.py:126-161) becomes
+// 16 runs with 302 taps (332 after padding every run to a multiple of 4 with zero weights, so that the inner loop has
+// no per-tap predicate).  64 x 32 output tile per CTA (8 row groups x 32 columns), halo staged in shared memory.
+//   run r: weights w[woff + k], k < Lpad, already in the order the window meets them:
+//   transpose = 0:  out[i][j] = sum_l psf[dy0 + l][dx] in[i - dy0 - l][j - dx]   (window starts at row i - dy0 - (L-1))
+//   transpose = 1:  out[i][j] = sum_l psf[dy0 + l][dx] in[i + dy0 + l][j + dx]   (window starts at row i + dy0)
+struct FhRuns { const int4* run; const float* w_fwd; const float* w_tr; int nruns, ntaps; int ymin, ymax, xmin, xmax; };   // run = (dx, dy0, L, woff)
+#define FH_CONV_MAX_RUNS 128
+#define FH_CONV_PAD_ROWS 4            // the window runs up to 3 zero-weight taps past the run, plus one look-ahead load
+// TILE_H = 64 (256 threads) for many planes, 32 (128 threads, twice the CTAs) when a launch has only a few planes.
+template <int TILE_H>
+__global__ void __launch_bounds__(TILE_H * 4)
+fh_k_conv_runs(const float* __restrict__ in, float* __restrict__ out, FhRuns R, int H, int W, int transpose) {
+  constexpr int NT = TILE_H * 4, NY = TILE_H / 8;
+  FH_DYN_SMEM(float, sm);
+  __shared__ int4 s_run[FH_CONV_MAX_RUNS];                 // (first tile row of the window, tile column offset, Lpad, woff)
+  __shared__ __align__(16) float s_w[FH_CONV_MAX_TAPS];
+  const int oy0 = transpose ? R.ymin : -R.ymax, oy1 = transpose ? R.ymax : -R.ymin;
+  const int ox0 = transpose ? R.xmin : -R.xmax, ox1 = transpose ? R.xmax : -R.xmin;
+  const int th = TILE_H + (oy1 - oy0) + FH_CONV_PAD_ROWS, tw = 32 + (ox1 - ox0);
+  const int tws = tw | 1;
+  float* tile = sm;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const int i0 = blockIdx.y * TILE_H, j0 = blockIdx.x * 32;
+  for (int t = tid; t < R.nruns; t += NT) {
+    const int4 r = R.run[t];                               // (dx, dy0, L, woff)
+    const int row0 = transpose ? (r.y - oy0) : (-r.y - (r.z - 1) - oy0);
+    const int col = (transpose ? r.x : -r.x) - ox0;
+    s_run[t] = make_int4(row0, col, (r.z + 3) & ~3, r.w);
+  }
+  const float* wsrc = transpose ? R.w_tr : R.w_fwd;
+  for (int t = tid; t < R.ntaps; t += NT) s_w[t] = wsrc[t];
+  const bool pow2 = ((H & (H - 1)) | (W & (W - 1))) == 0;
+  for (int r = threadIdx.y; r < th; r += NY) {             // the pad rows are real image rows too (finite: 0 * x = 0)
+    int gi = i0 + oy0 + r;
+    if (pow2) gi &= H - 1; else { gi %= H; if (gi < 0) gi += H; }
+    const float* srow = in + plane + (size_t)gi * W;
+    for (int c = threadIdx.x; c < tw; c += 32) {
+      int gj = j0 + ox0 + c;
+      if (pow2) gj &= W - 1; else { gj %= W; if (gj < 0) gj += W; }
+      tile[r * tws + c] = srow[gj];
+    }
+  }
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const float* base = tile + (threadIdx.y * 8) * tws + threadIdx.x;
+#define FH_CONV_TAP(wv, kk)                                                                   \
+  do {                                                                                        \
+    _Pragma("unroll") for (int e = 0; e < 8; ++e) acc[e] = fmaf((wv), win[(e + (kk)) & 7], acc[e]);  \
+    win[(kk)] = q[(kk) * tws];                           /* the window moves down one input row */     \
+  } while (0)
+  for (int t = 0; t < R.nruns; ++t) {
+    const int4 r = s_run[t];
+    const float* q = base + r.x * tws + r.y;
+    const float4* wq = reinterpret_cast<const float4*>(s_w + r.w);
+    float win[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) win[e] = q[e * tws];
+    q += 8 * tws;
+    for (int k0 = 0; k0 < r.z; k0 += 8) {
+      const float4 wa = wq[0];
+      FH_CONV_TAP(wa.x, 0); FH_CONV_TAP(wa.y, 1); FH_CONV_TAP(wa.z, 2); FH_CONV_TAP(wa.w, 3);
+      if (k0 + 4 >= r.z) break;                            // uniform: runs are padded to multiples of 4
+      const float4 wb = wq[1];
+      FH_CONV_TAP(wb.x, 4); FH_CONV_TAP(wb.y, 5); FH_CONV_TAP(wb.z, 6); FH_CONV_TAP(wb.w, 7);
+      q += 8 * tws; wq += 2;
+    }
+  }
+#undef FH_CONV_TAP
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[plane + (size_t)(i0 + threadIdx.y * 8 + e) * W + j0 + threadIdx.x] = acc[e];
+}
+
 // Separable circular convolution (rank-1 PSF = col (x) row):  out = conv_cols(kc) conv_rows(kr) in.
 // Taps: kr[a] at offset (a - cr), kc[a] at offset (a - cc); transpose flips the sign of the offsets.
 struct FhSepTaps { const float* kr; const float* kc; int nr, nc, cr, cc; };

@@ -49,6 +49,8 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return {x, y}; }
