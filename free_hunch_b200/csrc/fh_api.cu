@@ -96,6 +96,7 @@ extern "C" int fh_prof_report(char* buf, int buflen) { if (buf && buflen > 0) bu
     if (_e != cudaSuccess) FH_FAIL(FH_ECUDA, "kernel launch failed: %s", cudaGetErrorString(_e)); \
   } while (0)
 
+#define FH_STATE_POOL 2                // parked states per context (one image's state is ~60 MB)
 struct fh_ctx {
   int device, max_batch, C, H, W, max_rank;
   long d;
@@ -126,7 +127,7 @@ struct fh_ctx {
   int res_ok;                         // the resident kernel's cooperative grid fits this device
   // Device buffers of destroyed states, kept for the next fh_state_create of the same batch: a sampler builds one state
   // per image, and cudaMalloc / cudaFree of its ~60 MB synchronise the device (measured: sporadic 10-100 ms stalls).
-  struct fh_state* state_pool[4];
+  struct fh_state* state_pool[FH_STATE_POOL];
   long long* trace;                   // FH_TRACE=1: clock64 checkpoints of the fused CG kernels (8 kernels x 16 slots)
 };
 
@@ -276,7 +277,7 @@ extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
 
 extern "C" int fh_ctx_destroy(fh_ctx* c) {
   if (!c) return FH_OK;
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < FH_STATE_POOL; ++i)
     if (fh_state* p = c->state_pool[i]) {
       cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs);
       free(p);
@@ -363,7 +364,7 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
   fh_state* s = (fh_state*)calloc(1, sizeof(fh_state));
   s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0; s->sig2 = 1.0;
   const size_t vec = (size_t)batch * s->d * sizeof(float);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < FH_STATE_POOL; ++i) {
     fh_state* p = c->state_pool[i];
     if (p && p->B == batch) {                               // reuse the buffers of a destroyed state (no cudaMalloc)
       c->state_pool[i] = nullptr;
@@ -384,7 +385,7 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
 extern "C" int fh_state_destroy(fh_state* s) {
   if (!s) return FH_OK;
   if (s->ctx)
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < FH_STATE_POOL; ++i)
       if (!s->ctx->state_pool[i]) {                         // park the buffers; work queued on them is stream-ordered
         s->ctx->state_pool[i] = s;                          // before whatever the next owner queues
         return FH_OK;
@@ -807,15 +808,16 @@ extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int
       const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
       const size_t smem = (size_t)(th * tw + th * 33) * sizeof(float);
       FH_LAUNCH(fh_k_conv_sep, grid, block, smem, stream, in, out, k, c->H, c->W, transpose);
-    } else if (c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
+    } else if (planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms && c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
                (size_t)(64 + o->ymax - o->ymin + FH_CONV_PAD_ROWS) * ((32 + o->xmax - o->xmin) | 1) * sizeof(float) <= 40 * 1024) {
-      // (a PSF whose columns are mostly gaps -- more than half of the run taps zero -- stays on the tap list)
+      // Enough planes to fill the machine with 64 x 32 tiles (measured: 84 vs 115 us at 48 planes).  With a few planes the
+      // launch is latency-bound and the tap-list kernel's 32 x 32 tiles win (21 us at 3 planes; column runs: 23 us with
+      // 64-row tiles, 26 us with 32-row tiles).  A PSF whose columns are mostly gaps (more than half of the run taps zero)
+      // stays on the tap list as well.
       FhRuns r{o->runs, o->run_wf, o->run_wt, o->nruns, o->nrun_taps, o->ymin, o->ymax, o->xmin, o->xmax};
-      const int tile_h = planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms ? 64 : 32;      // few planes: smaller tiles, more CTAs
-      const int th = tile_h + (o->ymax - o->ymin) + FH_CONV_PAD_ROWS, tw = (32 + (o->xmax - o->xmin)) | 1;
+      const int th = 64 + (o->ymax - o->ymin) + FH_CONV_PAD_ROWS, tw = (32 + (o->xmax - o->xmin)) | 1;
       const size_t smem = (size_t)th * tw * sizeof(float);
-      if (tile_h == 64) FH_LAUNCH(fh_k_conv_runs<64>, dim3(c->W / 32, c->H / 64, planes), dim3(32, 8), smem, stream, in, out, r, c->H, c->W, transpose);
-      else FH_LAUNCH(fh_k_conv_runs<32>, dim3(c->W / 32, c->H / 32, planes), dim3(32, 4), smem, stream, in, out, r, c->H, c->W, transpose);
+      FH_LAUNCH(fh_k_conv_runs<64>, dim3(c->W / 32, c->H / 64, planes), dim3(32, 8), smem, stream, in, out, r, c->H, c->W, transpose);
     } else {
       FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
       const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;
