@@ -793,6 +793,13 @@ static long op_ylen(const fh_op* o) {
   return (long)c->C * (c->H / o->sf) * (c->W / o->sf);
 }
 
+static inline bool conv_runs_pays(const fh_ctx* c, int planes) {
+#ifdef FH_EMU
+  if (getenv("FH_EMU_CONV_RUNS")) return true;            // CPU emulation: the test picks the kernel
+#endif
+  return planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms;
+}
+
 extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int transpose, void* stream) {
   if (!o || !in || !out || batch < 1) FH_FAIL(FH_EINVAL, "bad fh_op_apply arguments");
   fh_ctx* c = o->ctx;
@@ -808,7 +815,7 @@ extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int
       const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
       const size_t smem = (size_t)(th * tw + th * 33) * sizeof(float);
       FH_LAUNCH(fh_k_conv_sep, grid, block, smem, stream, in, out, k, c->H, c->W, transpose);
-    } else if (planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms && c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
+    } else if (conv_runs_pays(c, planes) && c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
                (size_t)(64 + o->ymax - o->ymin + FH_CONV_PAD_ROWS) * ((32 + o->xmax - o->xmin) | 1) * sizeof(float) <= 40 * 1024) {
       // Enough planes to fill the machine with 64 x 32 tiles (measured: 84 vs 115 us at 48 planes).  With a few planes the
       // launch is latency-bound and the tap-list kernel's 32 x 32 tiles win (21 us at 3 planes; column runs: 23 us with

@@ -92,7 +92,7 @@ def test_reference_unit_test_preseeded_vectors(E, pairs):
     assert rel_l2(inv_cov, g[p + "inv_cov"]) < 1e-4
 
 
-def test_operators_and_cg_small(E, assets):
+def test_operators_and_cg_small(E, assets, monkeypatch):
     """Operators (vs the oracle's FFT operators with a float64 OTF) and batched CG on 2 x 64 x 64 images."""
     rs = np.random.RandomState(0)
     Hh, C = 64, 2
@@ -103,6 +103,11 @@ def test_operators_and_cg_small(E, assets):
         oo = fo.GaussianBlurOracle(assets[key], 0.1, image_size=Hh, otf_dtype=np.complex128)
         assert rel_l2(op.apply(torch.tensor(x)), oo.A(x)) < 1e-6
         assert rel_l2(op.apply(torch.tensor(x), transpose=True), oo.AT(x)) < 1e-6
+    # the motion PSF through both pixel-space kernels: the tap list above (few planes), the column-run kernel here
+    monkeypatch.setenv("FH_EMU_CONV_RUNS", "1")
+    assert rel_l2(op.apply(torch.tensor(x)), oo.A(x)) < 1e-6
+    assert rel_l2(op.apply(torch.tensor(x), transpose=True), oo.AT(x)) < 1e-6
+    monkeypatch.delenv("FH_EMU_CONV_RUNS")
     op = E.Operator.conv(ctx, assets["bicubic_x4"], 4)
     oo = fo.SuperResolutionOracle(assets["bicubic_x4"], 0.1, 4, image_size=Hh, otf_dtype=np.complex128)
     ys = rs.standard_normal((2, C, Hh // 4, Hh // 4))
