@@ -160,6 +160,19 @@ def test_argument_errors(E):
         E.Operator.conv(ctx, np.zeros((4, 4), np.float32), 1)       # even kernel size
     with pytest.raises(_lib.FreeHunchLibraryError):
         E.CovState(ctx, 2, E.BASIS_IDENTITY)                         # batch > max_batch
+    with pytest.raises(_lib.FreeHunchLibraryError):
+        ctx.set_cg_mode(7)                                           # not one of FH_CG_AUTO / STREAMING / RESIDENT
+    # the asynchronous solve exists only where the resident kernel applies: identity basis -> FH_ESTATE -> None
+    st = E.CovState(ctx, 1, E.BASIS_IDENTITY)
+    st.init(torch.ones(64), 4.0)
+    op = E.Operator.inpaint(ctx, np.ones((8, 8), np.float32))
+    y = torch.zeros(1, 1, 8, 8)
+    assert E.cg_solve_async(st, op, y, y, 0.01, 1.0) is None
+    # a destroyed state's buffers are reused by the next state of the same batch (no cudaMalloc / cudaFree per image)
+    st.close()
+    st2 = E.CovState(ctx, 1, E.BASIS_IDENTITY)
+    st2.init(torch.full((64,), 2.0), 9.0)
+    assert st2.rank == 0 and rel_l2(st2.cov_dot(torch.ones(1, 1, 8, 8)).reshape(-1), 2.0 * np.ones(64)) < 1e-6
 
 
 def test_fused_dct_basis_path(E, assets, monkeypatch):
