@@ -436,7 +436,7 @@ static int core_at(fh_state* s, const float* delta, double* Gs_out, const float*
   int rc = gram(s, s->m, xr, nx, delta, stream);
   if (rc) return rc;
   const size_t smem = (size_t)(2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * sizeof(double);
-  FH_LAUNCH(fh_k_core, dim3(s->B), dim3(256), smem, stream, c->gramK, s->Gz, s->m, Gs_out, tu_s ? 1 : 0, var2_old, c->coef, c->status);
+  FH_LAUNCH(fh_k_core, dim3(s->B), dim3(FH_CORE_THREADS), smem, stream, c->gramK, s->Gz, s->m, Gs_out, tu_s ? 1 : 0, var2_old, c->coef, c->status);
   FH_KCHECK();
   return FH_OK;
 }
@@ -793,11 +793,14 @@ static long op_ylen(const fh_op* o) {
   return (long)c->C * (c->H / o->sf) * (c->W / o->sf);
 }
 
+// The column-run kernel is used for every batch size: choosing by the number of planes (the tap list is 2 us faster
+// per launch at 3 planes: 21 vs 23 us) would make a batch-4 solve differ from four batch-1 solves in the last bits.
 static inline bool conv_runs_pays(const fh_ctx* c, int planes) {
 #ifdef FH_EMU
-  if (getenv("FH_EMU_CONV_RUNS")) return true;            // CPU emulation: the test picks the kernel
+  return getenv("FH_EMU_CONV_RUNS") != nullptr;           // CPU emulation: the test picks the kernel, default tap list
 #endif
-  return planes * (c->W / 32) * (c->H / 64) >= 2 * c->sms;
+  (void)c; (void)planes;
+  return true;
 }
 
 extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int transpose, void* stream) {
@@ -817,10 +820,8 @@ extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int
       FH_LAUNCH(fh_k_conv_sep, grid, block, smem, stream, in, out, k, c->H, c->W, transpose);
     } else if (conv_runs_pays(c, planes) && c->H % 64 == 0 && o->nruns <= FH_CONV_MAX_RUNS && o->nrun_taps <= FH_CONV_MAX_TAPS && o->nrun_taps <= 2 * o->nt &&
                (size_t)(64 + o->ymax - o->ymin + FH_CONV_PAD_ROWS) * ((32 + o->xmax - o->xmin) | 1) * sizeof(float) <= 40 * 1024) {
-      // Enough planes to fill the machine with 64 x 32 tiles (measured: 84 vs 115 us at 48 planes).  With a few planes the
-      // launch is latency-bound and the tap-list kernel's 32 x 32 tiles win (21 us at 3 planes; column runs: 23 us with
-      // 64-row tiles, 26 us with 32-row tiles).  A PSF whose columns are mostly gaps (more than half of the run taps zero)
-      // stays on the tap list as well.
+      // 64 x 32 tiles: 84 vs 115 us at 48 planes, 23 vs 21 us at 3 planes (latency-bound there; 32-row tiles: 26 us).
+      // A PSF whose columns are mostly gaps (more than half of the run taps zero) stays on the tap list.
       FhRuns r{o->runs, o->run_wf, o->run_wt, o->nruns, o->nrun_taps, o->ymin, o->ymax, o->xmin, o->xmax};
       const int th = 64 + (o->ymax - o->ymin) + FH_CONV_PAD_ROWS, tw = (32 + (o->xmax - o->xmin)) | 1;
       const size_t smem = (size_t)th * tw * sizeof(float);

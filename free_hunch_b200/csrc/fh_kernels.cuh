@@ -310,41 +310,52 @@ fh_k_gram_reduce(const double* __restrict__ partial, int nparts, int R, double* 
 // Gauss-Jordan inverse with partial pivoting of the n x n matrix A (row-major, ld = FH_MAXM) into Ainv.
 // Returns (in every thread) 0 on success, 1 if a pivot underflowed.
 __device__ inline int fh_invert(double* A, double* Ainv, int n, double* s_red, int* s_piv) {
+  // Three barriers per column (the first version had six and let thread 0 scan the column for the pivot alone, which was
+  // half of fh_k_core's time): warp 0 finds the pivot with a shuffle arg-max (first row among equals, like a serial
+  // scan), then the old pivot row / row c and the elimination factors are staged, then every element is updated from
+  // the staged copies.  Same arithmetic, same order of operations per element as the plain algorithm.
+  __shared__ double s_rowp[2 * FH_MAXM], s_rowc[2 * FH_MAXM];
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int idx = tid; idx < n * n; idx += nt) Ainv[(idx / n) * FH_MAXM + (idx % n)] = ((idx / n) == (idx % n)) ? 1.0 : 0.0;
   __syncthreads();
   int bad = 0;
   for (int c = 0; c < n; ++c) {
-    if (tid == 0) {
-      int p = c; double best = fabs(A[c * FH_MAXM + c]);
-      for (int r = c + 1; r < n; ++r) { double v = fabs(A[r * FH_MAXM + c]); if (v > best) { best = v; p = r; } }
-      s_piv[0] = p; s_piv[1] = (best < 1e-300) ? 1 : 0;
+    if (tid < 32) {
+      double best = -1.0; int p = c;
+      for (int r = c + tid; r < n; r += 32) { const double v = fabs(A[r * FH_MAXM + c]); if (v > best) { best = v; p = r; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, p, o);
+        if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+      }
+      if (tid == 0) { s_piv[0] = p; s_piv[1] = (best < 1e-300) ? 1 : 0; }
     }
     __syncthreads();
     const int p = s_piv[0];
     bad |= s_piv[1];
-    if (p != c) {
-      for (int j = tid; j < 2 * n; j += nt) {
-        double* M = (j < n) ? A : Ainv; const int jj = (j < n) ? j : j - n;
-        double t = M[c * FH_MAXM + jj]; M[c * FH_MAXM + jj] = M[p * FH_MAXM + jj]; M[p * FH_MAXM + jj] = t;
-      }
-    }
-    __syncthreads();
-    const double inv = 1.0 / A[c * FH_MAXM + c];
-    __syncthreads();
+    const double inv = 1.0 / A[p * FH_MAXM + c];
     for (int j = tid; j < 2 * n; j += nt) {
-      double* M = (j < n) ? A : Ainv; const int jj = (j < n) ? j : j - n;
-      M[c * FH_MAXM + jj] *= inv;
+      const double* M = (j < n) ? A : Ainv; const int jj = (j < n) ? j : j - n;
+      s_rowp[j] = M[p * FH_MAXM + jj] * inv;               // the new row c
+      s_rowc[j] = M[c * FH_MAXM + jj];                     // what row p receives (p != c)
     }
+    // elimination factors of the matrix AFTER the row swap: row p holds the old row c
+    for (int r = tid; r < n; r += nt) s_red[r] = (r == c) ? 0.0 : A[((r == p) ? c : r) * FH_MAXM + c];
     __syncthreads();
-    // eliminate column c from all other rows; factors read before being overwritten
-    for (int r = tid; r < n; r += nt) s_red[r] = (r == c) ? 0.0 : A[r * FH_MAXM + c];
-    __syncthreads();
-    for (int idx = tid; idx < n * 2 * n; idx += nt) {
-      const int r = idx / (2 * n), j = idx % (2 * n);
-      double* M = (j < n) ? A : Ainv; const int jj = (j < n) ? j : j - n;
-      const double f = s_red[r];
-      if (f != 0.0) M[r * FH_MAXM + jj] -= f * M[c * FH_MAXM + jj];
+    {
+      // thread = (column j of [A | Ainv], row group): the staged pivot-row entry stays in a register while the thread
+      // walks down its rows -- no division per element, conflict-free shared-memory columns
+      const int per = (2 * n <= 64) ? 64 : 128, j = tid & (per - 1), g = tid / per, ng = nt / per;
+      if (j < 2 * n) {
+        double* M = (j < n) ? A : Ainv; const int jj = (j < n) ? j : j - n;
+        const double rp = s_rowp[j], rc = s_rowc[j];
+        for (int r = g; r < n; r += ng) {
+          const double f = s_red[r];
+          const double cur = (r == p) ? rc : M[r * FH_MAXM + jj];
+          M[r * FH_MAXM + jj] = (r == c) ? rp : ((f != 0.0) ? cur - f * rp : cur);
+        }
+      }
     }
     __syncthreads();
   }
@@ -356,7 +367,8 @@ __device__ inline int fh_invert(double* A, double* Ainv, int n, double* s_red, i
 //   c1 = Gz zs;  zt = zds + var2_old*zdps + var2_old*K c1;  c2 = Gs zt;  coef = var2_old*c1 + c2
 // where zs = Z s, zds = Z(delta s), zdps = Z(delta pi s) are columns m+2, m, m+1 of the weighted Gram whose
 // extra rows were [s, pi.*s, s./delta].
-__global__ void __launch_bounds__(256)
+#define FH_CORE_THREADS 1024          // one CTA per image: latency-bound column steps, so as many row groups as a CTA can have
+__global__ void __launch_bounds__(FH_CORE_THREADS)
 fh_k_core(const double* __restrict__ K, const double* __restrict__ Gz, int m, double* __restrict__ Gs,
           int time_update, double var2_old, double* __restrict__ coef, int* __restrict__ status) {
   FH_DYN_SMEM(double, sm);
@@ -370,21 +382,44 @@ fh_k_core(const double* __restrict__ K, const double* __restrict__ Gz, int m, do
   const double* Gzb = Gz + b * (size_t)(FH_MAXM * FH_MAXM);
   double* Gsb = Gs + b * (size_t)(FH_MAXM * FH_MAXM);
   if (m == 0) return;
-  for (int idx = tid; idx < m * m; idx += nt) {
-    const int i = idx / m, j = idx % m;
-    double s = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < m; ++k) s += Kb[i * FH_GRAM_LD + k] * Gzb[k * FH_MAXM + j];
-    A[i * FH_MAXM + j] = s;
+  // A = I + K Gz.  Thread = (column j, row group of 4 rows at a time): the Gz entry of a k is loaded once for four
+  // rows, the four K entries are warp-uniform; no division per element (the first version: one element per thread and
+  // iteration with two dependent global loads per FMA, ~12 us per product at m = 56).
+  {
+    const int j = tid & (FH_MAXM - 1), g = tid / FH_MAXM, ng = nt / FH_MAXM;
+    for (int i0 = 4 * g; i0 < m; i0 += 4 * ng) {
+      double s4[4] = {0.0, 0.0, 0.0, 0.0};
+      if (j < m) {
+        for (int k = 0; k < m; ++k) {
+          const double gz = Gzb[k * FH_MAXM + j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s4[q] += Kb[min(i0 + q, m - 1) * FH_GRAM_LD + k] * gz;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i0 + q < m) A[(i0 + q) * FH_MAXM + j] = s4[q] + ((i0 + q == j) ? 1.0 : 0.0);
+      }
+    }
   }
   __syncthreads();
   const int bad = fh_invert(A, Ai, m, red, piv);
   if (bad && tid == 0) atomicAdd(status, 1);
   // Gs = -Gz * Ai   (into A, then symmetrise into global)
-  for (int idx = tid; idx < m * m; idx += nt) {
-    const int i = idx / m, j = idx % m;
-    double s = 0.0;
-    for (int k = 0; k < m; ++k) s += Gzb[i * FH_MAXM + k] * Ai[k * FH_MAXM + j];
-    A[i * FH_MAXM + j] = -s;
+  {
+    const int j = tid & (FH_MAXM - 1), g = tid / FH_MAXM, ng = nt / FH_MAXM;
+    for (int i0 = 4 * g; i0 < m; i0 += 4 * ng) {
+      double s4[4] = {0.0, 0.0, 0.0, 0.0};
+      if (j < m) {
+        for (int k = 0; k < m; ++k) {
+          const double ai = Ai[k * FH_MAXM + j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s4[q] += Gzb[min(i0 + q, m - 1) * FH_MAXM + k] * ai;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i0 + q < m) A[(i0 + q) * FH_MAXM + j] = -s4[q];
+      }
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < m * m; idx += nt) {
