@@ -358,12 +358,21 @@ extern "C" int fh_dct2(fh_ctx* c, const float* in, float* out, int nplanes, int 
 }
 
 // ------------------------------------------------------------------------------------------- state
+static int state_alloc(fh_ctx* c, fh_state* s, int batch) {
+  const size_t vec = (size_t)batch * c->d * sizeof(float);
+  FH_CUDA(cudaMalloc((void**)&s->pi, vec));
+  FH_CUDA(cudaMalloc((void**)&s->delta, vec));
+  FH_CUDA(cudaMalloc((void**)&s->Z, (size_t)batch * c->max_rank * c->d * sizeof(float) + 16));
+  FH_CUDA(cudaMalloc((void**)&s->Gz, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&s->Gs, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  return FH_OK;
+}
+
 extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) {
   if (!c || !out || batch < 1 || batch > c->max_batch) FH_FAIL(FH_EINVAL, "bad fh_state_create arguments");
   if (basis == FH_BASIS_DCT && (c->H != FH_N || c->W != FH_N)) FH_FAIL(FH_EINVAL, "DCT basis needs 256x256 images");
   fh_state* s = (fh_state*)calloc(1, sizeof(fh_state));
   s->ctx = c; s->B = batch; s->basis = basis; s->m = 0; s->d = c->d; s->var2 = 1.0; s->sig2 = 1.0;
-  const size_t vec = (size_t)batch * s->d * sizeof(float);
   for (int i = 0; i < FH_STATE_POOL; ++i) {
     fh_state* p = c->state_pool[i];
     if (p && p->B == batch) {                               // reuse the buffers of a destroyed state (no cudaMalloc)
@@ -374,11 +383,18 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
       return FH_OK;
     }
   }
-  FH_CUDA(cudaMalloc((void**)&s->pi, vec));
-  FH_CUDA(cudaMalloc((void**)&s->delta, vec));
-  FH_CUDA(cudaMalloc((void**)&s->Z, (size_t)batch * c->max_rank * s->d * sizeof(float) + 16));
-  FH_CUDA(cudaMalloc((void**)&s->Gz, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
-  FH_CUDA(cudaMalloc((void**)&s->Gs, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  int rc = state_alloc(c, s, batch);
+  if (rc) return rc;
+  // A sampler typically builds the next image's state while it still holds the previous one: allocate a spare set of
+  // buffers together with the first state, so that the second image does not pay ~100 ms of cudaMalloc in its loop.
+  for (int i = 0; i < FH_STATE_POOL; ++i)
+    if (!c->state_pool[i]) {
+      fh_state* spare = (fh_state*)calloc(1, sizeof(fh_state));
+      spare->ctx = c; spare->B = batch; spare->basis = basis; spare->d = c->d;
+      if (state_alloc(c, spare, batch) == FH_OK) c->state_pool[i] = spare;
+      else { cudaFree(spare->pi); cudaFree(spare->delta); cudaFree(spare->Z); cudaFree(spare->Gz); cudaFree(spare->Gs); free(spare); cudaGetLastError(); }
+      break;
+    }
   *out = s;
   return FH_OK;
 }
