@@ -103,7 +103,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_s=0.1):
+    def __init__(self, index, period_s=0.25):
         self.index, self.rows, self.proc, self.first = index, [], None, 0
         self.period, self.how, self._stop, self._thread = period_s, None, threading.Event(), None
 
@@ -464,6 +464,9 @@ def run_b200(a, assets):
         torch.cuda.synchronize()
         if k >= 0:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        if host_trace:
+            top = sorted(host_trace, key=lambda kv: -kv[1])[:4]
+            print(f"[host-e2e] pass {k} {(time.perf_counter() - t0) * 1e3:.1f} ms; host total {sum(v for _, v in host_trace) * 1e3:.1f} ms; top {[(n, round(v * 1e3, 2)) for n, v in top]}", file=sys.stderr, flush=True)
     gc.enable()
     e2e_total = reduce_max(float(sum(e2e_ms)))
     clk = clocks.stop() if rank == 0 else None
