@@ -411,8 +411,10 @@ def run_b200(a, assets):
         # (that was the "second timed step is slow" stall: the warm-up dropped every mechanism at once, the timed loop did not)
         _, mech = sample(op, torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev))
     # ---- device-resident arm: inputs already in HBM, CUDA events per step, L2 flushed between steps
-    if rank == 0 and not clocks.rows:
-        time.sleep(2.0)                                   # make sure the sampler is past its start-up
+    if rank == 0 and not os.environ.get("FH_BENCH_NO_CLOCKS"):
+        t_wait = time.perf_counter()                       # let the sampler get past its start-up: a few complete query
+        while len(clocks.rows) < 3 and time.perf_counter() - t_wait < 3.0:   # cycles (first NVML calls on a fresh box are slow
+            time.sleep(0.05)                               # and contend with launches for driver locks)
     # a cyclic-GC pass over the interpreter's objects is tens of ms of host time in the middle of a 80 ms step: collect
     # now, then keep the collector off while steps are being timed
     gc.collect()
