@@ -152,6 +152,8 @@ struct fh_op {
   int4* runs; float *run_wf, *run_wt; int nruns, nrun_taps;   // the PSF as one dense vertical run per column (fh_k_conv_runs)
 };
 
+static void state_free_buffers(fh_state* p);
+
 static inline dim3 ew_grid(long d, int B) { return dim3((unsigned)fh_nchunks(d), (unsigned)B, 1); }
 static inline int vec_ok(long d) { return (d % 4 == 0) ? 1 : 0; }
 
@@ -278,10 +280,7 @@ extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
 extern "C" int fh_ctx_destroy(fh_ctx* c) {
   if (!c) return FH_OK;
   for (int i = 0; i < FH_STATE_POOL; ++i)
-    if (fh_state* p = c->state_pool[i]) {
-      cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs);
-      free(p);
-    }
+    if (c->state_pool[i]) state_free_buffers(c->state_pool[i]);
   cudaFree(c->tw256); cudaFree(c->post); cudaFree(c->cw); cudaFree(c->plane_tmp);
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
@@ -358,6 +357,18 @@ extern "C" int fh_dct2(fh_ctx* c, const float* in, float* out, int nplanes, int 
 }
 
 // ------------------------------------------------------------------------------------------- state
+static void state_free_buffers(fh_state* p) {
+  cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs);
+  free(p);
+}
+// A pool slot for a state of `batch` images: a free one, else one parked for a different batch size (evicted).
+static int pool_slot_for(fh_ctx* c, int batch) {
+  for (int i = 0; i < FH_STATE_POOL; ++i) if (!c->state_pool[i]) return i;
+  for (int i = 0; i < FH_STATE_POOL; ++i)
+    if (c->state_pool[i]->B != batch) { state_free_buffers(c->state_pool[i]); c->state_pool[i] = nullptr; return i; }
+  return -1;
+}
+
 static int state_alloc(fh_ctx* c, fh_state* s, int batch) {
   const size_t vec = (size_t)batch * c->d * sizeof(float);
   FH_CUDA(cudaMalloc((void**)&s->pi, vec));
@@ -387,27 +398,25 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
   if (rc) return rc;
   // A sampler typically builds the next image's state while it still holds the previous one: allocate a spare set of
   // buffers together with the first state, so that the second image does not pay ~100 ms of cudaMalloc in its loop.
-  for (int i = 0; i < FH_STATE_POOL; ++i)
-    if (!c->state_pool[i]) {
+  {
+    const int i = pool_slot_for(c, batch);
+    if (i >= 0) {
       fh_state* spare = (fh_state*)calloc(1, sizeof(fh_state));
       spare->ctx = c; spare->B = batch; spare->basis = basis; spare->d = c->d;
       if (state_alloc(c, spare, batch) == FH_OK) c->state_pool[i] = spare;
-      else { cudaFree(spare->pi); cudaFree(spare->delta); cudaFree(spare->Z); cudaFree(spare->Gz); cudaFree(spare->Gs); free(spare); cudaGetLastError(); }
-      break;
+      else { state_free_buffers(spare); cudaGetLastError(); }
     }
+  }
   *out = s;
   return FH_OK;
 }
 extern "C" int fh_state_destroy(fh_state* s) {
   if (!s) return FH_OK;
-  if (s->ctx)
-    for (int i = 0; i < FH_STATE_POOL; ++i)
-      if (!s->ctx->state_pool[i]) {                         // park the buffers; work queued on them is stream-ordered
-        s->ctx->state_pool[i] = s;                          // before whatever the next owner queues
-        return FH_OK;
-      }
-  cudaFree(s->pi); cudaFree(s->delta); cudaFree(s->Z); cudaFree(s->Gz); cudaFree(s->Gs);
-  free(s);
+  if (s->ctx) {
+    const int i = pool_slot_for(s->ctx, s->B);              // park the buffers; work queued on them is stream-ordered
+    if (i >= 0) { s->ctx->state_pool[i] = s; return FH_OK; } // before whatever the next owner queues
+  }
+  state_free_buffers(s);
   return FH_OK;
 }
 extern "C" int fh_state_rank(const fh_state* s) { return s ? s->m : -1; }
