@@ -18,6 +18,10 @@ _SIGNATURES = {
     "fh_cg_kernel_time": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_void_p]),
     "fh_cg_solve_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p]),
+    "fh_cg_solve_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fh_cg_solve_f64_async": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, c_void_p,
+                                      c_void_p, c_void_p]),
     "fh_cg_resident_time": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_float), c_void_p]),
     "fh_trace_read": (c_int, [c_void_p, c_void_p]),
     "fh_prof_enable": (c_int, [c_int]),
@@ -33,6 +37,7 @@ _SIGNATURES = {
     "fh_state_rank": (c_int, [c_void_p]),
     "fh_state_var2": (c_double, [c_void_p]),
     "fh_cov_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fh_cov_dot_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "fh_time_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "fh_space_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_state_set_cov_vectors": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),

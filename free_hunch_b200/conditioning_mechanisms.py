@@ -256,17 +256,21 @@ class FreeHunch(ConditioningMechanism):
         s2 = sigma_f ** 2
         with self.timer("denoiser"):
             p_y_xt_grad = torch.autograd.grad((mat.detach() * x_0_mean).sum(), x_t)[0]                   # :280
+        # :283-288.  The reference runs batch 1; with B independent images per call the VJP-vs-Sigma.mat decision is taken
+        # PER IMAGE (a whole-batch statistic would make an image's guidance depend on its batch mates).
+        use_cov = (p_y_xt_grad * s2).flatten(1).std(dim=1) > self.denoiser_mean_error_threshold          # (B,), on the device
         if self.defer:
-            use_cov = (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold                      # :283, stays on device
             alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
-            p_y_xt_grad = torch.where(use_cov, alt, p_y_xt_grad * self.cond_scaling)
+            p_y_xt_grad = torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
             rec["fallback"] = use_cov
-        elif (p_y_xt_grad * s2).std() > self.denoiser_mean_error_threshold:                              # :283-285
-            p_y_xt_grad = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
-            rec["fallback"] = True
-        else:                                                                                            # :287-288
-            p_y_xt_grad = p_y_xt_grad * self.cond_scaling
-            rec["fallback"] = False
+        else:
+            flags = [bool(v) for v in use_cov.tolist()]                                                  # host read, like :283
+            if any(flags):
+                alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
+                p_y_xt_grad = alt if all(flags) else torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
+            else:
+                p_y_xt_grad = p_y_xt_grad * self.cond_scaling
+            rec["fallback"] = flags[0] if len(flags) == 1 else flags
         x_0_mean_new = x_0_mean + p_y_xt_grad * s2
         # :290-292 -- history stays ON DEVICE; only the last entry is ever read, so only it is kept
         self.sigmas.append(sigma_f)
@@ -284,7 +288,7 @@ class FreeHunch(ConditioningMechanism):
                    or r.get("_same_x") is not None]
         if not pending:
             return self.log
-        maxiter = 5000
+        maxiter = self.argv.get("maxiter", 5000)
         for r in pending:
             if not isinstance(r["niter"], list):
                 info = r["niter"].fetch()
@@ -292,7 +296,8 @@ class FreeHunch(ConditioningMechanism):
                 if any(n >= maxiter for n in info["niter"]):
                     warn("CG not converge.")
             if torch.is_tensor(r.get("fallback")):
-                r["fallback"] = bool(r["fallback"].item())
+                flags = [bool(v) for v in r["fallback"].reshape(-1).tolist()]
+                r["fallback"] = flags[0] if len(flags) == 1 else flags
             same = r.pop("_same_x", None)
             if same is not None and bool(same.item()):
                 raise RuntimeError("defer_host_reads: the mechanism was evaluated twice at the same x_t (sigma = "

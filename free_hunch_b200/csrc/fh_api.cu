@@ -6,6 +6,7 @@
 #include "fh_kernels.cuh"
 #include "fh_cg.cuh"
 #include "fh_cg_resident.cuh"
+#include "fh_cg_res64.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -129,6 +130,15 @@ struct fh_ctx {
   // per image, and cudaMalloc / cudaFree of its ~60 MB synchronise the device (measured: sporadic 10-100 ms stalls).
   struct fh_state* state_pool[FH_STATE_POOL];
   long long* trace;                   // FH_TRACE=1: clock64 checkpoints of the fused CG kernels (8 kernels x 16 slots)
+  // float64 resident CG solve (fh_cg_res64.cuh)
+  double2 *tw64, *e512;               // float64 stage twiddles / exp(-i pi k / 512)
+  double* r64_T[2];                   // (d) exchange planes
+  double* r64_ride[2];                // per-CTA partials that ride on the two grid barriers
+  double* d64[3];                     // (max_batch, d) float64 vectors: b, solution, A mu / converted inputs
+  double* d64_out;                    // (max_batch, d) float64 result of the float32 entry points
+  double* d64_y;                      // (max_batch, d) widened y of the float32 entry points
+  int r64_cap, r64_cap_tabs;          // rows of Z the float64 kernel keeps in shared memory (without / with the twiddle tables beside them)
+  int r64_ok;
 };
 
 struct fh_state {
@@ -168,7 +178,8 @@ extern "C" long long fh_launch_count(int reset) {
 // --------------------------------------------------------------------------------------------- ctx
 extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channels, int height, int width, int max_rank) {
   if (!out || max_batch < 1 || channels < 1 || height < 1 || width < 1) FH_FAIL(FH_EINVAL, "bad ctx arguments");
-  if (max_rank > FH_MAXM) FH_FAIL(FH_EINVAL, "max_rank %d > compiled limit %d", max_rank, FH_MAXM);
+  // Z is allocated with max_rank rows per image and indexed with stride FH_MAXM by every kernel: they must agree
+  if (max_rank != FH_MAXM) FH_FAIL(FH_EINVAL, "max_rank must be %d in this build (got %d)", FH_MAXM, max_rank);
   FH_CUDA(cudaSetDevice(device));
   fh_ctx* c = (fh_ctx*)calloc(1, sizeof(fh_ctx));
   c->device = device; c->max_batch = max_batch; c->C = channels; c->H = height; c->W = width; c->max_rank = max_rank;
@@ -225,6 +236,32 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
     c->res_seq = 0;
   }
   c->cg_mode = FH_CG_AUTO; c->cg_last_mode = 0; c->res_ok = 1;
+  {
+    // float64 tables of the resident float64 solve: stage twiddles [Ns = 4, 16, 64][r = 1..3][k < Ns] and exp(-i pi k / 512)
+    std::vector<double2> tw64(FH_R64_TW), e512(FH_N);
+    int off = 0;
+    for (int Ns = 4; Ns <= 64; Ns *= 4) {
+      for (int r = 1; r <= 3; ++r)
+        for (int k = 0; k < Ns; ++k) {
+          const double a = -2.0 * M_PI * (double)k * r / (4.0 * Ns);
+          tw64[off + (r - 1) * Ns + k] = make_double2(cos(a), sin(a));
+        }
+      off += 3 * Ns;
+    }
+    for (int k = 0; k < FH_N; ++k) { const double th = -M_PI * k / (2.0 * FH_N); e512[k] = make_double2(cos(th), sin(th)); }
+    FH_CUDA(cudaMalloc((void**)&c->tw64, tw64.size() * sizeof(double2)));
+    FH_CUDA(cudaMalloc((void**)&c->e512, e512.size() * sizeof(double2)));
+    FH_CUDA(cudaMemcpy(c->tw64, tw64.data(), tw64.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    FH_CUDA(cudaMemcpy(c->e512, e512.data(), e512.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) {
+      FH_CUDA(cudaMalloc((void**)&c->r64_T[i], (size_t)c->d * sizeof(double)));
+      FH_CUDA(cudaMalloc((void**)&c->r64_ride[i], ((size_t)c->d / FH_RES_SLICE + 1) * sizeof(double)));
+    }
+    for (int i = 0; i < 3; ++i) FH_CUDA(cudaMalloc((void**)&c->d64[i], (size_t)max_batch * c->d * sizeof(double)));
+    FH_CUDA(cudaMalloc((void**)&c->d64_out, (size_t)max_batch * c->d * sizeof(double)));
+    FH_CUDA(cudaMalloc((void**)&c->d64_y, (size_t)max_batch * c->d * sizeof(double)));
+    c->r64_cap = 32; c->r64_cap_tabs = 30; c->r64_ok = c->res_ok;
+  }
   c->trace = nullptr;
   if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
 #ifndef FH_EMU
@@ -254,16 +291,35 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
     FH_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     const long rows = (long)channels * height;
     c->res_ok = (coop && height == FH_N && width == FH_N && rows % FH_RES_ROWS == 0 && rows / FH_RES_ROWS <= (long)per_sm * c->sms) ? 1 : 0;
+    // float64 variant: as many rows of Z as fit beside its fixed shared memory
+    int smem_max = 0;
+    FH_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    c->r64_cap = std::min(FH_RES_MAXM, (int)((smem_max - (int)sizeof(FhRes64Smem)) / (FH_RES_SLICE * 4)));
+    c->r64_cap_tabs = std::min(FH_RES_MAXM, (int)((smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs)) / (FH_RES_SLICE * 4)));
+    c->r64_ok = 0;
+    if (c->res_ok && c->r64_cap >= 0 && c->r64_cap_tabs >= 0) {
+      const int smem64 = (int)sizeof(FhRes64Smem) + c->r64_cap * FH_RES_SLICE * 4;
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+      int a = 0, b = 0, e = 0;
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, fh_k_cg_res64<false, true>, FH_PASS_THREADS, smem64));
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fh_k_cg_res64<false, false>, FH_PASS_THREADS, smem64));
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, fh_k_cg_res64<true, false>, FH_PASS_THREADS, smem64));
+      c->r64_ok = (rows / FH_RES_ROWS <= (long)std::min(std::min(a, b), e) * c->sms) ? 1 : 0;
+    }
   }
 #else
   c->res_ok = (height == FH_N && width == FH_N && ((long)channels * height) % FH_RES_ROWS == 0) ? 1 : 0;
+  c->r64_ok = c->res_ok;
+  if (const char* e = getenv("FH_EMU_R64_CAP")) { c->r64_cap = atoi(e); c->r64_cap_tabs = std::max(0, c->r64_cap - 2); }   // CPU emulation: the test picks the resident row counts
 #endif
   *out = c;
   return FH_OK;
 }
 
 extern "C" int fh_ctx_set_cg_mode(fh_ctx* c, int mode) {
-  if (!c || mode < FH_CG_AUTO || mode > FH_CG_RESIDENT) FH_FAIL(FH_EINVAL, "bad fh_ctx_set_cg_mode arguments");
+  if (!c || mode < FH_CG_AUTO || mode > FH_CG_RESIDENT_F32) FH_FAIL(FH_EINVAL, "bad fh_ctx_set_cg_mode arguments");
   c->cg_mode = mode;
   return FH_OK;
 }
@@ -286,6 +342,10 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
   cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace); cudaFree(c->res_ll); cudaFree(c->grid_counter);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
+  cudaFree(c->tw64); cudaFree(c->e512);
+  for (int i = 0; i < 2; ++i) { cudaFree(c->r64_T[i]); cudaFree(c->r64_ride[i]); }
+  for (int i = 0; i < 3; ++i) cudaFree(c->d64[i]);
+  cudaFree(c->d64_out); cudaFree(c->d64_y);
   cudaFree(c->part_a); cudaFree(c->part_b); cudaFree(c->cg_sc); cudaFreeHost(c->cg_sc_host); cudaFreeHost((void*)c->mirror_host); cudaFree(c->status);
   free(c);
   return FH_OK;
@@ -395,7 +455,7 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
     }
   }
   int rc = state_alloc(c, s, batch);
-  if (rc) return rc;
+  if (rc) { state_free_buffers(s); cudaGetLastError(); return rc; }      // partial allocation: nothing leaks
   // A sampler typically builds the next image's state while it still holds the previous one: allocate a spare set of
   // buffers together with the first state, so that the second image does not pay ~100 ms of cudaMalloc in its loop.
   {
@@ -830,6 +890,8 @@ static inline bool conv_runs_pays(const fh_ctx* c, int planes) {
 
 extern "C" int fh_op_apply(fh_op* o, const float* in, float* out, int batch, int transpose, void* stream) {
   if (!o || !in || !out || batch < 1) FH_FAIL(FH_EINVAL, "bad fh_op_apply arguments");
+  if (o->kind == FH_OP_INPAINT && o->mask_batch != 1 && o->mask_batch != batch)
+    FH_FAIL(FH_EINVAL, "mask batch %d does not match the batch %d (one mask for all images, or one per image)", o->mask_batch, batch);
   fh_ctx* c = o->ctx;
   const int planes = batch * c->C;
   if (o->kind == FH_OP_INPAINT) {
@@ -951,8 +1013,10 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
 static bool resident_applies(const fh_state* s, const FhCgFused& P) {
   const fh_ctx* c = s->ctx;
   if (!(c->res_ok && P.fuse != 0 && s->m <= FH_MAXM) || c->cg_mode == FH_CG_STREAMING) return false;
-  return c->cg_mode == FH_CG_RESIDENT || s->B <= FH_RES_AUTO_MAX_BATCH;
+  return c->cg_mode == FH_CG_RESIDENT || c->cg_mode == FH_CG_RESIDENT_F32 || s->B <= FH_RES_AUTO_MAX_BATCH;
 }
+// which resident kernel: float64 (the parity path; FH_CG_AUTO, FH_CG_RESIDENT) or the float32 one (FH_CG_RESIDENT_F32)
+static bool resident_is_f64(const fh_ctx* c) { return c->cg_mode != FH_CG_RESIDENT_F32 && c->r64_ok; }
 
 // Whole solve in one launch per image (fh_cg_resident.cuh): Z stays in shared memory, x/r/p/q in registers.
 static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y, const float* mu, double rtol, int last,
@@ -1001,6 +1065,166 @@ static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y,
   return fh_op_apply(o, x, mat_out, B, 1, stream);
 }
 
+// ---- float64 resident solve (fh_cg_res64.cuh) -------------------------------------------------------------------------
+static int launch_res64(fh_ctx* c, const FhCgFused& P, FhCgRes64 R, cudaStream_t st) {
+  const dim3 grid((unsigned)P.strips_per_image), block(FH_PASS_THREADS);
+  const size_t nblk = grid.x, half = (size_t)c->d / 2;
+  R.T[0] = c->r64_T[0]; R.T[1] = c->r64_T[1];
+  R.ride[0] = c->r64_ride[0]; R.ride[1] = c->r64_ride[1];
+  R.ll_dots = c->res_ll + 2 * half;
+  R.ll_sum = R.ll_dots + FH_MAXM * nblk;
+  R.tw = c->tw64; R.e512 = c->e512;
+  R.mr_cap = c->r64_cap;
+  const unsigned need = (unsigned)P.last_allowed + 3u;
+  if (c->res_seq > 0xffffffffu - need - 1u) {
+    FH_CUDA(cudaMemsetAsync(c->res_ll, 0, c->res_ll_bytes, st));
+    c->res_seq = 0;
+  }
+  R.seq_base = c->res_seq;
+  c->res_seq += need;
+  R.grid_counter = c->grid_counter + R.image;
+  FH_CUDA(cudaMemsetAsync(R.grid_counter, 0, sizeof(unsigned), st));
+  // three instantiations: tables in shared memory while the rank leaves room for them, through L1 above that, and the
+  // partially resident one above the resident capacity
+  const bool tabs = P.m <= c->r64_cap_tabs;
+  const bool big = !tabs && P.m > c->r64_cap;
+  const size_t smem = sizeof(FhRes64Smem) + (tabs ? sizeof(FhRes64Tabs) : 0) + (size_t)std::min(P.m, c->r64_cap) * FH_RES_SLICE * sizeof(float);
+#ifdef FH_EMU
+  (void)st;
+  if (tabs) emu::launch_coop([&] { fh_k_cg_res64<false, true>(P, R); }, grid, block, smem);
+  else if (big) emu::launch_coop([&] { fh_k_cg_res64<true, false>(P, R); }, grid, block, smem);
+  else emu::launch_coop([&] { fh_k_cg_res64<false, false>(P, R); }, grid, block, smem);
+  ++fh_g_launches;
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (fh_g_prof_on) fh_prof_begin("fh_k_cg_res64", st);
+  if (tabs) FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_res64<false, true>, P, R));
+  else if (big) FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_res64<true, false>, P, R));
+  else FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_cg_res64<false, false>, P, R));
+  if (fh_g_prof_on) fh_prof_end(st);
+  ++fh_g_launches;
+#endif
+  return FH_OK;
+}
+
+// out = A in (transpose = 0) or A^T in, float64, for every operator kind (once per solve: right-hand side and result)
+static int op_apply64(fh_op* o, const double* in, double* out, int batch, int transpose, void* stream) {
+  fh_ctx* c = o->ctx;
+  const int planes = batch * c->C;
+  if (o->kind == FH_OP_INPAINT) FH_FAIL(FH_EINVAL, "op_apply64: the mask is applied by the caller");
+  FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
+  if (o->kind == FH_OP_BLUR) {
+    if (c->H % 32 || c->W % 32) FH_FAIL(FH_EINVAL, "blur needs image sizes divisible by 32");
+    const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;
+    const size_t smem = (size_t)th * tw * sizeof(double);
+    if (smem > 48 * 1024) FH_FAIL(FH_EINVAL, "PSF support too large for the float64 convolution tile");
+    FH_LAUNCH(fh_k_conv_taps64, dim3(c->W / 32, c->H / 32, planes), dim3(32, 8), smem, stream, in, out, t, c->H, c->W, transpose);
+  } else if (!transpose) {
+    const int n = (c->H / o->sf) * (c->W / o->sf);
+    FH_LAUNCH(fh_k_sr_forward64, dim3((n + 255) / 256, planes), dim3(256), 0, stream, in, out, t, c->H, c->W, o->sf);
+  } else {
+    const int n = c->H * c->W;
+    FH_LAUNCH(fh_k_sr_transpose64, dim3((n + 255) / 256, planes), dim3(256), 0, stream, in, out, t, c->H, c->W, o->sf);
+  }
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// Whole solve in float64: b = y - A mu (float64 convolution), one cooperative launch per image, mat = u or A^T u (float64).
+// y: float64 (B, n); mu: float64 (B, d); mat_out: float64 (B, d).  info_dev != null: nothing is read back.
+static int cg_solve_res64(fh_state* s, fh_op* o, FhCgFused P, const double* y, const double* mu, double sigma_y2, double rtol,
+                          int last, int use_stop, double* mat_out, int* niter_host, int* optimal_host, double* resid_host,
+                          void* stream, FhCgInfo* info_dev) {
+  fh_ctx* c = s->ctx;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->B;
+  const long n = s->d;
+  const long hw = (long)c->H * c->W;
+  double *bv = c->d64[0], *x = c->d64[1], *amu = c->d64[2];
+  int rc;
+  const double* a = mu;
+  if (o->kind != FH_OP_INPAINT) {
+    if ((rc = op_apply64(o, mu, amu, B, 0, stream))) return rc;
+    a = amu;
+  }
+  FH_LAUNCH(fh_k_rhs64, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, a, P.mask, P.mask_batch, hw, bv, n);
+  FH_KCHECK();
+  FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
+  P.strips_per_image = (int)(s->d / FH_RES_SLICE);
+  P.ystrips = P.strips_per_image;
+  P.last_allowed = last;
+  P.mirror = nullptr;
+  double* xout = (o->kind == FH_OP_INPAINT) ? mat_out : x;
+  for (int b = 0; b < B; ++b) {
+    FhCgRes64 R{};
+    R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n;
+    R.rtol = rtol; R.atol = 0.0; R.sy2 = sigma_y2; R.use_stop = use_stop; R.image = b;
+    R.info_out = info_dev ? info_dev + b : nullptr;
+    if ((rc = launch_res64(c, P, R, st))) return rc;
+  }
+  if (o->kind != FH_OP_INPAINT && (rc = op_apply64(o, x, mat_out, B, 1, stream))) return rc;
+  if (info_dev) return FH_OK;
+  FH_CUDA(cudaMemcpyAsync(c->cg_sc_host, c->cg_sc, (size_t)B * sizeof(FhCgScalars), cudaMemcpyDeviceToHost, st));
+  FH_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    if (!c->cg_sc_host[b].done) FH_FAIL(FH_ESTATE, "resident float64 CG kernel did not finish image %d", b);
+    if (niter_host) niter_host[b] = c->cg_sc_host[b].niter;
+    if (optimal_host) optimal_host[b] = c->cg_sc_host[b].optimal;
+    if (resid_host) resid_host[b] = sqrt(c->cg_sc_host[b].resid2);
+  }
+  return FH_OK;
+}
+
+// Sigma v in float64 (denoiser_cov_vector_dot, online_update_bfgs.py:370-374, for a float64 v): one pass of the resident
+// float64 kernel without operator -- 2-D DCT, delta (w_hat + Z^T Gs Z delta w_hat), inverse DCT, all float64.  The mechanism
+// needs it because mu + Sigma mat cancels to ~1 % of its terms at high sigma (a float32 product costs two digits there).
+extern "C" int fh_cov_dot_f64(fh_state* s, const double* v, double* out, void* stream) {
+  if (!s || !v || !out) FH_FAIL(FH_EINVAL, "bad fh_cov_dot_f64 arguments");
+  fh_ctx* c = s->ctx;
+  if (s->basis != FH_BASIS_DCT || !c->r64_ok) FH_FAIL(FH_ESTATE, "fh_cov_dot_f64 needs the DCT basis and the resident float64 kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  FhCgFused P = fused_params(s, nullptr, 8);
+  P.sc = c->cg_sc; P.sy2 = 0.f;
+  P.strips_per_image = (int)(s->d / FH_RES_SLICE);
+  P.ystrips = P.strips_per_image;
+  P.last_allowed = 1;
+  P.mirror = nullptr;
+  FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)s->B * sizeof(FhCgScalars), st));
+  for (int b = 0; b < s->B; ++b) {
+    FhCgRes64 R{};
+    R.bvec = v + (size_t)b * s->d; R.x_out = out + (size_t)b * s->d;
+    R.rtol = 1.0; R.atol = 0.0; R.sy2 = 0.0; R.use_stop = 0; R.image = b; R.apply_only = 1;
+    int rc = launch_res64(c, P, R, st);
+    if (rc) return rc;
+  }
+  return FH_OK;
+}
+
+// float32 entry points over the float64 solve: widen mu, narrow mat (both exact / one rounding)
+static int cg_solve_res64_f32io(fh_state* s, fh_op* o, const FhCgFused& P, const float* y, const float* mu, double sigma_y2,
+                                double rtol, int last, int use_stop, float* mat_out, int* niter_host, int* optimal_host,
+                                double* resid_host, void* stream, FhCgInfo* info_dev) {
+  fh_ctx* c = s->ctx;
+  const long tot = (long)s->B * s->d;
+  // d64[2] doubles as the widened mu for inpainting (no A mu needed there); blur: A mu overwrites it only after it was read
+  double* mu64 = c->d64_out;
+  FH_LAUNCH(fh_k_f2d, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream, mu, mu64, tot);
+  const long ytot = (long)s->B * op_ylen(o);
+  FH_LAUNCH(fh_k_f2d, dim3((unsigned)((ytot + 255) / 256)), dim3(256), 0, stream, y, c->d64_y, ytot);
+  FH_KCHECK();
+  // the result may overwrite the widened mu: mu is consumed (rhs) before any image's solve starts
+  int rc = cg_solve_res64(s, o, P, c->d64_y, mu64, sigma_y2, rtol, last, use_stop, c->d64_out, niter_host, optimal_host, resid_host, stream, info_dev);
+  if (rc) return rc;
+  FH_LAUNCH(fh_k_d2f, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream, (const double*)c->d64_out, mat_out, tot);
+  FH_KCHECK();
+  return FH_OK;
+}
+
 // DCT-basis solve: the iteration of fh_cg.cuh.  5 launches per iteration when the operator folds into the DCT passes
 // (mask, separable blur), 9 otherwise (p update, A^T, 4 passes, A, q, x/r update).
 static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
@@ -1021,10 +1245,14 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
   P.last_allowed = last;
   if (resident_applies(s, P)) {
-    c->cg_last_mode = FH_CG_RESIDENT;
+    if (resident_is_f64(c)) {
+      c->cg_last_mode = FH_CG_RESIDENT;
+      return cg_solve_res64_f32io(s, o, P, y, mu, sigma_y2, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream, nullptr);
+    }
+    c->cg_last_mode = FH_CG_RESIDENT_F32;
     return cg_solve_resident(s, o, P, y, mu, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream);
   }
-  if (c->cg_mode == FH_CG_RESIDENT)
+  if (c->cg_mode == FH_CG_RESIDENT || c->cg_mode == FH_CG_RESIDENT_F32)
     FH_FAIL(FH_EINVAL, "resident CG solve requested but not applicable (operator does not fold into the DCT passes, or the device cannot hold the cooperative grid)");
   c->cg_last_mode = FH_CG_STREAMING;
   const bool fusedop = P.fuse != 0;
@@ -1126,6 +1354,7 @@ extern "C" int fh_cg_solve_async(fh_state* s, fh_op* o, const float* y, const fl
                                  int maxiter, int fixed_iters, float* mat_out, fh_cg_info* info_dev, void* stream) {
   if (!s || !o || !y || !mu || !mat_out || !info_dev || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve_async arguments");
   if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  if (o->kind == FH_OP_INPAINT && o->mask_batch != 1 && o->mask_batch != s->B) FH_FAIL(FH_EINVAL, "mask batch %d does not match the state's batch %d", o->mask_batch, s->B);
   if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_ESTATE, "asynchronous solve needs the DCT basis");
   fh_ctx* c = s->ctx;
   FhCgFused P = fused_params(s, o, 8);
@@ -1133,9 +1362,43 @@ extern "C" int fh_cg_solve_async(fh_state* s, fh_op* o, const float* y, const fl
   P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
   const int use_stop = fixed_iters > 0 ? 0 : 1;
   const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
-  c->cg_last_mode = FH_CG_RESIDENT;
   static_assert(sizeof(FhCgInfo) == sizeof(fh_cg_info), "device record layout");
+  if (resident_is_f64(c)) {
+    c->cg_last_mode = FH_CG_RESIDENT;
+    return cg_solve_res64_f32io(s, o, P, y, mu, sigma_y2, rtol, last, use_stop, mat_out, nullptr, nullptr, nullptr, stream, reinterpret_cast<FhCgInfo*>(info_dev));
+  }
+  c->cg_last_mode = FH_CG_RESIDENT_F32;
   return cg_solve_resident(s, o, P, y, mu, rtol, last, use_stop, mat_out, nullptr, nullptr, nullptr, stream, reinterpret_cast<FhCgInfo*>(info_dev));
+}
+
+// The guidance solve with float64 in and out (the reference's own precision): mu and mat are float64, y float32.
+// Available where the float64 resident kernel applies; otherwise FH_ESTATE (use the float32 entry points).
+static int solve_f64_common(fh_state* s, fh_op* o, const double* y, const double* mu, double sigma_y2, double rtol, int maxiter,
+                            int fixed_iters, double* mat_out, int* niter_host, int* optimal_host, double* resid_host,
+                            fh_cg_info* info_dev, void* stream) {
+  if (!s || !o || !y || !mu || !mat_out || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve_f64 arguments");
+  if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_ESTATE, "float64 solve needs the DCT basis");
+  if (o->kind == FH_OP_INPAINT && o->mask_batch != 1 && o->mask_batch != s->B) FH_FAIL(FH_EINVAL, "mask batch %d does not match the state's batch %d", o->mask_batch, s->B);
+  fh_ctx* c = s->ctx;
+  FhCgFused P = fused_params(s, o, 8);
+  if (!resident_applies(s, P) || !resident_is_f64(c))
+    FH_FAIL(FH_ESTATE, "float64 solve needs the resident float64 kernel (rank %d, operator kind %d, cg mode %d)", s->m, o->kind, c->cg_mode);
+  P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
+  const int use_stop = fixed_iters > 0 ? 0 : 1;
+  const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
+  c->cg_last_mode = FH_CG_RESIDENT;
+  return cg_solve_res64(s, o, P, y, mu, sigma_y2, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream,
+                        reinterpret_cast<FhCgInfo*>(info_dev));
+}
+extern "C" int fh_cg_solve_f64(fh_state* s, fh_op* o, const double* y, const double* mu, double sigma_y2, double rtol, int maxiter,
+                               int fixed_iters, double* mat_out, int* niter_host, int* optimal_host, double* resid_host, void* stream) {
+  return solve_f64_common(s, o, y, mu, sigma_y2, rtol, maxiter, fixed_iters, mat_out, niter_host, optimal_host, resid_host, nullptr, stream);
+}
+extern "C" int fh_cg_solve_f64_async(fh_state* s, fh_op* o, const double* y, const double* mu, double sigma_y2, double rtol, int maxiter,
+                                     int fixed_iters, double* mat_out, fh_cg_info* info_dev, void* stream) {
+  if (!info_dev) FH_FAIL(FH_EINVAL, "fh_cg_solve_f64_async needs info_dev");
+  return solve_f64_common(s, o, y, mu, sigma_y2, rtol, maxiter, fixed_iters, mat_out, nullptr, nullptr, nullptr, info_dev, stream);
 }
 
 extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* mu, double sigma_y2, double rtol,
@@ -1143,6 +1406,7 @@ extern "C" int fh_cg_solve(fh_state* s, fh_op* o, const float* y, const float* m
                            double* resid_host, void* stream) {
   if (!s || !o || !y || !mu || !mat_out || maxiter < 1) FH_FAIL(FH_EINVAL, "bad fh_cg_solve arguments");
   if (!(rtol > 0) && fixed_iters <= 0) FH_FAIL(FH_EINVAL, "rtol must be positive");
+  if (o->kind == FH_OP_INPAINT && o->mask_batch != 1 && o->mask_batch != s->B) FH_FAIL(FH_EINVAL, "mask batch %d does not match the state's batch %d", o->mask_batch, s->B);
   if (s->basis == FH_BASIS_DCT)
     return cg_solve_fused(s, o, y, mu, sigma_y2, rtol, maxiter, fixed_iters, mat_out, niter_host, optimal_host, resid_host, stream);
   fh_ctx* c = s->ctx;
@@ -1276,9 +1540,13 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   if (!ok) FH_FAIL(FH_EINVAL, "resident kernel does not apply to this state / operator");
   P.sc = c->cg_sc; P.sy2 = 0.01f; P.last_allowed = iters;
   P.strips_per_image = (int)(s->d / FH_RES_SLICE); P.ystrips = P.strips_per_image;
+  const bool f64 = resident_is_f64(c);                  // the kernel fh_cg_solve would run in the current mode
   FhCgResident R{};
   R.bvec = c->cgv[0]; R.x_out = c->cgv[5]; R.rtol = 1.0; R.atol = 0.0; R.use_stop = 0; R.image = 0;
   R.timing = 1;                         // a converged workspace must not end the run early (the arithmetic is the same)
+  FhCgRes64 R64{};
+  R64.bvec = c->d64[0]; R64.x_out = c->d64[1]; R64.rtol = 1.0; R64.atol = 0.0; R64.sy2 = 0.01; R64.use_stop = 0; R64.image = 0;
+  R64.timing = 1;
   cudaEvent_t e0, e1;
   FH_CUDA(cudaEventCreate(&e0)); FH_CUDA(cudaEventCreate(&e1));
   int rc = FH_OK;
@@ -1286,7 +1554,7 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
     if (pass) FH_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < (pass ? reps : 1) && rc == FH_OK; ++i) {
       FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, sizeof(FhCgScalars), st));
-      rc = launch_resident(c, P, R, st);
+      rc = f64 ? launch_res64(c, P, R64, st) : launch_resident(c, P, R, st);
     }
     if (pass) FH_CUDA(cudaEventRecord(e1, st));
   }

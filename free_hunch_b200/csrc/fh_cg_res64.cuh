@@ -1,0 +1,774 @@
+// Resident CG solve in FLOAT64 arithmetic: the parity path of the guidance solve.
+//
+// Why float64.  The reference runs cg.py:230-292 in float64 on a system whose condition number reaches ~1e6
+// (Sigma = dct_variance spans 7 decades, sigma_y^2 = 0.01).  A CPU experiment with the oracle shows
+// that ANY float32 rounding inside the loop -- even rounding only q = A p to float32 with everything else in float64 --
+// delays the stop by 20-50 % (34 instead of 28 iterations at sigma = 80, 2670 instead of 1937 at rtol 1e-6) and moves the
+// first-call output by O(1) at the reference's default rtol.  So the vectors x, r, p, q, the 2-D DCTs, the blur taps, the
+// low-rank products and every reduction are float64 here; only the STORED operands delta and Z stay float32 (they define
+// the operator; widening them is exact).  B200 issues 57.6 DFMA/clk/SM (measured, tools/micro/fp64_rates.cu), half the
+// FP32 rate, so the price is < 2x on the arithmetic and nothing on the exchanges.
+//
+// Structure (one cooperative launch per image, 128 CTAs x 256 threads, CTA s owns rows [6s, 6s+6) of the 768 image rows
+// in the pixel domain and of the basis layout in the DCT domain, Z slices resident in shared memory -- see
+// fh_cg_resident.cuh for the layout).  Float64 makes two algebraic restructurings safe that float32 did not allow (the
+// float32 kernel lost conjugacy with them), and they remove two of the five grid-wide exchanges of an iteration:
+//   * linearity: the forward 2-D DCT is applied to the new RESIDUAL r' as soon as it exists, and the direction's
+//     transform follows by  w_hat(p') = w_hat(r') + beta w_hat(p)  once beta is known.  The r.r partials therefore ride on
+//     the grid barrier of the first plane exchange instead of needing an exchange of their own;
+//   * Parseval: p.Ap = sigma_y^2 p.p + w_hat . (Sigma_hat w_hat) is available in the DCT domain, BEFORE the inverse
+//     transform, so its partials ride on the barrier of the second plane exchange.
+// One pass k of the loop (k = 0: initial residual r0 = b - A_op b with x0 = b, cg.py:230-235):
+//   F1  v = r (k = 0: b); mask / row-blur^T; row DCT; transposed store -> T0          | barrier 1 (+ r.r partials)
+//   F2  T0 -> column blur^T; column DCT = w_hat(r); stop test of iteration k-1; beta; p = r + beta p; w_hat(p) likewise
+//       partial Z (delta w_hat)                                                        | dot exchange (two hops)
+//   B1  coef = Gs sums; v = delta (w_hat + Z^T coef); p.Ap partial; column IDCT; column blur; -> T1 | barrier 2 (+ p.Ap)
+//   B2  T1 -> row IDCT; row blur / mask = t; q = sy2 p + t; alpha; x += alpha p; r -= alpha q; r.r partial
+#pragma once
+#include "fh_cg_resident.cuh"
+
+#define FH_R64_LD 320                                // padded FFT buffer length (FH_PAD), in double2
+#define FH_R64_RS 320                                // row stride of a staged strip, in doubles (256 + 16 B of padding per 64 B)
+// column -> position inside a staged row: 2 doubles of padding after every 8, so that the 16-byte window loads of the
+// convolution (lanes 64 B apart) fall on distinct bank groups (unpadded: 4-way conflicts, ncu: 35 % excess wavefronts)
+#define FH_R64_POS(c) ((c) + (((c) >> 3) << 1))
+#define FH_R64_TW 252                                // stage twiddles: Ns = 4 (3 x 4), 16 (3 x 16), 64 (3 x 64)
+
+struct FhRes64Smem {
+  double2 X[FH_RES_ROWS / 2][FH_R64_LD];             // FFT ping-pong; X doubles as the strip's input rows, Y as its output
+  double2 Y[FH_RES_ROWS / 2][FH_R64_LD];             // rows; Y also hosts the scratch of the low-rank stages (FhRes64Scratch)
+  // The twiddle tables (FhRes64Tabs, 8 KB) follow this struct only in the TABS = true instantiation: with them 30 rows
+  // of Z fit beside the FFT buffers, without them 32 -- the rank a 30-step Heun run ends with.  TABS = false reads them
+  // through the read-only path instead (they stay in the ~28 KB of L1 that the 227 KB carve-out leaves: every other
+  // global access of the kernel bypasses L1), which costs 1.7 us per iteration (measured) and is used only above rank 30.
+  double taps[4][FH_RES_TAPS];                       // row A^T, column A^T, column A, row A (centre padded to a multiple of 4)
+  double s_red[4][8];                                // block-sum slots: ride 1, p.Ap partial, ride 2, r.r partial
+  fh_mbar_t bar;
+  unsigned long long pad_;
+};
+struct FhRes64Tabs {
+  double2 tw[FH_R64_TW + 4];                         // [stage][r = 1..3][k < Ns]: exp(-2 pi i k r / (4 Ns))
+  double2 e512[FH_N];                                // exp(-i pi k / 512): post- (forward) and conjugated pre-twiddle (inverse)
+};
+struct FhRes64Scratch {                              // lives in Y while no transform is in flight
+  double s_w[FH_PASS_THREADS / 32][FH_MAXM];
+  double s_sum[FH_MAXM];
+  double s_c[FH_MAXM];
+};
+static_assert(sizeof(FhRes64Scratch) <= sizeof(double2) * (FH_RES_ROWS / 2) * FH_R64_LD, "scratch must fit the FFT buffer");
+static_assert(FH_RES_ROWS * FH_R64_RS * sizeof(double) <= sizeof(double2) * (FH_RES_ROWS / 2) * FH_R64_LD, "rows must fit the FFT buffer");
+
+struct FhCgRes64 {
+  const double* bvec;          // (d) right-hand side b (pixel layout); x0 = b
+  double* x_out;               // (d) solution
+  double* T[2];                // (d) each: half-transformed planes (forward / inverse), transposed exchange through L2
+  double* ride[2];             // (grid) each: per-CTA partial sums that ride on barrier 1 (r.r; pass 0: b.b) / barrier 2 (p.Ap)
+  uint4* ll_dots;              // [FH_MAXM][grid] flag-in-data slots: per-CTA partial of (Z (delta w_hat))_i
+  uint4* ll_sum;               // [FH_MAXM] slots, FH_LL_SPREAD apart: the totals, published by row i's owner CTA
+  unsigned* grid_counter;
+  unsigned seq_base;
+  double rtol, atol, sy2;
+  int use_stop, image, timing;
+  int apply_only;              // 1: no solve -- x_out = Sigma bvec (one pass of the loop without operator, fh_cov_dot_f64)
+  int mr_cap;                  // rows of Z that fit in shared memory
+  FhCgInfo* info_out;
+  const double2* tw;           // device tables (FH_R64_TW, FH_N entries)
+  const double2* e512;
+};
+
+// ---- float64 pieces of the strip transform -----------------------------------------------------------------------
+__device__ __forceinline__ double2 fh_cmul64(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 fh_cadd64(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 fh_csub64(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <int SIGN>
+__device__ __forceinline__ void fh_dft4_64(double2& a0, double2& a1, double2& a2, double2& a3) {
+  const double2 s02 = fh_cadd64(a0, a2), d02 = fh_csub64(a0, a2), s13 = fh_cadd64(a1, a3), t = fh_csub64(a1, a3);
+  const double2 d13 = SIGN < 0 ? make_double2(t.y, -t.x) : make_double2(-t.y, t.x);
+  a0 = fh_cadd64(s02, s13); a2 = fh_csub64(s02, s13); a1 = fh_cadd64(d02, d13); a3 = fh_csub64(d02, d13);
+}
+__device__ __forceinline__ double2 fh_ldg_d2(const double2* p) {
+#ifdef FH_EMU
+  return *p;
+#else
+  double2 v;
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#endif
+}
+template <bool TABS> __device__ __forceinline__ double2 fh_tab(const double2* p) { return TABS ? *p : fh_ldg_d2(p); }
+template <int SIGN, int NS, bool TABS>
+__device__ __forceinline__ void fh_fft256_stage64(const double2* __restrict__ in, double2* __restrict__ out, int j, const double2* __restrict__ tw) {
+  const int k = j & (NS - 1);
+  double2 v0 = in[FH_PAD(j)], v1 = in[FH_PAD(j + 64)], v2 = in[FH_PAD(j + 128)], v3 = in[FH_PAD(j + 192)];
+  constexpr int OFF = (NS == 4) ? 0 : (NS == 16) ? 12 : 60;
+  double2 w1 = fh_tab<TABS>(tw + OFF + k), w2 = fh_tab<TABS>(tw + OFF + NS + k), w3 = fh_tab<TABS>(tw + OFF + 2 * NS + k);
+  if (SIGN > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+  v1 = fh_cmul64(v1, w1); v2 = fh_cmul64(v2, w2); v3 = fh_cmul64(v3, w3);
+  fh_dft4_64<SIGN>(v0, v1, v2, v3);
+  const int j0 = ((j - k) << 2) + k;
+  out[FH_PAD(j0)] = v0; out[FH_PAD(j0 + NS)] = v1; out[FH_PAD(j0 + 2 * NS)] = v2; out[FH_PAD(j0 + 3 * NS)] = v3;
+}
+// Orthonormal DCT-II (INV = false) / DCT-III (INV = true) of the 6 rows in `in` (stride FH_R64_RS) into `out`; same
+// algorithm, aliasing rules and barrier contract as fh_dct_strip_core (fh_dct.cuh): `in` may alias Xb, `out` may alias Yb.
+template <bool INV, bool TABS>
+__device__ __forceinline__ void fh_dct64_core(const double* in, double* out, double2 (*Xb)[FH_R64_LD], double2 (*Yb)[FH_R64_LD],
+                                              const double2* __restrict__ tw, const double2* __restrict__ e512) {
+  constexpr int SIGN = INV ? +1 : -1;
+  const int f = threadIdx.x >> 6, j = threadIdx.x & 63;
+  const bool act = f < FH_RES_ROWS / 2;
+  const int fc = act ? f : 0;
+  const double* ra = in + (2 * fc) * FH_R64_RS;
+  const double* rb = ra + FH_R64_RS;
+  double* oa = out + (2 * fc) * FH_R64_RS;
+  double* ob = oa + FH_R64_RS;
+  double2* X = Xb[fc];
+  double2* Y = Yb[fc];
+  if (act) {
+    double2 v[4];
+    if (!INV) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = j + 64 * r;
+        const int src = (n < 128) ? 2 * n : 511 - 2 * n;
+        v[r] = make_double2(ra[FH_R64_POS(src)], rb[FH_R64_POS(src)]);
+      }
+    } else {
+      const double sc0 = 0.0625, sc1 = 0.044194173824159216;       // 1/sqrt(N), 1/sqrt(2N)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = j + 64 * r;
+        const double sk = (k == 0) ? sc0 : sc1;
+        const int kn = (FH_N - k) & (FH_N - 1);
+        const double sn = (k == 0) ? 0.0 : sc1;
+        const double A = ra[FH_R64_POS(k)] * sk + rb[FH_R64_POS(kn)] * sn;
+        const double B = rb[FH_R64_POS(k)] * sk - ra[FH_R64_POS(kn)] * sn;
+        const double2 e = fh_tab<TABS>(e512 + k);
+        v[r] = fh_cmul64(make_double2(e.x, -e.y), make_double2(A, B));
+      }
+    }
+    fh_dft4_64<SIGN>(v[0], v[1], v[2], v[3]);
+    double2* y = Y + FH_PAD(4 * j);
+    y[0] = v[0]; y[1] = v[1]; y[2] = v[2]; y[3] = v[3];
+  }
+  __syncthreads();
+  if (act) fh_fft256_stage64<SIGN, 4, TABS>(Y, X, j, tw);
+  __syncthreads();
+  if (act) fh_fft256_stage64<SIGN, 16, TABS>(X, Y, j, tw);
+  __syncthreads();
+  if (act) fh_fft256_stage64<SIGN, 64, TABS>(Y, X, j, tw);
+  __syncthreads();
+  if (act) {
+    if (!INV) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = j + 64 * r;
+        const double2 zk = X[FH_PAD(k)];
+        const double2 zn = X[FH_PAD((FH_N - k) & (FH_N - 1))];
+        const double hf = (k == 0) ? 0.03125 : 0.044194173824159216;            // 0.5 * sqrt(1/N), 0.5 * sqrt(2/N)
+        const double2 va = make_double2(hf * (zk.x + zn.x), hf * (zk.y - zn.y));
+        const double2 vb = make_double2(hf * (zk.y + zn.y), -hf * (zk.x - zn.x));
+        const double2 e = fh_tab<TABS>(e512 + k);
+        oa[FH_R64_POS(k)] = e.x * va.x - e.y * va.y;
+        ob[FH_R64_POS(k)] = e.x * vb.x - e.y * vb.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = j + 64 * r;
+        const int pos = (n < 128) ? 2 * n : 511 - 2 * n;
+        const double2 z = X[FH_PAD(n)];
+        oa[FH_R64_POS(pos)] = z.x;
+        ob[FH_R64_POS(pos)] = z.y;
+      }
+    }
+  }
+}
+
+// the thread's 6 elements of a strip: double2 #t, #t+256, #t+512 (flat element e = 2 (t + 256 h) -> row e >> 8, column e & 255)
+__device__ __forceinline__ void fh_r64_put(double* sm_rows, const double (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int e = 2 * (threadIdx.x + FH_PASS_THREADS * h);
+    *reinterpret_cast<double2*>(sm_rows + (e >> 8) * FH_R64_RS + FH_R64_POS(e & 255)) = make_double2(r[2 * h], r[2 * h + 1]);
+  }
+}
+__device__ __forceinline__ void fh_r64_get(const double* sm_rows, double (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int e = 2 * (threadIdx.x + FH_PASS_THREADS * h);
+    const double2 v = *reinterpret_cast<const double2*>(sm_rows + (e >> 8) * FH_R64_RS + FH_R64_POS(e & 255));
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+__device__ __forceinline__ double2 fh_ld_cg_d2(const double2* p) {
+#ifdef FH_EMU
+  return *p;
+#else
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void fh_r64_load_plane(const double* src, double (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const double2 v = fh_ld_cg_d2(reinterpret_cast<const double2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void fh_r64_load(const double* __restrict__ src, double (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const double2 v = reinterpret_cast<const double2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+// transposed store of strip s into the exchange plane: element (global row g, column k) -> row (plane(g), k), column g & 255
+__device__ __forceinline__ void fh_r64_store_t(const double* sm_rows, double* __restrict__ T, int s) {
+  const int k = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const int g = FH_RES_ROWS * s + 2 * h;
+    double* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
+    *reinterpret_cast<double2*>(d) = make_double2(sm_rows[(2 * h) * FH_R64_RS + FH_R64_POS(k)], sm_rows[(2 * h + 1) * FH_R64_RS + FH_R64_POS(k)]);
+  }
+}
+
+// In-place circular correlation along the 6 rows, float64 (register window, 8 outputs per thread, warps 0..5 active).
+__device__ __forceinline__ void fh_r64_conv(double* sm_rows, const double* __restrict__ taps, int n4, int c4) {
+  const int row = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool act = row < FH_RES_ROWS;
+  double acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+  if (act) {
+    const double* rr = sm_rows + row * FH_R64_RS;
+    const int base = 8 * l - c4;
+    double win[12];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = (base + 2 * u) & (FH_N - 1);
+      const double2 v = *reinterpret_cast<const double2*>(rr + FH_R64_POS(c));
+      win[2 * u] = v.x; win[2 * u + 1] = v.y;
+    }
+    for (int a0 = 0; a0 < n4; a0 += 4) {
+      const int c0 = (base + a0 + 8) & (FH_N - 1), c1 = (base + a0 + 10) & (FH_N - 1);
+      const double2 f0 = *reinterpret_cast<const double2*>(rr + FH_R64_POS(c0));
+      const double2 f1 = *reinterpret_cast<const double2*>(rr + FH_R64_POS(c1));
+      win[8] = f0.x; win[9] = f0.y; win[10] = f1.x; win[11] = f1.y;
+      const double2 t0 = *reinterpret_cast<const double2*>(taps + a0);
+      const double2 t1 = *reinterpret_cast<const double2*>(taps + a0 + 2);
+      const double tt[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fma(tt[aa], win[aa + e], acc[e]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) win[u] = win[u + 4];
+    }
+  }
+  __syncthreads();
+  if (act) {
+    double* wr = sm_rows + row * FH_R64_RS + FH_R64_POS(8 * l);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<double2*>(wr + 2 * u) = make_double2(acc[2 * u], acc[2 * u + 1]);
+  }
+  __syncthreads();
+}
+// like fh_res_stage_taps, widened to float64
+__device__ __forceinline__ int fh_r64_stage_taps(double* s_taps, const float* __restrict__ k, int n, int c, int forward) {
+  const int cen = forward ? n - 1 - c : c;
+  const int sh = (4 - (cen & 3)) & 3;
+  const int n4 = (n + sh + 3) & ~3;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int a = i - sh;
+    s_taps[i] = (a >= 0 && a < n) ? (double)(forward ? k[n - 1 - a] : k[a]) : 0.0;
+  }
+  return (n4 << 8) | (cen + sh);
+}
+// the thread's 6 elements of a Z row slice that is not resident: from L2, past L1 (L1 is left to the twiddle tables)
+__device__ __forceinline__ void fh_r64_get_z_l2(const float* src, float (&r)[FH_RES_ROWS]) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    const float2 v = fh_ld_cg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+// lane l ends with the warp total of v[l] (31 shuffles of 64 bits)
+__device__ __forceinline__ double fh_warp_transpose_sum32_d(double (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const double send = hi ? v[k] : v[k + o];
+      const double keep = hi ? v[k + o] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+// Block sums without barriers of their own: every warp posts its total into an 8-entry slot BEFORE a __syncthreads the
+// caller needs anyway, and whoever needs the block total adds the 8 entries in a fixed order AFTER it (bit-identical in
+// every thread; a slot is rewritten one pass later, many barriers after its last read).
+__device__ __forceinline__ void fh_r64_post(double v, double* slot8) {
+  v = fh_warp_sum(v);
+  if ((threadIdx.x & 31) == 0) slot8[threadIdx.x >> 5] = v;
+}
+__device__ __forceinline__ double fh_r64_sum8(const double* slot8) {
+  double t = slot8[0];
+#pragma unroll
+  for (int w = 1; w < FH_PASS_THREADS / 32; ++w) t += slot8[w];
+  return t;
+}
+// per-thread share of the partials that rode on a grid barrier (read past L1); block total via fh_r64_post / fh_r64_sum8
+__device__ __forceinline__ double fh_r64_ride_part(const double* ride, int nblk) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += FH_PASS_THREADS) v += fh_ldcg(ride + i);
+  return v;
+}
+// float32 -> float64 on the integer pipe (exact for normal numbers; zero becomes 2^-127, subnormals are garbage of that
+// size: both vanish against the other operand).  F2F.F64.F32 issues at 16/clk/SM on B200 (measured) and so does this
+// sequence on the ALU pipe: alternating them doubles the widening rate of the low-rank stages.
+__device__ __forceinline__ double fh_widen_alu(float f) {
+  const unsigned u = fh_f2u(f);
+  const unsigned hi = (((unsigned)((int)u >> 3)) & 0x8fffffffu) + 0x38000000u;
+  return fh_u2d(u << 29, hi);
+}
+#define FH_WIDEN(z, e) (((e) & 1) ? fh_widen_alu(z) : (double)(z))
+
+// grid = C*256/6 CTAs (cooperative), block = 256, dynamic shared memory = sizeof(FhRes64Smem) + min(m, mr_cap) * 6 KB.
+// BIG = false: every row of Z resident (m <= mr_cap and m <= 32).  BIG = true: rows >= mr_cap are re-read from L2.
+// TABS = true: twiddle tables in shared memory (costs two rows of Z); false: read through L1.
+template <bool BIG, bool TABS>
+__global__ void __launch_bounds__(FH_PASS_THREADS, 1)
+fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
+  FH_DYN_SMEM(unsigned char, smem_raw);
+  FhRes64Smem& sm = *reinterpret_cast<FhRes64Smem*>(smem_raw);
+  FhRes64Scratch& sc = *reinterpret_cast<FhRes64Scratch*>(sm.Y);
+  FhRes64Tabs* tabs = reinterpret_cast<FhRes64Tabs*>(smem_raw + sizeof(FhRes64Smem));
+  float* Zs = reinterpret_cast<float*>(smem_raw + sizeof(FhRes64Smem) + (TABS ? sizeof(FhRes64Tabs) : 0));
+  const double2* tw = TABS ? tabs->tw : R.tw;
+  const double2* e512 = TABS ? tabs->e512 : R.e512;
+  double* rows_a = reinterpret_cast<double*>(sm.X);
+  double* rows_b = reinterpret_cast<double*>(sm.Y);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x;
+  const unsigned nblk = gridDim.x;
+  const int m = P.m;
+  const int mr = BIG ? min(m, R.mr_cap) : m;
+  const long d = (long)nblk * FH_RES_SLICE;
+  const size_t img = (size_t)R.image * d;
+  const size_t soff = (size_t)s * FH_RES_SLICE;
+
+  // ---- prologue ----
+  if (tid == 0) { fh_mbar_init(&sm.bar, 1); fh_mbar_fence_init(); }
+  __syncthreads();
+  const float* zsrc = P.Z + (size_t)R.image * FH_MAXM * d + soff;
+  if (mr > 0 && warp == 0) {
+    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)mr * FH_RES_SLICE * 4u);
+    __syncwarp();
+    for (int i = lane; i < mr; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, FH_RES_SLICE * 4u, &sm.bar);
+  }
+  if (TABS) {
+    for (int i = tid; i < FH_R64_TW; i += FH_PASS_THREADS) tabs->tw[i] = R.tw[i];
+    for (int i = tid; i < FH_N; i += FH_PASS_THREADS) tabs->e512[i] = R.e512[i];
+  }
+  int tp[4] = {0, 0, 0, 0};
+  if (P.fuse == 2) {
+    tp[0] = fh_r64_stage_taps(sm.taps[0], P.kr, P.nr, P.cr, 0);
+    tp[1] = fh_r64_stage_taps(sm.taps[1], P.kc, P.nc, P.cc, 0);
+    tp[2] = fh_r64_stage_taps(sm.taps[2], P.kc, P.nc, P.cc, 1);
+    tp[3] = fh_r64_stage_taps(sm.taps[3], P.kr, P.nr, P.cr, 1);
+  }
+  float dl[FH_RES_ROWS], mk[FH_RES_ROWS];
+  fh_g_get<FH_RES_ROWS>(P.delta + img + soff, dl);
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e) mk[e] = 1.f;
+  if (P.fuse == 1) {
+    const float* mp = P.mask + (size_t)(P.mask_batch > 1 ? R.image : 0) * FH_N * FH_N;
+#pragma unroll
+    for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+      const int e = 2 * (tid + FH_PASS_THREADS * h);
+      const int g = FH_RES_ROWS * s + (e >> 8);
+      const float2 v = *reinterpret_cast<const float2*>(mp + (size_t)(g & (FH_N - 1)) * FH_N + (e & (FH_N - 1)));
+      mk[2 * h] = v.x; mk[2 * h + 1] = v.y;
+    }
+  }
+  constexpr int CP = BIG ? 4 : 8, NG = BIG ? 16 : 4, CROWS = FH_PASS_THREADS / CP;
+  const int ci = tid / CP, cpart = tid % CP;
+  double gs[NG];
+#pragma unroll
+  for (int u = 0; u < NG; ++u) gs[u] = 0.0;
+  if (ci < m) {
+    const double* g = P.Gs + ((size_t)R.image * FH_MAXM + ci) * FH_MAXM;
+#pragma unroll
+    for (int u = 0; u < NG; ++u) gs[u] = (cpart + CP * u < m) ? g[cpart + CP * u] : 0.0;
+  }
+  unsigned bar_target = 0;
+  double x[FH_RES_ROWS], r[FH_RES_ROWS], p[FH_RES_ROWS], wp[FH_RES_ROWS];
+  fh_r64_load(R.bvec + soff, x);
+  {
+    double bb = 0.0;                                     // what rides on barrier 1: pass 0 |b|^2, later |r|^2
+#pragma unroll
+    for (int e = 0; e < FH_RES_ROWS; ++e) { r[e] = x[e]; p[e] = 0.0; wp[e] = 0.0; bb = fma(x[e], x[e], bb); }
+    fh_r64_post(bb, sm.s_red[3]);
+  }
+  double rr_old = 0.0, stop2 = -1.0, resid2 = 0.0;
+  int niter = 0, optimal = 0;
+  bool z_ready = (mr == 0);
+  __syncthreads();
+
+#define FH_R64TRACE(slot) do { if (k == 3) FH_TRACE(P, 6, slot); } while (0)
+  for (int k = 0;; ++k) {
+    const unsigned seq = R.seq_base + (unsigned)k + 1u;
+    // ------------------------------------------------------------------ F1: rows forward of r (pass 0: of b = x0)
+    FH_R64TRACE(0);
+    {
+      double w[FH_RES_ROWS];
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) w[e] = r[e] * (double)mk[e];
+      fh_r64_put(rows_a, w);
+      __syncthreads();
+      if (tid == 0) R.ride[0][s] = fh_r64_sum8(sm.s_red[3]);
+      if (P.fuse == 2) fh_r64_conv(rows_a, sm.taps[0], tp[0] >> 8, tp[0] & 255);
+      fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      __syncthreads();
+      fh_r64_store_t(rows_b, R.T[0], s);
+    }
+    FH_R64TRACE(1);
+    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    // ------------------------------------------------------------------ F2: columns forward; scalars; new direction
+    FH_R64TRACE(2);
+    double wr[FH_RES_ROWS];
+    {
+      double t[FH_RES_ROWS];
+      fh_r64_load_plane(R.T[0] + soff, t);
+      fh_r64_post(fh_r64_ride_part(R.ride[0], (int)nblk), sm.s_red[0]);
+      fh_r64_put(rows_a, t);
+      __syncthreads();
+      const double S1 = fh_r64_sum8(sm.s_red[0]);
+      if (P.fuse == 2) fh_r64_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255);
+      fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      __syncthreads();
+      fh_r64_get(rows_b, wr);
+      __syncthreads();                                   // Y is free for the scratch of the low-rank stages
+      if (k == 0) {
+        const double stop = fmax(R.rtol * sqrt(S1), R.atol);                    // cg.py:237
+        stop2 = R.use_stop ? stop * stop : -1.0;
+        if (s == 0 && tid == 0) { P.sc[R.image].bnorm2 = S1; P.sc[R.image].stop2 = stop2; }
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) { p[e] = x[e]; wp[e] = wr[e]; }
+      } else {
+        resid2 = S1;
+        double beta = 0.0;
+        if (k >= 2) {                                                          // end of CG iteration k - 1 (cg.py:258-263)
+          niter = k - 1;
+          const bool converged = (stop2 >= 0.0) && (S1 <= stop2);
+          if (converged) optimal = 1;
+          if (converged || k - 1 >= P.last_allowed) break;
+          beta = S1 / rr_old;
+        }
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) { p[e] = fma(beta, p[e], r[e]); wp[e] = fma(beta, wp[e], wr[e]); }
+        rr_old = S1;
+      }
+    }
+    FH_R64TRACE(3);
+    // ------------------------------------------------------------------ low-rank part: coef = Gs Z (delta w_hat)
+    double vv[FH_RES_ROWS];
+#pragma unroll
+    for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = wp[e];
+    if (m > 0) {
+      if (!z_ready) { fh_mbar_wait(&sm.bar, 0); z_ready = true; }
+      double wd[FH_RES_ROWS];
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) wd[e] = wp[e] * (double)dl[e];
+      {
+        double acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          acc[i] = 0.0;
+          if (i < mr) {
+            float z[FH_RES_ROWS];
+            fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+#pragma unroll
+            for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fma(FH_WIDEN(z[e], e), wd[e], acc[i]);
+          }
+        }
+        const double tot = fh_warp_transpose_sum32_d(acc);
+        if (lane < mr) sc.s_w[warp][lane] = tot;
+      }
+      if (BIG) {
+        for (int c0 = mr; c0 < m; c0 += 32) {            // rows that did not fit: straight from L2, 4 rows (12 loads) in flight
+          double acc[32];
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += 4) {
+            float z[4][FH_RES_ROWS];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c0 + i0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + i0 + u) * d, z[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[i0 + u] = 0.0;
+              if (c0 + i0 + u < m) {
+#pragma unroll
+                for (int e = 0; e < FH_RES_ROWS; ++e) acc[i0 + u] = fma(FH_WIDEN(z[u][e], e), wd[e], acc[i0 + u]);
+              }
+            }
+          }
+          const double tot = fh_warp_transpose_sum32_d(acc);
+          if (c0 + lane < m) sc.s_w[warp][c0 + lane] = tot;
+        }
+      }
+      __syncthreads();
+      if (tid < m) {
+        double t = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t += sc.s_w[wv][tid];
+        fh_ll_put_double(R.ll_dots + (size_t)tid * nblk + s, t, seq);
+      }
+      FH_R64TRACE(4);
+      {
+        constexpr int OROWS = BIG ? FH_MAXM : FH_RES_MAXM;
+        const int own_step = (int)nblk / OROWS > 0 ? (int)nblk / OROWS : 1;
+        if (warp == 0) {
+          if (s % own_step == 0 && s / own_step < m) {
+            const int i = s / own_step;
+            const uint4* col = R.ll_dots + (size_t)i * nblk;
+            double t = 0.0;
+            for (int k0 = lane; k0 < (int)nblk; k0 += 128) {
+              if (k0 + 96 < (int)nblk) {
+                uint4 v[4];
+                fh_ll_wait<4>(col + k0, 32, seq, v);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t += fh_u2d(v[u].x, v[u].z);
+              } else {
+                for (int kk = k0; kk < (int)nblk; kk += 32) {
+                  uint4 v[1];
+                  fh_ll_wait<1>(col + kk, 0, seq, v);
+                  t += fh_u2d(v[0].x, v[0].z);
+                }
+              }
+            }
+            t = fh_warp_sum(t);
+            if (lane == 0) fh_ll_put_double(R.ll_sum + (size_t)i * FH_LL_SPREAD, t, seq);
+          }
+#pragma unroll
+          for (int g = 0; g < (BIG ? 2 : 1); ++g) {
+            const int row = lane + 32 * g;
+            double tot = 0.0;
+            if (row < m) {
+              uint4 v[1];
+              fh_ll_wait<1>(R.ll_sum + (size_t)row * FH_LL_SPREAD, 0, seq, v);
+              tot = fh_u2d(v[0].x, v[0].z);
+            }
+            sc.s_sum[row] = tot;
+          }
+        }
+        FH_R64TRACE(5);
+        __syncthreads();
+        double a = 0.0;
+#pragma unroll
+        for (int u = 0; u < NG; ++u) a += gs[u] * sc.s_sum[cpart + CP * u];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (!BIG) a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (cpart == 0 && ci < CROWS) sc.s_c[ci] = a;
+        __syncthreads();
+      }
+      FH_R64TRACE(6);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < mr) {
+          const double c = sc.s_c[i];
+          float z[FH_RES_ROWS];
+          fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+#pragma unroll
+          for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = fma(c, FH_WIDEN(z[e], e), vv[e]);
+        }
+      }
+      if (BIG) {
+        for (int c0 = mr; c0 < m; c0 += 4) {
+          float z[4][FH_RES_ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (c0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + u) * d, z[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + u < m) {
+              const double c = sc.s_c[c0 + u];
+#pragma unroll
+              for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = fma(c, FH_WIDEN(z[u][e], e), vv[e]);
+            }
+          }
+        }
+      }
+    }
+    FH_R64TRACE(7);
+    // ------------------------------------------------------------------ B1: Sigma_hat w_hat; p.Ap partial; columns inverse
+    {
+      double loc = 0.0, pp = 0.0;
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) {
+        vv[e] *= (double)dl[e];
+        loc = fma(wp[e], vv[e], loc);
+        pp = fma(p[e], p[e], pp);
+      }
+      fh_r64_post(fma(R.sy2, pp, loc), sm.s_red[1]);
+      fh_r64_put(rows_a, vv);
+      __syncthreads();                                   // also: the scratch in Y is dead, the transform may use Y again
+      if (tid == 0) R.ride[1][s] = fh_r64_sum8(sm.s_red[1]);
+      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      __syncthreads();
+      if (P.fuse == 2) fh_r64_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255);
+      fh_r64_store_t(rows_b, R.T[1], s);
+    }
+    FH_R64TRACE(8);
+    fh_grid_sync(R.grid_counter, bar_target, nblk);
+    // ------------------------------------------------------------------ B2: rows inverse; q; step
+    FH_R64TRACE(9);
+    {
+      double t[FH_RES_ROWS];
+      fh_r64_load_plane(R.T[1] + soff, t);
+      fh_r64_post(fh_r64_ride_part(R.ride[1], (int)nblk), sm.s_red[2]);
+      fh_r64_put(rows_a, t);
+      __syncthreads();
+      const double pAp = fh_r64_sum8(sm.s_red[2]);
+      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      __syncthreads();
+      if (P.fuse == 2) fh_r64_conv(rows_b, sm.taps[3], tp[3] >> 8, tp[3] & 255);
+      fh_r64_get(rows_b, t);
+      double rr = 0.0;
+      if (R.apply_only) {                                // Sigma v for fh_cov_dot_f64: t is the result
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) x[e] = t[e];
+        break;
+      }
+      if (k == 0) {
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) {        // r0 = b - A_op b     (cg.py:233-235, x0 = b)
+          const double q = fma(R.sy2, p[e], t[e] * (double)mk[e]);
+          r[e] = x[e] - q;
+          rr = fma(r[e], r[e], rr);
+        }
+      } else {
+        if (pAp <= 1e-16 && !R.timing) { niter = k; break; }                    // cg.py:250
+        const double alpha = rr_old / pAp;
+#pragma unroll
+        for (int e = 0; e < FH_RES_ROWS; ++e) {
+          const double q = fma(R.sy2, p[e], t[e] * (double)mk[e]);
+          x[e] = fma(alpha, p[e], x[e]);
+          r[e] = fma(-alpha, q, r[e]);
+          rr = fma(r[e], r[e], rr);
+        }
+      }
+      fh_r64_post(rr, sm.s_red[3]);
+    }
+    FH_R64TRACE(10);
+  }
+  if (!z_ready) fh_mbar_wait(&sm.bar, 0);
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h)
+    reinterpret_cast<double2*>(R.x_out + soff)[tid + FH_PASS_THREADS * h] = make_double2(x[2 * h], x[2 * h + 1]);
+  if (s == 0 && tid == 0) {
+    FhCgScalars* w = P.sc + R.image;
+    w->resid2 = resid2;
+    w->rr[0] = rr_old; w->rr[1] = rr_old;
+    w->niter = niter;
+    w->optimal = optimal;
+    fh_set_done(w, niter + 1);
+    if (R.info_out) { R.info_out->residual_norm = sqrt(resid2); R.info_out->niter = niter; R.info_out->optimal = optimal; }
+  }
+}
+
+// ---- float64 helpers around the solve (once per solve, not per iteration) --------------------------------------------
+// Circular convolution with a sparse tap list in float64 (the operator of fh_k_conv_taps):
+//   transpose = 0:  out[i][j] = sum_t w_t in[(i - dy_t) mod H][(j - dx_t) mod W]      transpose = 1: offsets negated
+// 32 x 32 output tile per CTA, halo staged in shared memory.  grid = (W/32, H/32, planes), block (32, 8).
+__global__ void __launch_bounds__(256)
+fh_k_conv_taps64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int transpose) {
+  FH_DYN_SMEM(double, sm);
+  const int oy0 = transpose ? taps.ymin : -taps.ymax, oy1 = transpose ? taps.ymax : -taps.ymin;
+  const int ox0 = transpose ? taps.xmin : -taps.xmax, ox1 = transpose ? taps.xmax : -taps.xmin;
+  const int th = 32 + (oy1 - oy0), tw = 32 + (ox1 - ox0);
+  const int tws = tw | 1;
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < th; r += 8) {
+    int gi = (i0 + oy0 + r) % H; if (gi < 0) gi += H;
+    const double* srow = in + plane + (size_t)gi * W;
+    for (int c = threadIdx.x; c < tw; c += 32) {
+      int gj = (j0 + ox0 + c) % W; if (gj < 0) gj += W;
+      sm[r * tws + c] = srow[gj];
+    }
+  }
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const double* base = sm + threadIdx.y * tws + threadIdx.x;
+  for (int t = 0; t < taps.n; ++t) {
+    const int oy = transpose ? taps.dy[t] : -taps.dy[t];
+    const int ox = transpose ? taps.dx[t] : -taps.dx[t];
+    const double wv = (double)taps.w[t];
+    const double* p = base + (oy - oy0) * tws + (ox - ox0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = fma(wv, p[8 * q * tws], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[plane + (size_t)(i0 + threadIdx.y + 8 * q) * W + j0 + threadIdx.x] = acc[q];
+}
+// Super-resolution in float64: forward = conv then [0::sf, 0::sf]; transpose = zero insertion then conv^T (utils_sisr.py:44-61).
+__global__ void __launch_bounds__(256)
+fh_k_sr_forward64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int sf) {
+  const int h = H / sf, w = W / sf;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p = blockIdx.y;
+  if (idx >= h * w) return;
+  const int I = idx / w, J = idx % w;
+  const double* src = in + p * (size_t)H * W;
+  double acc = 0.0;
+  for (int t = 0; t < taps.n; ++t) {
+    const int gi = (sf * I - taps.dy[t] + H) & (H - 1), gj = (sf * J - taps.dx[t] + W) & (W - 1);
+    acc = fma((double)taps.w[t], src[(size_t)gi * W + gj], acc);
+  }
+  out[p * (size_t)h * w + idx] = acc;
+}
+__global__ void __launch_bounds__(256)
+fh_k_sr_transpose64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int sf) {
+  const int h = H / sf, w = W / sf;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t p = blockIdx.y;
+  if (idx >= H * W) return;
+  const int i = idx / W, j = idx % W;
+  const double* src = in + p * (size_t)h * w;
+  double acc = 0.0;
+  for (int t = 0; t < taps.n; ++t) {
+    const int gi = (i + taps.dy[t] + H) & (H - 1), gj = (j + taps.dx[t] + W) & (W - 1);
+    if ((gi % sf) == 0 && (gj % sf) == 0) acc = fma((double)taps.w[t], src[(size_t)(gi / sf) * w + gj / sf], acc);
+  }
+  out[p * (size_t)H * W + idx] = acc;
+}
+// b = mask .* y - mask .* mu (inpainting, conditioning_mechanisms.py:407) or y - A mu (:515, :663), in float64
+__global__ void __launch_bounds__(256)
+fh_k_rhs64(const double* __restrict__ y, const double* __restrict__ amu, const float* __restrict__ mask, int mask_batch, long hw,
+           double* __restrict__ bvec, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t b = blockIdx.y;
+  if (i >= n) return;
+  const double yv = y[b * n + i], av = amu[b * n + i];
+  if (mask) {
+    const double mk = (double)mask[(mask_batch > 1 ? b * hw : 0) + (i % hw)];
+    bvec[b * n + i] = mk * yv - mk * av;
+  } else {
+    bvec[b * n + i] = yv - av;
+  }
+}
+__global__ void __launch_bounds__(256) fh_k_f2d(const float* __restrict__ in, double* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+__global__ void __launch_bounds__(256) fh_k_d2f(const double* __restrict__ in, float* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}

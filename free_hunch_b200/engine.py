@@ -4,6 +4,7 @@ Tensors go in and out as torch tensors on the context's device (float32, contigu
 sees raw pointers and the current CUDA stream.  Nothing here computes on the host.
 """
 import ctypes
+import zlib
 
 import numpy as np
 import torch
@@ -11,7 +12,8 @@ import torch
 from . import _lib
 
 BASIS_IDENTITY, BASIS_DCT = 0, 1
-CG_AUTO, CG_STREAMING, CG_RESIDENT = 0, 1, 2      # fh_ctx_set_cg_mode (include/free_hunch_b200.h)
+CG_AUTO, CG_STREAMING, CG_RESIDENT, CG_RESIDENT_F32 = 0, 1, 2, 3      # fh_ctx_set_cg_mode (include/free_hunch_b200.h)
+FH_ESTATE = -4
 MAX_RANK = 64            # FH_MAXM: rows of Z (two per BFGS space update)
 
 
@@ -57,10 +59,11 @@ class Context:
         t = torch.as_tensor(t)
         if t.device.type != "cpu":
             return self.prep(t)
-        flat = t.reshape(-1)
-        step = max(1, flat.numel() // 61)
+        flat = t.reshape(-1).contiguous()
         key = (flat.data_ptr(), flat.numel(), str(flat.dtype))
-        sig = (float(flat[::step].double().sum()), float(flat[0]), float(flat[-1])) if flat.numel() else (0.0, 0.0, 0.0)
+        # full-content checksum (~1 ms for 786 KB): a strided sample could return a stale device copy after an in-place
+        # edit or when a freed host buffer's address is reused by different data
+        sig = zlib.crc32(memoryview(flat.numpy()).cast("B")) if flat.numel() else 0
         cache = self.__dict__.setdefault("_upload_cache", {})
         hit = cache.get(key)
         if hit is not None and hit[0] == sig:
@@ -127,6 +130,13 @@ class CovState:
         return _lib.lib().fh_state_var2(self._h)
 
     def cov_dot(self, v):
+        if torch.is_tensor(v) and v.dtype == torch.float64 and self.basis == BASIS_DCT:
+            v64 = _prep64(self.ctx, v, self.shape)
+            out = torch.empty_like(v64)
+            rc = _lib.lib().fh_cov_dot_f64(self._h, _ptr(v64), _ptr(out), self.ctx.stream())
+            if rc != FH_ESTATE:
+                _lib.check(rc)
+                return out
         v = self.ctx.prep(v, self.shape)
         out = torch.empty_like(v)
         _lib.check(_lib.lib().fh_cov_dot(self._h, _ptr(v), _ptr(out), self.ctx.stream()))
@@ -236,17 +246,39 @@ class Operator:
             pass
 
 
+def _prep64(ctx, t, shape):
+    t = torch.as_tensor(t).to(device=ctx.device, dtype=torch.float64).contiguous()
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def _wants_f64(mu):
+    return torch.is_tensor(mu) and mu.dtype == torch.float64
+
+
 def cg_solve(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
-    """(mat, info): the guidance solve of conditioning_mechanisms.py:384-419/489-527/641-675 for a batch."""
+    """(mat, info): the guidance solve of conditioning_mechanisms.py:384-419/489-527/641-675 for a batch.
+    A float64 `mu` (what the reference's denoiser wrapper returns) takes the float64 entry point
+    (fh_cg_solve_f64: float64 right-hand side, CG and result) where it is available; mat then is float64."""
     ctx = state.ctx
-    y = ctx.prep(y, op.y_shape(state.B))
-    mu = ctx.prep(mu, state.shape)
-    mat = torch.empty_like(mu)
     niter = (ctypes.c_int * state.B)()
     optimal = (ctypes.c_int * state.B)()
     resid = (ctypes.c_double * state.B)()
-    _lib.check(_lib.lib().fh_cg_solve(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
-                                      int(fixed_iters), _ptr(mat), niter, optimal, resid, ctx.stream()))
+    rc = FH_ESTATE
+    if _wants_f64(mu):
+        mu64 = _prep64(ctx, mu, state.shape)
+        mat = torch.empty_like(mu64)
+        y64 = _prep64(ctx, y, op.y_shape(state.B))
+        rc = _lib.lib().fh_cg_solve_f64(state._h, op._h, _ptr(y64), _ptr(mu64), float(sigma_y2), float(rtol), int(maxiter),
+                                        int(fixed_iters), _ptr(mat), niter, optimal, resid, ctx.stream())
+    if rc == FH_ESTATE:
+        y = ctx.prep(y, op.y_shape(state.B))
+        mu = ctx.prep(mu, state.shape)
+        mat = torch.empty_like(mu)
+        rc = _lib.lib().fh_cg_solve(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
+                                    int(fixed_iters), _ptr(mat), niter, optimal, resid, ctx.stream())
+    _lib.check(rc)
     info = {"niter": list(niter), "optimal": [bool(o) for o in optimal], "residual_norm": list(resid)}
     return mat, info
 
@@ -265,16 +297,24 @@ class DeferredCgInfo:
 
 
 def cg_solve_async(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0):
-    """(mat, DeferredCgInfo) with no host synchronisation, or None where the resident kernel does not apply
-    (fh_cg_solve_async returns FH_ESTATE: the caller uses cg_solve)."""
+    """(mat, DeferredCgInfo) with no host synchronisation, or None where no resident kernel applies
+    (FH_ESTATE: the caller uses cg_solve).  float64 `mu` -> float64 solve and result, as in cg_solve."""
     ctx = state.ctx
-    y = ctx.prep(y, op.y_shape(state.B))
-    mu = ctx.prep(mu, state.shape)
-    mat = torch.empty_like(mu)
     info = torch.zeros(16 * state.B, dtype=torch.uint8, device=ctx.device)
-    rc = _lib.lib().fh_cg_solve_async(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
-                                      int(fixed_iters), _ptr(mat), _ptr(info), ctx.stream())
-    if rc == -4:                       # FH_ESTATE
+    rc = FH_ESTATE
+    if _wants_f64(mu):
+        mu64 = _prep64(ctx, mu, state.shape)
+        mat = torch.empty_like(mu64)
+        y64 = _prep64(ctx, y, op.y_shape(state.B))
+        rc = _lib.lib().fh_cg_solve_f64_async(state._h, op._h, _ptr(y64), _ptr(mu64), float(sigma_y2), float(rtol), int(maxiter),
+                                              int(fixed_iters), _ptr(mat), _ptr(info), ctx.stream())
+    if rc == FH_ESTATE:
+        y = ctx.prep(y, op.y_shape(state.B))
+        mu = ctx.prep(mu, state.shape)
+        mat = torch.empty_like(mu)
+        rc = _lib.lib().fh_cg_solve_async(state._h, op._h, _ptr(y), _ptr(mu), float(sigma_y2), float(rtol), int(maxiter),
+                                          int(fixed_iters), _ptr(mat), _ptr(info), ctx.stream())
+    if rc == FH_ESTATE:
         return None
     _lib.check(rc)
     return mat, DeferredCgInfo(info, state.B)

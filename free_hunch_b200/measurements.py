@@ -258,11 +258,16 @@ class InpaintingOperator(_LinearOperator):
 
     def __init__(self, device=None, sigma_s=0.1, mask_opt=None, mask=None, **kwargs):
         size = mask_opt["image_size"] if mask_opt is not None else mask.shape[-1]
-        self._setup((1, 3, size, size), sigma_s, device)
         if mask is None:
-            torch.randn(*self.in_shape)        # the reference draws an unused image first (measurements.py:244)
-            mask = MaskGenerator(**mask_opt)(torch.zeros(*self.in_shape))
-        self.mask = torch.as_tensor(mask, dtype=torch.float32).to(self.device).reshape(-1, 3, size, size)
+            torch.randn(1, 3, size, size)      # the reference draws an unused image first (measurements.py:244)
+            mask = MaskGenerator(**mask_opt)(torch.zeros(1, 3, size, size))
+        mask = torch.as_tensor(mask, dtype=torch.float32).reshape(-1, 3, size, size)
+        # one mask per image, shared by its channels (measurements.py:287-299 builds it that way); the library applies
+        # channel 0 to all three, so a per-channel mask must be refused rather than silently misapplied
+        if not (torch.equal(mask[:, 0], mask[:, 1]) and torch.equal(mask[:, 0], mask[:, 2])):
+            raise ValueError("InpaintingOperator: the mask must be identical across channels")
+        self._setup((mask.shape[0], 3, size, size), sigma_s, device)       # workspace sized for the mask's own batch
+        self.mask = mask.to(self.device)
         self.op = engine.Operator.inpaint(self.ctx, self.mask[:, 0])
         self.out_shape = self.in_shape
 

@@ -88,3 +88,24 @@ class AnalyticDCTGaussianDenoiser(torch.nn.Module):
         s2 = float(sigma) ** 2
         gain = self.v / (self.v + s2)
         return _SymmetricDctGain.apply(x, gain, self.fh_ctx), None
+
+
+class AnalyticDCTGaussianDenoiser64(torch.nn.Module):
+    """The same stand-in denoiser in float64 PyTorch (dense 256 x 256 DCT matrices, plain matmuls, autograd VJP): what
+    the golden runs of the reference use as `model` (tests/golden/make_golden.py), so that a parity run differs from the
+    reference only in the hot path under test and not in the stand-in's own float32 transforms."""
+
+    def __init__(self, dct_variance, device):
+        super().__init__()
+        n = dct_variance.shape[-1]
+        kk = np.arange(n)[:, None]
+        nn = np.arange(n)[None, :]
+        cm = np.sqrt(2.0 / n) * np.cos(np.pi * (2 * nn + 1) * kk / (2 * n))
+        cm[0] /= np.sqrt(2.0)
+        self.register_buffer("cm", torch.from_numpy(cm).to(device))
+        self.register_buffer("v", torch.as_tensor(np.asarray(dct_variance), dtype=torch.float64).to(device))
+
+    def forward(self, x, sigma):
+        gain = self.v / (self.v + float(sigma) ** 2)
+        xh = self.cm @ x.to(torch.float64) @ self.cm.T
+        return self.cm.T @ (gain * xh) @ self.cm, None

@@ -8,6 +8,10 @@
  * void*.  Functions return 0 on success and a negative FH_E* code on failure; fh_last_error() gives text.
  * Nothing in this library falls back to the CPU: without a CUDA device every call fails with FH_ECUDA.
  *
+ * Threading / streams: one host thread and ONE stream per fh_ctx at a time.  The context owns scratch planes and the
+ * buffers of destroyed states (parked for reuse by the next fh_state_create); both are protected by stream order only,
+ * so work of one context must not be spread over several streams without the caller ordering them with events.
+ *
  * Layout: an "image vector" is (B, C, H, W) contiguous float32, d = C*H*W per image.  In the DCT basis
  * (image_base_covariance = dct_diagonal) H = W = 256 is required.
  */
@@ -52,6 +56,7 @@ int fh_ctx_destroy(fh_ctx* ctx);
 #define FH_CG_AUTO 0
 #define FH_CG_STREAMING 1
 #define FH_CG_RESIDENT 2
+#define FH_CG_RESIDENT_F32 3 /* the float32 predecessor of the resident kernel (kept for comparison; not a parity path) */
 int fh_ctx_set_cg_mode(fh_ctx* ctx, int mode);
 int fh_ctx_cg_last_mode(const fh_ctx* ctx); /* FH_CG_STREAMING or FH_CG_RESIDENT: path of the last DCT-basis solve */
 
@@ -67,11 +72,14 @@ int fh_state_create(fh_ctx* ctx, fh_state** out, int batch, int basis);
 int fh_state_destroy(fh_state* st);
 int fh_state_init(fh_state* st, const float* init_variance_dev, double init_noise_variance, void* stream);
 int fh_state_rank(const fh_state* st); /* m = rows of Z (2 per space update) */
-double fh_state_var2(const fh_state* st);
+double fh_state_var2(const fh_state* st); /* sigma^2 the Sigma side of the state currently sits at */
 
 /* Sigma . v  -- denoiser_cov_vector_dot, online_update_bfgs.py:194-204 (identity) and :370-374 (DCT:
  * v and the result are in pixel space, DCT -> diag+low-rank -> IDCT happens inside). */
 int fh_cov_dot(fh_state* st, const float* v_dev, float* out_dev, void* stream);
+/* The same product with float64 in and out and float64 arithmetic throughout (DCT basis; FH_ESTATE otherwise): the
+ * mechanism's mu + Sigma mat (conditioning_mechanisms.py:284-285) cancels to ~1 % of its terms at high sigma. */
+int fh_cov_dot_f64(fh_state* st, const double* v_dev, double* out_dev, void* stream);
 
 /* update_time_step, online_update_bfgs.py:153-192 (+ DCT wrapper :357-360).  x/score/mean_out/score_out
  * are (B,d).  only_covariance!=0 skips the score/mean update (outputs untouched, may be NULL). */
@@ -130,6 +138,15 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
 typedef struct { double residual_norm; int niter; int optimal; } fh_cg_info;
 int fh_cg_solve_async(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                       int maxiter, int fixed_iters, float* mat_out_dev, fh_cg_info* info_dev, void* stream);
+/* The guidance solve in the reference's own precision (cg.py runs in float64): y_dev, mu_dev and mat_out_dev
+ * are float64; right-hand side, CG vectors, DCTs, operator taps, low-rank products and reductions
+ * are all float64 (fh_cg_res64.cuh); only the stored delta and Z are float32.  Same stopping rule and outputs as
+ * fh_cg_solve / fh_cg_solve_async.  FH_ESTATE where the resident float64 kernel does not apply. */
+int fh_cg_solve_f64(fh_state* st, fh_op* op, const double* y_dev, const double* mu_dev, double sigma_y2, double rtol,
+                    int maxiter, int fixed_iters, double* mat_out_dev, int* niter_host, int* optimal_host,
+                    double* resid_host, void* stream);
+int fh_cg_solve_f64_async(fh_state* st, fh_op* op, const double* y_dev, const double* mu_dev, double sigma_y2, double rtol,
+                          int maxiter, int fixed_iters, double* mat_out_dev, fh_cg_info* info_dev, void* stream);
 /* bench.py's roofline: average device time (ms) of `reps` back-to-back launches of ONE kernel of the fused CG
  * iteration at the state's current rank, CUDA events on `stream`.  which: 0 fwd_rows, 1 fwd_cols, 2 inv_cols,
  * 3 inv_rows, 4 xr.  Only for operators that fold into the DCT passes (inpainting, separable blur). */

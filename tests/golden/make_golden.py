@@ -389,6 +389,113 @@ def golden_mechanism(ob, cm, ms, max_rtol=1.0, t_steps=None, fname="mechanism.np
     print(fname, ": calls", call, "niters", niters, "k", int(g["k_final"]))
 
 
+def golden_config(ob, cm, ms, operator, num_steps, solver, max_rtol, fname, seed=5):
+    """A FULL BASELINE configuration through the real reference: BFGSOnlineUpdate inside the EDM Heun / Euler loop of
+    generate_conditional.py:131-167 on the complete `num_steps` sigma grid (30-step Heun = 59 mechanism calls, 100-step
+    Euler = 100), analytic DCT-Gaussian denoiser (float64 dense DCT), for gaussian_blur / motion_blur / inpainting
+    (random mask, p in [0.6, 0.8]) / super_resolution x4.  Stores the per-call outputs and the final sample (subsampled),
+    the CG iteration count of every call, and whatever the test needs to rebuild the same inputs (OTF, mask bits, y)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), ".."))
+    from oracle import fh_oracle as fo
+    g = {}
+    data_dir = os.path.join(REF, "data", "imagenet")
+    var = torch.load(os.path.join(data_dir, "dct_variance.pt")).to(torch.float64)
+    shape = (1, 3, 256, 256)
+    n = 256
+    kk = np.arange(n)[:, None]; nn = np.arange(n)[None, :]
+    Cm = np.sqrt(2.0 / n) * np.cos(np.pi * (2 * nn + 1) * kk / (2 * n)); Cm[0] /= np.sqrt(2.0)
+    Cm = torch.from_numpy(Cm)
+
+    def model(x, sigma):
+        gain = var / (var + sigma ** 2)
+        xh = Cm @ x.to(torch.float64) @ Cm.T
+        return Cm.T @ (gain * xh) @ Cm, None
+
+    x_clean = synth_image(var.numpy(), seed)
+    os.chdir(REF)
+    if operator == "inpainting":
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        opt = dict(mask_type="random", mask_prob_range=(0.6, 0.8), image_size=256)
+        op = ms.get_operator("inpainting", device="cpu", sigma_s=0.1, mask_opt=opt)      # draws the mask (numpy global RNG)
+        mask = op.mask.to(torch.float64)
+        g["mask_bits"] = np.packbits(mask.numpy()[0, 0].astype(np.uint8))
+        y = (torch.from_numpy(x_clean) + 0.1 * torch.from_numpy(make_inputs(seed + 4, shape))) * mask
+    elif operator == "super_resolution":
+        op = ms.get_operator("super_resolution", in_shape=shape, scale_factor=4, sigma_s=0.1, device="cpu")
+        y = op.forward(torch.from_numpy(x_clean).float(), noiseless=True).to(torch.float64)
+        y = y + 0.1 * torch.from_numpy(make_inputs(seed + 4, tuple(y.shape)))
+        g["y"] = y.numpy().astype(np.float32)
+        y = torch.from_numpy(g["y"])
+    else:
+        kw = dict(intensity=3.0) if operator == "gaussian_blur" else dict(intensity=0.5)
+        op = ms.get_operator(operator, in_shape=shape, kernel_size=61, sigma_s=0.1, device="cpu", **kw)
+        y = op.forward(torch.from_numpy(x_clean), noiseless=True) + 0.1 * torch.from_numpy(make_inputs(seed + 4, shape))
+        if operator == "motion_blur":
+            g["FB"] = op.pre_calculated[0].numpy()[0, 0]
+    t_steps = fo.edm_sigma_steps(num_steps)
+    mech = cm.BFGSOnlineUpdate(1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(t_steps[0] ** 2, dtype=torch.float64),
+                               data_dim=3 * 256 * 256, max_vector_count=100000, data_dir=data_dir, image_base_covariance="dct_diagonal",
+                               pca_component_count=0, denoiser_mean_error_threshold=0.2, use_analytical_score_time_update=True,
+                               project_to_diagonal=False, space_step_update_threshold=10.0, space_step_update_lower_threshold=1.0,
+                               max_rtol=max_rtol, do_space_updates=True, use_analytic_var_at_end=False, solver_type="customcuda",
+                               use_rtol_func=True, diffpir_lambda=0)
+    import conditioning_utils.cg as rcg
+    import time
+    niters = []
+    orig_cg = rcg.cg
+
+    def spy(*a, **k):
+        x, info = orig_cg(*a, **k)
+        niters.append(info["niter"])
+        return x, info
+    rcg.cg = spy
+    cm.cg = spy if hasattr(cm, "cg") else None
+    t0 = time.time()
+    x_next = torch.from_numpy(make_inputs(seed - 3, shape)) * t_steps[0]
+    call = 0
+    N = len(t_steps) - 1
+    for i, (tc, tn) in enumerate(zip(t_steps[:-1], t_steps[1:])):
+        x_hat = x_next.detach().clone()
+        with torch.enable_grad():
+            den = mech(x_hat.requires_grad_(), model, y, torch.tensor(tc, dtype=torch.float64)).detach()
+        g[f"call{call}_out"] = sub(den.numpy()).astype(np.float32) if call % 4 else sub(den.numpy()); call += 1
+        d_cur = (x_hat.detach() - den) / tc
+        h = tn - tc
+        x_prime = x_hat.detach() + h * d_cur
+        if solver == "euler" or i == N - 1:
+            x_next = x_prime
+        else:
+            with torch.enable_grad():
+                den2 = mech(x_prime.clone().requires_grad_(), model, y, torch.tensor(tn, dtype=torch.float64)).detach()
+            g[f"call{call}_out"] = sub(den2.numpy()); call += 1
+            d_prime = x_prime / tn - den2 / tn
+            x_next = x_hat.detach() + h * (0.5 * d_cur + 0.5 * d_prime)
+        print(f"  [{fname}] step {i + 1}/{N} sigma {tc:.4f} calls {call} cg {sum(niters)} t {time.time() - t0:.0f}s", flush=True)
+    rcg.cg = orig_cg
+    g["t_steps"] = np.asarray(t_steps)
+    g["niters"] = np.array(niters)
+    g["final"] = sub(x_next.numpy())
+    g["final_norm"] = np.array(np.linalg.norm(x_next.numpy()))
+    g["k_final"] = np.array(mech.covariance_model.vectors_denoiser_cov_u.shape[-1])
+    g["max_rtol"] = np.array(max_rtol)
+    g["seed"] = np.array(seed)
+    np.savez_compressed(os.path.join(OUT, fname), **g)
+    print(fname, ": calls", call, "cg total", sum(niters), "k", int(g["k_final"]), f"{time.time() - t0:.0f}s")
+
+
+CONFIGS = {   # name -> (operator, num_steps, solver, max_rtol)
+    "c1_gauss_heun30": ("gaussian_blur", 30, "heun", 1.0),
+    "c2_inpaint_heun30": ("inpainting", 30, "heun", 1.0),
+    "c3_sr_heun30": ("super_resolution", 30, "heun", 1.0),
+    "c4_motion_euler100": ("motion_blur", 100, "euler", 1.0),
+    "c1_gauss_heun30_tight": ("gaussian_blur", 30, "heun", 1e-6),
+    "c2_inpaint_heun30_tight": ("inpainting", 30, "heun", 1e-6),
+    "c3_sr_heun30_tight": ("super_resolution", 30, "heun", 1e-6),
+    "c4_motion_euler100_tight": ("motion_blur", 100, "euler", 1e-6),
+}
+
+
 def golden_misc(cm):
     """rtol schedule, sigma grid (round_sigma of the iDDPM-linear wrapper), toy Gaussian mixture."""
     g = {}
@@ -459,6 +566,9 @@ if __name__ == "__main__":
     if "misc" in which: golden_misc(cm)
     if "full" in which: golden_full(ob, cm, ms)
     if "mech" in which: golden_mechanism(ob, cm, ms)
+    for name, (opn, ns, solver, mr) in CONFIGS.items():
+        if name in which:
+            golden_config(ob, cm, ms, opn, ns, solver, mr, f"cfg_{name}.npz")
     if "mech_tight" in which:
         golden_mechanism(ob, cm, ms, max_rtol=1e-6, t_steps=np.array([80.2878, 8.463, 5.1405, 2.2699, 0.2053, 0.0]),
                          fname="mechanism_tight.npz")

@@ -79,11 +79,11 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--profile-kernels", action="store_true")
-    ap.add_argument("--mode", default="auto", choices=["auto", "streaming", "resident"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "streaming", "resident", "resident_f32"])
     args = ap.parse_args()
     ctx, st, op, y, mu, t_time, t_space = build(args)
     B, k = args.batch, st.rank // 2
-    ctx.set_cg_mode({"auto": E.CG_AUTO, "streaming": E.CG_STREAMING, "resident": E.CG_RESIDENT}[args.mode])
+    ctx.set_cg_mode({"auto": E.CG_AUTO, "streaming": E.CG_STREAMING, "resident": E.CG_RESIDENT, "resident_f32": E.CG_RESIDENT_F32}[args.mode])
     for _ in range(2):
         E.cg_solve(st, op, y, mu, 0.01, 1.0, maxiter=args.iters, fixed_iters=args.iters)
     torch.cuda.synchronize()
@@ -110,7 +110,7 @@ def main():
            "launches_per_iteration": launches / args.reps / done,
            "algorithmic_MB_per_iteration": alg / 1e6, "achieved_GBps": alg / (us_it * 1e-6) / 1e9,
            "time_update_ms": t_time, "space_update_ms": t_space, "niter": info["niter"][0],
-           "cg_path": {E.CG_STREAMING: "streaming", E.CG_RESIDENT: "resident"}.get(ctx.cg_last_mode)}
+           "cg_path": {E.CG_STREAMING: "streaming", E.CG_RESIDENT: "resident (float64)", E.CG_RESIDENT_F32: "resident (float32)"}.get(ctx.cg_last_mode)}
     if args.profile_kernels:
         E.profile_kernels(False)
         out["kernels"] = {n: [c, round(t / c * 1e3, 2)] for n, (c, t) in E.kernel_profile().items()}
