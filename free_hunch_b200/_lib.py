@@ -39,6 +39,8 @@ _SIGNATURES = {
     "fh_cov_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "fh_cov_dot_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "fh_time_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "fh_time_update_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "fh_space_update_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_space_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_state_set_cov_vectors": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),
     "fh_state_drop_all": (c_int, [c_void_p, c_double, c_void_p]),

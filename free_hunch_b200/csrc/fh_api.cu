@@ -137,7 +137,7 @@ struct fh_ctx {
   double* d64[3];                     // (max_batch, d) float64 vectors: b, solution, A mu / converted inputs
   double* d64_out;                    // (max_batch, d) float64 result of the float32 entry points
   double* d64_y;                      // (max_batch, d) widened y of the float32 entry points
-  int r64_cap, r64_cap_tabs;          // rows of Z the float64 kernel keeps in shared memory (without / with the twiddle tables beside them)
+  int r64_smem_max;                   // opt-in shared memory per block: the float64 kernel's Z capacity is what its fixed part, tables and gather staging leave
   int r64_ok;
 };
 
@@ -160,6 +160,7 @@ struct fh_op {
   float *kr, *kc; int nr, nc, cr, cc;
   float* psf_dense; int ks;           // dense PSF on the device (fast x4 super-resolution kernels)
   int4* runs; float *run_wf, *run_wt; int nruns, nrun_taps;   // the PSF as one dense vertical run per column (fh_k_conv_runs)
+  int4* runs6; double *run_wf6, *run_wt6; int nrun_taps6;     // the same runs with float64 weights, every run padded to a multiple of 6 (fh_r64_gather_conv)
 };
 
 static void state_free_buffers(fh_state* p);
@@ -260,7 +261,7 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
     for (int i = 0; i < 3; ++i) FH_CUDA(cudaMalloc((void**)&c->d64[i], (size_t)max_batch * c->d * sizeof(double)));
     FH_CUDA(cudaMalloc((void**)&c->d64_out, (size_t)max_batch * c->d * sizeof(double)));
     FH_CUDA(cudaMalloc((void**)&c->d64_y, (size_t)max_batch * c->d * sizeof(double)));
-    c->r64_cap = 32; c->r64_cap_tabs = 30; c->r64_ok = c->res_ok;
+    c->r64_smem_max = 227 * 1024; c->r64_ok = c->res_ok;
   }
   c->trace = nullptr;
   if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
@@ -294,25 +295,23 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
     // float64 variant: as many rows of Z as fit beside its fixed shared memory
     int smem_max = 0;
     FH_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    c->r64_cap = std::min(FH_RES_MAXM, (int)((smem_max - (int)sizeof(FhRes64Smem)) / (FH_RES_SLICE * 4)));
-    c->r64_cap_tabs = std::min(FH_RES_MAXM, (int)((smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs)) / (FH_RES_SLICE * 4)));
+    c->r64_smem_max = smem_max;
     c->r64_ok = 0;
-    if (c->res_ok && c->r64_cap >= 0 && c->r64_cap_tabs >= 0) {
-      const int smem64 = (int)sizeof(FhRes64Smem) + c->r64_cap * FH_RES_SLICE * 4;
-      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
-      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
-      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+    if (c->res_ok && smem_max >= (int)(sizeof(FhRes64Smem) + sizeof(FhRes64Tabs))) {
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+      FH_CUDA(cudaFuncSetAttribute(fh_k_cg_res64<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
       int a = 0, b = 0, e = 0;
-      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, fh_k_cg_res64<false, true>, FH_PASS_THREADS, smem64));
-      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fh_k_cg_res64<false, false>, FH_PASS_THREADS, smem64));
-      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, fh_k_cg_res64<true, false>, FH_PASS_THREADS, smem64));
-      c->r64_ok = (rows / FH_RES_ROWS <= (long)std::min(std::min(a, b), e) * c->sms) ? 1 : 0;
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, fh_k_cg_res64<false, true>, FH_PASS_THREADS, smem_max));
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fh_k_cg_res64<false, false>, FH_PASS_THREADS, smem_max));
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, fh_k_cg_res64<true, false>, FH_PASS_THREADS, smem_max));
+      c->r64_ok = ((long)channels * FH_R64_CPP <= (long)std::min(std::min(a, b), e) * c->sms) ? 1 : 0;
     }
   }
 #else
   c->res_ok = (height == FH_N && width == FH_N && ((long)channels * height) % FH_RES_ROWS == 0) ? 1 : 0;
   c->r64_ok = c->res_ok;
-  if (const char* e = getenv("FH_EMU_R64_CAP")) { c->r64_cap = atoi(e); c->r64_cap_tabs = std::max(0, c->r64_cap - 2); }   // CPU emulation: the test picks the resident row counts
+  if (const char* e = getenv("FH_EMU_R64_SMEM")) c->r64_smem_max = atoi(e);      // CPU emulation: the test shrinks the shared memory to reach the L2 / L1 variants at small rank
 #endif
   *out = c;
   return FH_OK;
@@ -664,11 +663,28 @@ extern "C" int fh_time_update(fh_state* s, const float* x, const float* score, d
   return from_basis(s, c->scratch[3], mean_out, stream);
 }
 
-extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float* mean_at_xnext, double sigma_t,
-                               const float* x, const float* xnext, int project_to_diagonal, void* stream) {
-  if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update arguments");
-  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
-  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+// update_time_step with float64 in and out: the transfer itself runs in the float32 state (DCT, low-rank algebra), but the
+// result mu' = x + sigma'^2 s' is formed in float64 from the float64 x (|x| ~ sigma >> |mu'|: a float32 x would put its
+// rounding error, 6e-8 |x|, straight into mu').
+extern "C" int fh_time_update_f64(fh_state* s, const double* x, const double* score, double sigma_t, double sigma_tnext,
+                                  int only_cov, double* mean_out, double* score_out, void* stream) {
+  if (only_cov) return fh_time_update(s, nullptr, nullptr, sigma_t, sigma_tnext, 1, nullptr, nullptr, stream);
+  if (!s || !x || !score || !mean_out || !score_out) FH_FAIL(FH_EINVAL, "bad fh_time_update_f64 arguments");
+  fh_ctx* c = s->ctx;
+  const long tot = (long)s->B * s->d;
+  const dim3 g((unsigned)((tot + 255) / 256)), b(256);
+  FH_LAUNCH(fh_k_d2f, g, b, 0, stream, x, c->cgv[0], tot);
+  FH_LAUNCH(fh_k_d2f, g, b, 0, stream, score, c->cgv[1], tot);
+  FH_KCHECK();
+  int rc = fh_time_update(s, c->cgv[0], c->cgv[1], sigma_t, sigma_tnext, 0, c->cgv[2], c->cgv[3], stream);
+  if (rc) return rc;
+  FH_LAUNCH(fh_k_tu_finish64, g, b, 0, stream, x, (const float*)c->cgv[3], sigma_tnext * sigma_tnext, mean_out, score_out, tot);
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// Everything of the space update after dx (pixel space, scratch[0]) and de = sigma^2 (mu' - mu_hat) (scratch[1]) exist.
+static int space_update_from_diffs(fh_state* s, double sigma_t, void* stream) {
   fh_ctx* c = s->ctx;
   const int vec = vec_ok(s->d);
   int rc;
@@ -677,9 +693,6 @@ extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float*
   s->var2 = sigma_t * sigma_t;
   float* dxp = c->scratch[0];
   float* dep = c->scratch[1];
-  FH_LAUNCH(fh_k_su_diffs, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, x, xnext, mean_at_x, mean_at_xnext,
-            (float)(sigma_t * sigma_t), dxp, dep, s->d, vec);
-  FH_KCHECK();
   float* dx = c->scratch[2];
   float* de = c->scratch[3];
   if ((rc = to_basis(s, dxp, dx, stream))) return rc;
@@ -696,6 +709,33 @@ extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float*
   FH_KCHECK();
   s->m += 2;
   return refresh_core(s, stream);
+}
+
+extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float* mean_at_xnext, double sigma_t,
+                               const float* x, const float* xnext, int project_to_diagonal, void* stream) {
+  if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update arguments");
+  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
+  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  fh_ctx* c = s->ctx;
+  FH_LAUNCH(fh_k_su_diffs, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, x, xnext, mean_at_x, mean_at_xnext,
+            (float)(sigma_t * sigma_t), c->scratch[0], c->scratch[1], s->d, vec_ok(s->d));
+  FH_KCHECK();
+  return space_update_from_diffs(s, sigma_t, stream);
+}
+// The same update from float64 inputs (the reference's x and denoiser means are float64, generate_conditional.py:116):
+// dx = x' - x and de = sigma^2 (mu' - mu_hat) are DIFFERENCES of nearly equal images, so they are formed in float64 and
+// only then rounded to the float32 the state stores (forming them from float32-rounded inputs costs two to three digits).
+extern "C" int fh_space_update_f64(fh_state* s, const double* mean_at_x, const double* mean_at_xnext, double sigma_t,
+                                   const double* x, const double* xnext, int project_to_diagonal, void* stream) {
+  if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update_f64 arguments");
+  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
+  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  fh_ctx* c = s->ctx;
+  const long tot = (long)s->B * s->d;
+  FH_LAUNCH(fh_k_su_diffs64, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream, x, xnext, mean_at_x, mean_at_xnext, sigma_t * sigma_t,
+            c->scratch[0], c->scratch[1], tot);
+  FH_KCHECK();
+  return space_update_from_diffs(s, sigma_t, stream);
 }
 
 extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, const float* V, int kv, double sigma, void* stream) {
@@ -833,6 +873,26 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
     FH_CUDA(cudaMemcpy(o->runs, runs.data(), runs.size() * sizeof(int4), cudaMemcpyHostToDevice));
     FH_CUDA(cudaMemcpy(o->run_wf, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
     FH_CUDA(cudaMemcpy(o->run_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // float64 copy for the resident float64 solve: runs padded to a multiple of 6 taps (its window rotates in rounds of 6)
+    std::vector<int4> runs6; std::vector<double> wf6, wt6;
+    for (int b = 0; b < ks; ++b) {
+      int lo = -1, hi = -1;
+      for (int a = 0; a < ks; ++a) if (psf[a * ks + b] != 0.f) { if (lo < 0) lo = a; hi = a; }
+      if (lo < 0) continue;
+      const int L = hi - lo + 1, L6 = (L + 5) / 6 * 6;
+      runs6.push_back(make_int4(b - cen, lo - cen, L, (int)wf6.size()));
+      for (int k = 0; k < L6; ++k) {
+        wf6.push_back(k < L ? (double)psf[(hi - k) * ks + b] : 0.0);
+        wt6.push_back(k < L ? (double)psf[(lo + k) * ks + b] : 0.0);
+      }
+    }
+    o->nrun_taps6 = (int)wf6.size();
+    FH_CUDA(cudaMalloc((void**)&o->runs6, runs6.size() * sizeof(int4)));
+    FH_CUDA(cudaMalloc((void**)&o->run_wf6, wf6.size() * sizeof(double)));
+    FH_CUDA(cudaMalloc((void**)&o->run_wt6, wt6.size() * sizeof(double)));
+    FH_CUDA(cudaMemcpy(o->runs6, runs6.data(), runs6.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    FH_CUDA(cudaMemcpy(o->run_wf6, wf6.data(), wf6.size() * sizeof(double), cudaMemcpyHostToDevice));
+    FH_CUDA(cudaMemcpy(o->run_wt6, wt6.data(), wt6.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   // rank-1 test on the support box: psf == col (x) row exactly (to 1e-7 of the peak) -> separable path
   o->separable = false;
@@ -868,7 +928,7 @@ extern "C" int fh_op_create_conv(fh_ctx* c, fh_op** out, const float* psf, int k
 extern "C" int fh_op_destroy(fh_op* o) {
   if (!o) return FH_OK;
   cudaFree(o->t_dy); cudaFree(o->t_dx); cudaFree(o->t_w); cudaFree(o->kr); cudaFree(o->kc); cudaFree(o->psf_dense);
-  cudaFree(o->runs); cudaFree(o->run_wf); cudaFree(o->run_wt);
+  cudaFree(o->runs); cudaFree(o->run_wf); cudaFree(o->run_wt); cudaFree(o->runs6); cudaFree(o->run_wf6); cudaFree(o->run_wt6);
   free(o);
   return FH_OK;
 }
@@ -1010,9 +1070,14 @@ static int launch_resident(fh_ctx* c, const FhCgFused& P, FhCgResident R, cudaSt
 // One image at a time in ~18 us per iteration against ~38 us (B = 1) ... 14 us per image (B = 16) for the streaming
 // iteration that takes all images per launch: FH_CG_AUTO goes resident up to FH_RES_AUTO_MAX_BATCH images.
 #define FH_RES_AUTO_MAX_BATCH 4
-static bool resident_applies(const fh_state* s, const FhCgFused& P) {
+static FhR64Gen res64_gen(const fh_op* o, int m, int smem_room);
+// `o`: the operator (the float64 kernel also takes the non-separable ones through its gathers; the float32 kernel only
+// those that fold into the DCT passes, P.fuse != 0)
+static bool resident_applies(const fh_state* s, const FhCgFused& P, const fh_op* o = nullptr) {
   const fh_ctx* c = s->ctx;
-  if (!(c->res_ok && P.fuse != 0 && s->m <= FH_MAXM) || c->cg_mode == FH_CG_STREAMING) return false;
+  if (!c->res_ok || s->m > FH_MAXM || c->cg_mode == FH_CG_STREAMING) return false;
+  const bool f64 = c->cg_mode != FH_CG_RESIDENT_F32 && c->r64_ok;
+  if (P.fuse == 0 && !(f64 && o && res64_gen(o, 0, c->r64_smem_max - (int)sizeof(FhRes64Smem)).mode != 0)) return false;
   return c->cg_mode == FH_CG_RESIDENT || c->cg_mode == FH_CG_RESIDENT_F32 || s->B <= FH_RES_AUTO_MAX_BATCH;
 }
 // which resident kernel: float64 (the parity path; FH_CG_AUTO, FH_CG_RESIDENT) or the float32 one (FH_CG_RESIDENT_F32)
@@ -1066,15 +1131,50 @@ static int cg_solve_resident(fh_state* s, fh_op* o, FhCgFused P, const float* y,
 }
 
 // ---- float64 resident solve (fh_cg_res64.cuh) -------------------------------------------------------------------------
+// Shared memory the 2-D PSF gather needs for chunks of `cw` output columns.
+static size_t res64_conv_gbuf(const fh_op* o, int cw) {
+  const int th = FH_RES_ROWS + (o->ymax - o->ymin) + FH_RES_ROWS, tws = (cw + (o->xmax - o->xmin) + 2) & ~1;
+  const size_t bytes = ((size_t)th * tws + (size_t)(FH_PASS_THREADS / cw - 1) * FH_RES_ROWS * cw + ((o->nrun_taps6 + 1) & ~1)) * sizeof(double) +
+                       (size_t)o->nruns * sizeof(int4);
+  return (bytes + 15) & ~(size_t)15;
+}
+// The non-separable operators' description for the float64 kernel at rank m (mode 0 when the operator folds into the DCT
+// passes or has no gathers here: the caller then falls back to the streaming float32 iteration).  The 2-D PSF gather
+// trades shared memory against L2 round trips: one chunk = one round trip (~2 us), and every 6 KB given to it is a row of
+// Z that has to be re-read from L2 in every iteration (~0.7 us per row, measured) -- the chunk width minimising the sum.
+static FhR64Gen res64_gen(const fh_op* o, int m = 0, int smem_room = 180 * 1024) {
+  FhR64Gen G{};
+  if (!o) return G;
+  const fh_ctx* c = o->ctx;
+  if (o->kind == FH_OP_BLUR && !o->separable && o->nruns > 0 && o->nruns <= 64 && o->nrun_taps <= 2048) {
+    double best = 1e30;
+    for (int cw = 256; cw >= 32; cw >>= 1) {
+      const size_t bytes = res64_conv_gbuf(o, cw);
+      if ((long)bytes > (long)smem_room) continue;
+      const int cap = std::min(FH_RES_MAXM, (int)((smem_room - (long)bytes) / (FH_RES_SLICE * 4)));
+      const int nch = FH_N / cw;
+      const double cost = 2.0 * (4.5 + nch * 2.2) + 0.7 * std::max(0, m - cap);
+      if (cost < best) { best = cost; G.cw = cw; G.gbuf_bytes = (int)bytes; }
+    }
+    if (G.cw) {
+      G.mode = 3; G.runs = o->runs6; G.w_fwd = o->run_wf6; G.w_tr = o->run_wt6; G.nruns = o->nruns; G.ntaps = o->nrun_taps6;
+      G.ymin = o->ymin; G.ymax = o->ymax; G.xmin = o->xmin; G.xmax = o->xmax;
+    }
+  } else if (o->kind == FH_OP_SR && c->H == 256 && c->W == 256 && o->sf == 4 && o->ks <= FH_SR_KS && ((o->ks / 2) & 3) == 0) {
+    G.mode = 4; G.psf = o->psf_dense; G.ks = o->ks;
+    G.gbuf_bytes = (int)(((size_t)(FH_SR_KS * FH_R64_SRP + 10 * 64 + 128 + 2 * FH_SR_KS * (64 + 24)) * sizeof(double) + 15) & ~(size_t)15);
+  }
+  return G;
+}
+
 static int launch_res64(fh_ctx* c, const FhCgFused& P, FhCgRes64 R, cudaStream_t st) {
-  const dim3 grid((unsigned)P.strips_per_image), block(FH_PASS_THREADS);
+  const dim3 grid((unsigned)(c->C * FH_R64_CPP)), block(FH_PASS_THREADS);
   const size_t nblk = grid.x, half = (size_t)c->d / 2;
   R.T[0] = c->r64_T[0]; R.T[1] = c->r64_T[1];
   R.ride[0] = c->r64_ride[0]; R.ride[1] = c->r64_ride[1];
   R.ll_dots = c->res_ll + 2 * half;
   R.ll_sum = R.ll_dots + FH_MAXM * nblk;
   R.tw = c->tw64; R.e512 = c->e512;
-  R.mr_cap = c->r64_cap;
   const unsigned need = (unsigned)P.last_allowed + 3u;
   if (c->res_seq > 0xffffffffu - need - 1u) {
     FH_CUDA(cudaMemsetAsync(c->res_ll, 0, c->res_ll_bytes, st));
@@ -1084,11 +1184,18 @@ static int launch_res64(fh_ctx* c, const FhCgFused& P, FhCgRes64 R, cudaStream_t
   c->res_seq += need;
   R.grid_counter = c->grid_counter + R.image;
   FH_CUDA(cudaMemsetAsync(R.grid_counter, 0, sizeof(unsigned), st));
-  // three instantiations: tables in shared memory while the rank leaves room for them, through L1 above that, and the
-  // partially resident one above the resident capacity
-  const bool tabs = P.m <= c->r64_cap_tabs;
-  const bool big = !tabs && P.m > c->r64_cap;
-  const size_t smem = sizeof(FhRes64Smem) + (tabs ? sizeof(FhRes64Tabs) : 0) + (size_t)std::min(P.m, c->r64_cap) * FH_RES_SLICE * sizeof(float);
+  // Shared memory: fixed part, [twiddle tables], [gather staging of a non-separable operator], resident rows of Z.
+  // Three instantiations: tables in shared memory while the rank leaves room for them, through L1 above that, and the
+  // partially resident one above the capacity.
+  const int slice = FH_RES_SLICE * (int)sizeof(float);
+  const int room = c->r64_smem_max - (int)sizeof(FhRes64Smem) - R.gen.gbuf_bytes;
+  const int cap = std::max(0, std::min(FH_RES_MAXM, room / slice));
+  const int cap_tabs = std::max(-1, std::min(FH_RES_MAXM, (room - (int)sizeof(FhRes64Tabs)) / slice));
+  if (room < 0) FH_FAIL(FH_EINVAL, "operator staging does not fit the float64 kernel's shared memory");
+  const bool tabs = P.m <= cap_tabs;
+  const bool big = !tabs && P.m > cap;
+  R.mr_cap = cap;
+  const size_t smem = sizeof(FhRes64Smem) + (tabs ? sizeof(FhRes64Tabs) : 0) + (size_t)R.gen.gbuf_bytes + (size_t)std::min(P.m, cap) * slice;
 #ifdef FH_EMU
   (void)st;
   if (tabs) emu::launch_coop([&] { fh_k_cg_res64<false, true>(P, R); }, grid, block, smem);
@@ -1143,7 +1250,7 @@ static int cg_solve_res64(fh_state* s, fh_op* o, FhCgFused P, const double* y, c
   fh_ctx* c = s->ctx;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = s->B;
-  const long n = s->d;
+  const long n = op_ylen(o);                             // measurement space: d, or d / 16 for x4 super-resolution
   const long hw = (long)c->H * c->W;
   double *bv = c->d64[0], *x = c->d64[1], *amu = c->d64[2];
   int rc;
@@ -1155,13 +1262,15 @@ static int cg_solve_res64(fh_state* s, fh_op* o, FhCgFused P, const double* y, c
   FH_LAUNCH(fh_k_rhs64, dim3((unsigned)((n + 255) / 256), B), dim3(256), 0, stream, y, a, P.mask, P.mask_batch, hw, bv, n);
   FH_KCHECK();
   FH_CUDA(cudaMemsetAsync(c->cg_sc, 0, (size_t)B * sizeof(FhCgScalars), st));
-  P.strips_per_image = (int)(s->d / FH_RES_SLICE);
+  P.strips_per_image = c->C * FH_R64_CPP;
   P.ystrips = P.strips_per_image;
   P.last_allowed = last;
   P.mirror = nullptr;
+  const FhR64Gen gen = res64_gen(o, s->m, c->r64_smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs));
   double* xout = (o->kind == FH_OP_INPAINT) ? mat_out : x;
   for (int b = 0; b < B; ++b) {
     FhCgRes64 R{};
+    R.gen = gen;
     R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n;
     R.rtol = rtol; R.atol = 0.0; R.sy2 = sigma_y2; R.use_stop = use_stop; R.image = b;
     R.info_out = info_dev ? info_dev + b : nullptr;
@@ -1190,7 +1299,7 @@ extern "C" int fh_cov_dot_f64(fh_state* s, const double* v, double* out, void* s
   cudaStream_t st = (cudaStream_t)stream;
   FhCgFused P = fused_params(s, nullptr, 8);
   P.sc = c->cg_sc; P.sy2 = 0.f;
-  P.strips_per_image = (int)(s->d / FH_RES_SLICE);
+  P.strips_per_image = c->C * FH_R64_CPP;
   P.ystrips = P.strips_per_image;
   P.last_allowed = 1;
   P.mirror = nullptr;
@@ -1244,7 +1353,7 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
   const int use_stop = fixed_iters > 0 ? 0 : 1;
   const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
   P.last_allowed = last;
-  if (resident_applies(s, P)) {
+  if (resident_applies(s, P, o)) {
     if (resident_is_f64(c)) {
       c->cg_last_mode = FH_CG_RESIDENT;
       return cg_solve_res64_f32io(s, o, P, y, mu, sigma_y2, rtol, last, use_stop, mat_out, niter_host, optimal_host, resid_host, stream, nullptr);
@@ -1358,7 +1467,7 @@ extern "C" int fh_cg_solve_async(fh_state* s, fh_op* o, const float* y, const fl
   if (s->basis != FH_BASIS_DCT) FH_FAIL(FH_ESTATE, "asynchronous solve needs the DCT basis");
   fh_ctx* c = s->ctx;
   FhCgFused P = fused_params(s, o, 8);
-  if (!resident_applies(s, P)) FH_FAIL(FH_ESTATE, "asynchronous solve needs the resident kernel (rank %d, operator kind %d)", s->m, o->kind);
+  if (!resident_applies(s, P, o)) FH_FAIL(FH_ESTATE, "asynchronous solve needs the resident kernel (rank %d, operator kind %d)", s->m, o->kind);
   P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
   const int use_stop = fixed_iters > 0 ? 0 : 1;
   const int last = fixed_iters > 0 ? std::min(fixed_iters, maxiter) : maxiter;
@@ -1382,7 +1491,7 @@ static int solve_f64_common(fh_state* s, fh_op* o, const double* y, const double
   if (o->kind == FH_OP_INPAINT && o->mask_batch != 1 && o->mask_batch != s->B) FH_FAIL(FH_EINVAL, "mask batch %d does not match the state's batch %d", o->mask_batch, s->B);
   fh_ctx* c = s->ctx;
   FhCgFused P = fused_params(s, o, 8);
-  if (!resident_applies(s, P) || !resident_is_f64(c))
+  if (!resident_applies(s, P, o) || !resident_is_f64(c))
     FH_FAIL(FH_ESTATE, "float64 solve needs the resident float64 kernel (rank %d, operator kind %d, cg mode %d)", s->m, o->kind, c->cg_mode);
   P.sc = c->cg_sc; P.sy2 = (float)sigma_y2;
   const int use_stop = fixed_iters > 0 ? 0 : 1;
@@ -1535,7 +1644,7 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   FhCgFused P = fused_params(s, o, 8);
   const int saved_mode = c->cg_mode;
   c->cg_mode = FH_CG_AUTO;
-  const bool ok = resident_applies(s, P);
+  const bool ok = resident_applies(s, P, o);
   c->cg_mode = saved_mode;
   if (!ok) FH_FAIL(FH_EINVAL, "resident kernel does not apply to this state / operator");
   P.sc = c->cg_sc; P.sy2 = 0.01f; P.last_allowed = iters;
@@ -1547,6 +1656,7 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   FhCgRes64 R64{};
   R64.bvec = c->d64[0]; R64.x_out = c->d64[1]; R64.rtol = 1.0; R64.atol = 0.0; R64.sy2 = 0.01; R64.use_stop = 0; R64.image = 0;
   R64.timing = 1;
+  R64.gen = res64_gen(o, s->m, c->r64_smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs));
   cudaEvent_t e0, e1;
   FH_CUDA(cudaEventCreate(&e0)); FH_CUDA(cudaEventCreate(&e1));
   int rc = FH_OK;

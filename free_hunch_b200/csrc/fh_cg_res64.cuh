@@ -33,6 +33,11 @@
 // convolution (lanes 64 B apart) fall on distinct bank groups (unpadded: 4-way conflicts, ncu: 35 % excess wavefronts)
 #define FH_R64_POS(c) ((c) + (((c) >> 3) << 1))
 #define FH_R64_TW 252                                // stage twiddles: Ns = 4 (3 x 4), 16 (3 x 16), 64 (3 x 64)
+// Strips never straddle a channel plane here (unlike the float32 kernel's 128 x 6 rows): every plane is cut into 42 strips
+// of 6 rows and one of 4, i.e. 43 CTAs per plane, 129 for an RGB image.  The gathers of the non-separable operators
+// (halo rows wrap around inside ONE plane) would otherwise need two segments in the two straddling CTAs, which the whole
+// grid would wait for at the next barrier.
+#define FH_R64_CPP ((FH_N + FH_RES_ROWS - 1) / FH_RES_ROWS)          // CTAs per plane (43)
 
 struct FhRes64Smem {
   double2 X[FH_RES_ROWS / 2][FH_R64_LD];             // FFT ping-pong; X doubles as the strip's input rows, Y as its output
@@ -58,6 +63,16 @@ struct FhRes64Scratch {                              // lives in Y while no tran
 static_assert(sizeof(FhRes64Scratch) <= sizeof(double2) * (FH_RES_ROWS / 2) * FH_R64_LD, "scratch must fit the FFT buffer");
 static_assert(FH_RES_ROWS * FH_R64_RS * sizeof(double) <= sizeof(double2) * (FH_RES_ROWS / 2) * FH_R64_LD, "rows must fit the FFT buffer");
 
+struct FhR64Gen {
+  int mode;                       // 0: none (mask / separable blur / plain), 3: dense 2-D PSF as column runs, 4: x4 super-resolution
+  // mode 3: the PSF as one dense vertical run per column (fh_op: fh_k_conv_runs), weights in window order per direction
+  const int4* runs; const double* w_fwd; const double* w_tr; int nruns, ntaps, ymin, ymax, xmin, xmax;   // runs / weights padded to 6 taps
+  int cw;                         // output columns per staging chunk (256, 128, 64 or 32)
+  // mode 4: dense ks x ks PSF (row-major), centre ks / 2 (a multiple of 4), 256 x 256 planes, 64 x 64 measurements
+  const float* psf; int ks;
+  int gbuf_bytes;                 // shared-memory staging area the mode needs (between the tables and the Z rows)
+};
+
 struct FhCgRes64 {
   const double* bvec;          // (d) right-hand side b (pixel layout); x0 = b
   double* x_out;               // (d) solution
@@ -69,6 +84,7 @@ struct FhCgRes64 {
   unsigned seq_base;
   double rtol, atol, sy2;
   int use_stop, image, timing;
+  FhR64Gen gen;                // non-separable operator (mode 0: none)
   int apply_only;              // 1: no solve -- x_out = Sigma bvec (one pass of the loop without operator, fh_cov_dot_f64)
   int mr_cap;                  // rows of Z that fit in shared memory
   FhCgInfo* info_out;
@@ -112,10 +128,10 @@ __device__ __forceinline__ void fh_fft256_stage64(const double2* __restrict__ in
 // algorithm, aliasing rules and barrier contract as fh_dct_strip_core (fh_dct.cuh): `in` may alias Xb, `out` may alias Yb.
 template <bool INV, bool TABS>
 __device__ __forceinline__ void fh_dct64_core(const double* in, double* out, double2 (*Xb)[FH_R64_LD], double2 (*Yb)[FH_R64_LD],
-                                              const double2* __restrict__ tw, const double2* __restrict__ e512) {
+                                              const double2* __restrict__ tw, const double2* __restrict__ e512, int npair) {
   constexpr int SIGN = INV ? +1 : -1;
   const int f = threadIdx.x >> 6, j = threadIdx.x & 63;
-  const bool act = f < FH_RES_ROWS / 2;
+  const bool act = f < npair;
   const int fc = act ? f : 0;
   const double* ra = in + (2 * fc) * FH_R64_RS;
   const double* rb = ra + FH_R64_RS;
@@ -192,11 +208,12 @@ __device__ __forceinline__ void fh_r64_put(double* sm_rows, const double (&r)[FH
     *reinterpret_cast<double2*>(sm_rows + (e >> 8) * FH_R64_RS + FH_R64_POS(e & 255)) = make_double2(r[2 * h], r[2 * h + 1]);
   }
 }
-__device__ __forceinline__ void fh_r64_get(const double* sm_rows, double (&r)[FH_RES_ROWS]) {
+__device__ __forceinline__ void fh_r64_get(const double* sm_rows, double (&r)[FH_RES_ROWS], int npair) {
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
     const int e = 2 * (threadIdx.x + FH_PASS_THREADS * h);
-    const double2 v = *reinterpret_cast<const double2*>(sm_rows + (e >> 8) * FH_R64_RS + FH_R64_POS(e & 255));
+    double2 v = make_double2(0.0, 0.0);
+    if (h < npair) v = *reinterpret_cast<const double2*>(sm_rows + (e >> 8) * FH_R64_RS + FH_R64_POS(e & 255));
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
   }
 }
@@ -209,35 +226,54 @@ __device__ __forceinline__ double2 fh_ld_cg_d2(const double2* p) {
   return v;
 #endif
 }
-__device__ __forceinline__ void fh_r64_load_plane(const double* src, double (&r)[FH_RES_ROWS]) {
+__device__ __forceinline__ void fh_r64_load_plane(const double* src, double (&r)[FH_RES_ROWS], int npair) {
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-    const double2 v = fh_ld_cg_d2(reinterpret_cast<const double2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+    double2 v = make_double2(0.0, 0.0);
+    if (h < npair) v = fh_ld_cg_d2(reinterpret_cast<const double2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
   }
 }
-__device__ __forceinline__ void fh_r64_load(const double* __restrict__ src, double (&r)[FH_RES_ROWS]) {
+__device__ __forceinline__ void fh_r64_load(const double* __restrict__ src, double (&r)[FH_RES_ROWS], int npair) {
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-    const double2 v = reinterpret_cast<const double2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+    double2 v = make_double2(0.0, 0.0);
+    if (h < npair) v = reinterpret_cast<const double2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
   }
 }
-// transposed store of strip s into the exchange plane: element (global row g, column k) -> row (plane(g), k), column g & 255
-__device__ __forceinline__ void fh_r64_store_t(const double* sm_rows, double* __restrict__ T, int s) {
+__device__ __forceinline__ void fh_r64_store(double* dst, const double (&r)[FH_RES_ROWS], int npair) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h)
+    if (h < npair) reinterpret_cast<double2*>(dst)[threadIdx.x + FH_PASS_THREADS * h] = make_double2(r[2 * h], r[2 * h + 1]);
+}
+// float32 strip operands (delta, Z slices): float2 #t, #t+256, #t+512, zero beyond the strip's rows
+__device__ __forceinline__ void fh_r64_getf(const float* src, float (&r)[FH_RES_ROWS], int npair) {
+#pragma unroll
+  for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+    float2 v = make_float2(0.f, 0.f);
+    if (h < npair) v = reinterpret_cast<const float2*>(src)[threadIdx.x + FH_PASS_THREADS * h];
+    r[2 * h] = v.x; r[2 * h + 1] = v.y;
+  }
+}
+// transposed store of the strip starting at global row grow0 into the exchange plane: element (global row g, column k)
+// -> row (plane(g), k), column g & 255
+__device__ __forceinline__ void fh_r64_store_t(const double* sm_rows, double* __restrict__ T, int grow0, int npair) {
   const int k = threadIdx.x;
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-    const int g = FH_RES_ROWS * s + 2 * h;
-    double* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
-    *reinterpret_cast<double2*>(d) = make_double2(sm_rows[(2 * h) * FH_R64_RS + FH_R64_POS(k)], sm_rows[(2 * h + 1) * FH_R64_RS + FH_R64_POS(k)]);
+    if (h < npair) {
+      const int g = grow0 + 2 * h;
+      double* d = T + (size_t)(g >> 8) * FH_N * FH_N + (size_t)k * FH_N + (g & (FH_N - 1));
+      *reinterpret_cast<double2*>(d) = make_double2(sm_rows[(2 * h) * FH_R64_RS + FH_R64_POS(k)], sm_rows[(2 * h + 1) * FH_R64_RS + FH_R64_POS(k)]);
+    }
   }
 }
 
 // In-place circular correlation along the 6 rows, float64 (register window, 8 outputs per thread, warps 0..5 active).
-__device__ __forceinline__ void fh_r64_conv(double* sm_rows, const double* __restrict__ taps, int n4, int c4) {
+__device__ __forceinline__ void fh_r64_conv(double* sm_rows, const double* __restrict__ taps, int n4, int c4, int nrows) {
   const int row = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const bool act = row < FH_RES_ROWS;
+  const bool act = row < nrows;
   double acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.0;
@@ -287,10 +323,11 @@ __device__ __forceinline__ int fh_r64_stage_taps(double* s_taps, const float* __
   return (n4 << 8) | (cen + sh);
 }
 // the thread's 6 elements of a Z row slice that is not resident: from L2, past L1 (L1 is left to the twiddle tables)
-__device__ __forceinline__ void fh_r64_get_z_l2(const float* src, float (&r)[FH_RES_ROWS]) {
+__device__ __forceinline__ void fh_r64_get_z_l2(const float* src, float (&r)[FH_RES_ROWS], int npair) {
 #pragma unroll
   for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-    const float2 v = fh_ld_cg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
+    float2 v = make_float2(0.f, 0.f);
+    if (h < npair) v = fh_ld_cg(reinterpret_cast<const float2*>(src) + threadIdx.x + FH_PASS_THREADS * h);
     r[2 * h] = v.x; r[2 * h + 1] = v.y;
   }
 }
@@ -338,8 +375,199 @@ __device__ __forceinline__ double fh_widen_alu(float f) {
 }
 #define FH_WIDEN(z, e) (((e) & 1) ? fh_widen_alu(z) : (double)(z))
 
-// grid = C*256/6 CTAs (cooperative), block = 256, dynamic shared memory = sizeof(FhRes64Smem) + min(m, mr_cap) * 6 KB.
-// BIG = false: every row of Z resident (m <= mr_cap and m <= 32).  BIG = true: rows >= mr_cap are re-read from L2.
+// ---- non-separable operators (2-D PSF, x4 super-resolution): gathers through L2 --------------------------------------
+// A CTA owns rows [grow0, grow0 + nrows) of one plane.  A^T r and A t need rows of OTHER CTAs, so the operand is first
+// published to global memory (it stays in L2), the grid synchronises, and every CTA gathers its halo back into shared
+// memory.  Two extra grid barriers per iteration compared with the mask / separable blur, which fold into the DCT passes.
+#define FH_R64_SRP 28             // padded PSF row length of the x4 SR gathers (25 taps + 3 zeros: b0 + 4 t never leaves the row)
+
+// 16-byte asynchronous copies global -> shared past L1 (the published planes are rewritten every iteration by other CTAs:
+// an L1-allocating load could return last iteration's line), grouped so that the NEXT chunk's halo is in flight while
+// the current one is being convolved.
+#ifdef FH_EMU
+static inline void fh_cp16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+static inline void fh_cp_commit() {}
+template <int N> static inline void fh_cp_wait() {}
+#else
+__device__ __forceinline__ void fh_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fh_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fh_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fh_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+// tile[r][0 .. 2 npc) <- plane[(gi0 + r) & 255][(gj0 + ..) & 255], gj0 even; row stride tws (even).  Issues copies only.
+__device__ __forceinline__ void fh_r64_stage_tile(double* tile, int tws, const double* plane, int gi0, int gj0, int th, int npc) {
+  for (int idx = threadIdx.x; idx < th * npc; idx += FH_PASS_THREADS) {
+    const int rr = idx / npc, pc = idx - rr * npc;
+    fh_cp16(tile + rr * tws + 2 * pc, plane + (size_t)((gi0 + rr) & (FH_N - 1)) * FH_N + ((gj0 + 2 * pc) & (FH_N - 1)));
+  }
+}
+
+// mode 3: out rows (shared, staged-row layout) = A src (transpose = 0) or A^T src (transpose = 1) for this CTA's rows;
+// src is a published (C, 256, 256) float64 image.  The halo is staged in chunks of G.cw output columns (256, 128, 64 or
+// 32: the host gives the gather as much shared memory as the rank leaves, because a chunk is one L2 round trip -- ~2 us
+// from a plane other SMs have just written -- and the bytes in flight are what hides it).  Thread = (output column of
+// the chunk, run group): a group owns a subset of the PSF's column runs, every thread slides a 6-row window down its
+// image column (one shared load per tap for 6 FMAs); the groups' partial sums meet in shared memory in a fixed order.
+// Contains __syncthreads; all 256 threads.
+__device__ __forceinline__ void fh_r64_gather_conv(const double* src, double* out_rows, unsigned char* gbuf, const FhR64Gen& G,
+                                                   int pl, int row0, int transpose) {
+  const int tid = threadIdx.x;
+  const int cw = G.cw, ngrp = FH_PASS_THREADS / cw;
+  const int oy0 = transpose ? G.ymin : -G.ymax, oy1 = transpose ? G.ymax : -G.ymin;
+  const int ox0 = transpose ? G.xmin : -G.xmax, ox1 = transpose ? G.xmax : -G.xmin;
+  const int th = FH_RES_ROWS + (oy1 - oy0) + FH_RES_ROWS;                  // + 6: the zero-weight taps that pad a run to a multiple of 6 read on
+  const int tws = (cw + (ox1 - ox0) + 2) & ~1, npc = tws / 2;              // one spare column: the even-aligned origin may sit one left
+  double* tile = reinterpret_cast<double*>(gbuf);                          // [th][tws]
+  double* red = tile + (size_t)th * tws;                                   // [ngrp - 1][6][cw] partial sums of run groups 1..
+  double* wts = red + (size_t)(ngrp - 1) * FH_RES_ROWS * cw;               // weights of this direction, widened, every run padded to a multiple of 6
+  int4* srun = reinterpret_cast<int4*>(wts + ((G.ntaps + 1) & ~1));   // [nruns] (tile row of the window start, tile column offset, L6, woff6)
+  const double* plane = src + (size_t)pl * FH_N * FH_N;
+  const int sh = (ox0 & 1);                                                // chunk origins j0 are even: parity of the first column
+  __syncthreads();                                                         // gbuf may still be in use by the previous gather
+  fh_r64_stage_tile(tile, tws, plane, row0 + oy0, ox0 - sh, th, npc);
+  fh_cp_commit();
+  const double* wsrc = transpose ? G.w_tr : G.w_fwd;
+  for (int t = tid; t < G.ntaps; t += FH_PASS_THREADS) wts[t] = wsrc[t];
+  for (int t = tid; t < G.nruns; t += FH_PASS_THREADS) {
+    const int4 r = G.runs[t];                                              // (dx, dy0, L, offset of the padded weights)
+    const int L6 = (r.z + FH_RES_ROWS - 1) / FH_RES_ROWS * FH_RES_ROWS;
+    srun[t] = make_int4(transpose ? (r.y - oy0) : (-r.y - (r.z - 1) - oy0), (transpose ? r.x : -r.x) - ox0 + sh, L6, r.w);
+  }
+  const int jc = tid % cw, grp = tid / cw;
+  for (int j0 = 0; j0 < FH_N; j0 += cw) {
+    fh_cp_wait<0>();
+    __syncthreads();
+    double acc[FH_RES_ROWS];
+#pragma unroll
+    for (int e = 0; e < FH_RES_ROWS; ++e) acc[e] = 0.0;
+    for (int t = grp; t < G.nruns; t += ngrp) {
+      const int4 r = srun[t];
+      const double* q = tile + r.x * tws + r.y + jc;
+      const double* w = wts + r.w;
+      double win[FH_RES_ROWS];
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) win[e] = q[e * tws];
+      q += FH_RES_ROWS * tws;
+      // Six taps per round with a compile-time rotation of the window: before tap k slot j holds the input row congruent
+      // to j (mod 6) among rows k .. k+5, so output e reads slot (e + k) % 6 and the dead slot k % 6 takes row k + 6.
+      for (int k0 = 0; k0 < r.z; k0 += FH_RES_ROWS) {
+#pragma unroll
+        for (int kk = 0; kk < FH_RES_ROWS; ++kk) {
+          const double wv = w[k0 + kk];
+#pragma unroll
+          for (int e = 0; e < FH_RES_ROWS; ++e) acc[e] = fma(wv, win[(e + kk) % FH_RES_ROWS], acc[e]);
+          win[kk] = q[(k0 + kk) * tws];
+        }
+      }
+    }
+    if (grp > 0) {
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) red[((size_t)(grp - 1) * FH_RES_ROWS + e) * cw + jc] = acc[e];
+    }
+    __syncthreads();                                                       // tile fully read, partials visible
+    if (j0 + cw < FH_N) {                                                  // next chunk's halo flies while group 0 finishes this one
+      fh_r64_stage_tile(tile, tws, plane, row0 + oy0, j0 + cw + ox0 - sh, th, npc);
+      fh_cp_commit();
+    }
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) {
+        double v = acc[e];
+        for (int g = 0; g < ngrp - 1; ++g) v += red[((size_t)g * FH_RES_ROWS + e) * cw + jc];
+        out_rows[e * FH_R64_RS + FH_R64_POS(j0 + jc)] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// mode 4: PSF widened into shared memory, rows padded to FH_R64_SRP.  Caller syncs.
+__device__ __forceinline__ void fh_r64_sr_stage_psf(double* spsf, const FhR64Gen& G) {
+  for (int i = threadIdx.x; i < FH_SR_KS * FH_R64_SRP; i += FH_PASS_THREADS) {
+    const int a = i / FH_R64_SRP, b = i - a * FH_R64_SRP;
+    spsf[i] = (a < G.ks && b < G.ks) ? (double)G.psf[a * G.ks + b] : 0.0;
+  }
+}
+// mode 4, A^T: out rows = k (*)^T (zero insertion of the published 64 x 64 measurement plane `pl` of ysrc)   (utils_sisr.py:44-52)
+//   x[i][j] = sum over taps with (i + a - c) % 4 == 0 and (j + b - c) % 4 == 0 of k[a][b] y[((i + a - c) & 255) / 4][((j + b - c) & 255) / 4]
+__device__ __forceinline__ void fh_r64_sr_gather_at(const double* ysrc, double* out_rows, unsigned char* gbuf, const FhR64Gen& G,
+                                                    int pl, int row0, int nrows) {
+  const int tid = threadIdx.x;
+  const int c = G.ks / 2;
+  double* spsf = reinterpret_cast<double*>(gbuf);
+  double* ys = spsf + FH_SR_KS * FH_R64_SRP;                               // [10][64] measurement rows this strip touches
+  const int Ilo = (row0 - c) >> 2;                                         // floor
+  const int nI = ((row0 + FH_RES_ROWS - 1 + (G.ks - 1 - c)) >> 2) - Ilo + 1;    // <= 10
+  const double* yp = ysrc + (size_t)pl * (FH_N / 4) * (FH_N / 4);
+  __syncthreads();
+  for (int idx = tid; idx < nI * 64; idx += FH_PASS_THREADS)
+    ys[idx] = fh_ldcg(yp + (size_t)((Ilo + (idx >> 6)) & 63) * 64 + (idx & 63));
+  __syncthreads();
+  const int j = tid;
+  const int b0 = (4 - ((j - c) & 3)) & 3;
+  int qt[7];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) qt[t] = ((j + b0 + 4 * t - c) >> 2) & 63;
+  for (int e = 0; e < nrows; ++e) {
+    const int i = row0 + e;
+    const int a0 = (4 - ((i - c) & 3)) & 3;
+    double acc = 0.0;
+    for (int a = a0; a < G.ks; a += 4) {
+      const double* yr = ys + (size_t)(((i + a - c) >> 2) - Ilo) * 64;
+      const double* kr = spsf + a * FH_R64_SRP + b0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) acc = fma(kr[4 * t], yr[qt[t]], acc);    // taps beyond ks are zero
+    }
+    out_rows[e * FH_R64_RS + FH_R64_POS(j)] = acc;
+  }
+  __syncthreads();
+}
+// mode 4, A: the CTA's own measurement rows [yr0, yr0 + nyr) of plane pl from the published image tsrc   (utils_sisr.py:55-61)
+//   y[I][J] = sum_{a,b} k[a][b] t[(4 I - a + c) & 255][(4 J - b + c) & 255];  thread t < 64 nyr gets element (yr0 + t / 64, t % 64)
+// 16 measurement columns per step: their 25 x 88 image window is staged (double-buffered), 16 threads share an element.
+__device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigned char* gbuf, const FhR64Gen& G, int pl, int yr0, int nyr) {
+  const int tid = threadIdx.x;
+  const int c = G.ks / 2;
+  double* spsf = reinterpret_cast<double*>(gbuf);
+  double* qy = spsf + FH_SR_KS * FH_R64_SRP + 10 * 64;                     // [2][64] results
+  constexpr int TW = 64 + 2 * 12, NPC = TW / 2;
+  double* tile0 = qy + 128;                                                // [2][25][88] image windows
+  const double* plane = tsrc + (size_t)pl * FH_N * FH_N;
+  const int el = tid >> 4, part = tid & 15;
+  const int nstep = 4 * nyr;
+  __syncthreads();
+  fh_r64_stage_tile(tile0, TW, plane, 4 * yr0 - c, -c, FH_SR_KS, NPC);
+  fh_cp_commit();
+  for (int st = 0; st < nstep; ++st) {
+    const int yr = st >> 2, ch = st & 3;
+    double* tile = tile0 + (size_t)(st & 1) * FH_SR_KS * TW;
+    if (st + 1 < nstep) {
+      const int yr1 = (st + 1) >> 2, ch1 = (st + 1) & 3;
+      fh_r64_stage_tile(tile0 + (size_t)((st + 1) & 1) * FH_SR_KS * TW, TW, plane, 4 * (yr0 + yr1) - c, 64 * ch1 - c, FH_SR_KS, NPC);
+      fh_cp_commit();
+      fh_cp_wait<1>();
+    } else {
+      fh_cp_wait<0>();
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int q = part; q < G.ks * G.ks; q += 16) {
+      const int a = q / G.ks, b = q - a * G.ks;
+      acc = fma(spsf[a * FH_R64_SRP + b], tile[(2 * c - a) * TW + 4 * el + 2 * c - b], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (part == 0) qy[yr * 64 + 16 * ch + el] = acc;
+    __syncthreads();                                                       // the window is restaged two steps later
+  }
+  return tid < 64 * nyr ? qy[tid] : 0.0;
+}
+
+// grid = 43 CTAs per plane (cooperative), block = 256, dynamic shared memory = FhRes64Smem [+ tables] [+ gather staging]
+// + min(m, mr_cap) * 6 KB.  BIG = false: every row of Z resident.  BIG = true: rows >= mr_cap are re-read from L2.
 // TABS = true: twiddle tables in shared memory (costs two rows of Z); false: read through L1.
 template <bool BIG, bool TABS>
 __global__ void __launch_bounds__(FH_PASS_THREADS, 1)
@@ -348,7 +576,8 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
   FhRes64Smem& sm = *reinterpret_cast<FhRes64Smem*>(smem_raw);
   FhRes64Scratch& sc = *reinterpret_cast<FhRes64Scratch*>(sm.Y);
   FhRes64Tabs* tabs = reinterpret_cast<FhRes64Tabs*>(smem_raw + sizeof(FhRes64Smem));
-  float* Zs = reinterpret_cast<float*>(smem_raw + sizeof(FhRes64Smem) + (TABS ? sizeof(FhRes64Tabs) : 0));
+  unsigned char* gbuf = smem_raw + sizeof(FhRes64Smem) + (TABS ? sizeof(FhRes64Tabs) : 0);
+  float* Zs = reinterpret_cast<float*>(gbuf + R.gen.gbuf_bytes);
   const double2* tw = TABS ? tabs->tw : R.tw;
   const double2* e512 = TABS ? tabs->e512 : R.e512;
   double* rows_a = reinterpret_cast<double*>(sm.X);
@@ -358,44 +587,46 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
   const unsigned nblk = gridDim.x;
   const int m = P.m;
   const int mr = BIG ? min(m, R.mr_cap) : m;
-  const long d = (long)nblk * FH_RES_SLICE;
+  // geometry: CTA cc of plane pl owns rows [6 cc, 6 cc + nrows) of that plane, in the pixel AND in the basis layout
+  const int pl = s / FH_R64_CPP, cc = s - pl * FH_R64_CPP;
+  const int prow0 = cc * FH_RES_ROWS;                                       // first row inside the plane
+  const int nrows = min(FH_RES_ROWS, FH_N - prow0), npair = nrows >> 1;
+  const int grow0 = pl * FH_N + prow0;
+  const long d = (long)P.C * FH_N * FH_N;
   const size_t img = (size_t)R.image * d;
-  const size_t soff = (size_t)s * FH_RES_SLICE;
+  const size_t soff = (size_t)grow0 * FH_N;
+  const int fuse = R.gen.mode ? R.gen.mode : P.fuse;
+  // measurement-space ownership: the strip itself, except x4 super-resolution (64 x 64 planes: 1 or 2 rows per CTA)
+  const int yr0 = (cc * (FH_N / 4)) / FH_R64_CPP, nyr = ((cc + 1) * (FH_N / 4)) / FH_R64_CPP - yr0;
+  const size_t yoff = (size_t)pl * (FH_N / 4) * (FH_N / 4) + (size_t)yr0 * (FH_N / 4);       // fuse == 4 only
+  const bool yown = tid < 64 * nyr;
 
   // ---- prologue ----
   if (tid == 0) { fh_mbar_init(&sm.bar, 1); fh_mbar_fence_init(); }
   __syncthreads();
   const float* zsrc = P.Z + (size_t)R.image * FH_MAXM * d + soff;
   if (mr > 0 && warp == 0) {
-    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)mr * FH_RES_SLICE * 4u);
+    if (lane == 0) fh_mbar_expect_tx(&sm.bar, (unsigned)mr * (unsigned)nrows * FH_N * 4u);
     __syncwarp();
-    for (int i = lane; i < mr; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, FH_RES_SLICE * 4u, &sm.bar);
+    for (int i = lane; i < mr; i += 32) fh_tma_load_1d(Zs + (size_t)i * FH_RES_SLICE, zsrc + (size_t)i * d, (unsigned)nrows * FH_N * 4u, &sm.bar);
   }
   if (TABS) {
     for (int i = tid; i < FH_R64_TW; i += FH_PASS_THREADS) tabs->tw[i] = R.tw[i];
     for (int i = tid; i < FH_N; i += FH_PASS_THREADS) tabs->e512[i] = R.e512[i];
   }
   int tp[4] = {0, 0, 0, 0};
-  if (P.fuse == 2) {
+  if (fuse == 2) {
     tp[0] = fh_r64_stage_taps(sm.taps[0], P.kr, P.nr, P.cr, 0);
     tp[1] = fh_r64_stage_taps(sm.taps[1], P.kc, P.nc, P.cc, 0);
     tp[2] = fh_r64_stage_taps(sm.taps[2], P.kc, P.nc, P.cc, 1);
     tp[3] = fh_r64_stage_taps(sm.taps[3], P.kr, P.nr, P.cr, 1);
   }
+  if (fuse == 4) fh_r64_sr_stage_psf(reinterpret_cast<double*>(gbuf), R.gen);
   float dl[FH_RES_ROWS], mk[FH_RES_ROWS];
-  fh_g_get<FH_RES_ROWS>(P.delta + img + soff, dl);
+  fh_r64_getf(P.delta + img + soff, dl, npair);
 #pragma unroll
   for (int e = 0; e < FH_RES_ROWS; ++e) mk[e] = 1.f;
-  if (P.fuse == 1) {
-    const float* mp = P.mask + (size_t)(P.mask_batch > 1 ? R.image : 0) * FH_N * FH_N;
-#pragma unroll
-    for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
-      const int e = 2 * (tid + FH_PASS_THREADS * h);
-      const int g = FH_RES_ROWS * s + (e >> 8);
-      const float2 v = *reinterpret_cast<const float2*>(mp + (size_t)(g & (FH_N - 1)) * FH_N + (e & (FH_N - 1)));
-      mk[2 * h] = v.x; mk[2 * h + 1] = v.y;
-    }
-  }
+  if (fuse == 1) fh_r64_getf(P.mask + (size_t)(P.mask_batch > 1 ? R.image : 0) * FH_N * FH_N + (size_t)prow0 * FH_N, mk, npair);
   constexpr int CP = BIG ? 4 : 8, NG = BIG ? 16 : 4, CROWS = FH_PASS_THREADS / CP;
   const int ci = tid / CP, cpart = tid % CP;
   double gs[NG];
@@ -407,10 +638,17 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     for (int u = 0; u < NG; ++u) gs[u] = (cpart + CP * u < m) ? g[cpart + CP * u] : 0.0;
   }
   unsigned bar_target = 0;
+  // CG vectors of the measurement space.  fuse 1..3: the strip (6 per thread).  fuse 4: element 0 of threads < 64 nyr.
   double x[FH_RES_ROWS], r[FH_RES_ROWS], p[FH_RES_ROWS], wp[FH_RES_ROWS];
-  fh_r64_load(R.bvec + soff, x);
+  if (fuse == 4) {
+#pragma unroll
+    for (int e = 0; e < FH_RES_ROWS; ++e) x[e] = 0.0;
+    if (yown) x[0] = R.bvec[yoff + tid];
+  } else {
+    fh_r64_load(R.bvec + soff, x, npair);
+  }
   {
-    double bb = 0.0;                                     // what rides on barrier 1: pass 0 |b|^2, later |r|^2
+    double bb = 0.0;                                     // what rides on the first barrier: pass 0 |b|^2, later |r|^2
 #pragma unroll
     for (int e = 0; e < FH_RES_ROWS; ++e) { r[e] = x[e]; p[e] = 0.0; wp[e] = 0.0; bb = fma(x[e], x[e], bb); }
     fh_r64_post(bb, sm.s_red[3]);
@@ -423,20 +661,29 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
 #define FH_R64TRACE(slot) do { if (k == 3) FH_TRACE(P, 6, slot); } while (0)
   for (int k = 0;; ++k) {
     const unsigned seq = R.seq_base + (unsigned)k + 1u;
-    // ------------------------------------------------------------------ F1: rows forward of r (pass 0: of b = x0)
+    // ------------------------------------------------------------------ F1: rows forward of A^T r (pass 0: of A^T b)
     FH_R64TRACE(0);
-    {
+    if (fuse >= 3) {
+      // publish r (measurement space) and meet: the r.r partial rides on this barrier instead of the next one
+      if (fuse == 4) { if (yown) R.T[1][yoff + tid] = r[0]; }
+      else fh_r64_store(R.T[1] + soff, r, npair);
+      __syncthreads();
+      if (tid == 0) R.ride[0][s] = fh_r64_sum8(sm.s_red[3]);
+      fh_grid_sync(R.grid_counter, bar_target, nblk);
+      if (fuse == 4) fh_r64_sr_gather_at(R.T[1], rows_a, gbuf, R.gen, pl, prow0, nrows);
+      else fh_r64_gather_conv(R.T[1], rows_a, gbuf, R.gen, pl, prow0, 1);
+    } else {
       double w[FH_RES_ROWS];
 #pragma unroll
       for (int e = 0; e < FH_RES_ROWS; ++e) w[e] = r[e] * (double)mk[e];
       fh_r64_put(rows_a, w);
       __syncthreads();
       if (tid == 0) R.ride[0][s] = fh_r64_sum8(sm.s_red[3]);
-      if (P.fuse == 2) fh_r64_conv(rows_a, sm.taps[0], tp[0] >> 8, tp[0] & 255);
-      fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
-      __syncthreads();
-      fh_r64_store_t(rows_b, R.T[0], s);
+      if (fuse == 2) fh_r64_conv(rows_a, sm.taps[0], tp[0] >> 8, tp[0] & 255, nrows);
     }
+    fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
+    __syncthreads();
+    fh_r64_store_t(rows_b, R.T[0], grow0, npair);
     FH_R64TRACE(1);
     fh_grid_sync(R.grid_counter, bar_target, nblk);
     // ------------------------------------------------------------------ F2: columns forward; scalars; new direction
@@ -444,15 +691,15 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     double wr[FH_RES_ROWS];
     {
       double t[FH_RES_ROWS];
-      fh_r64_load_plane(R.T[0] + soff, t);
+      fh_r64_load_plane(R.T[0] + soff, t, npair);
       fh_r64_post(fh_r64_ride_part(R.ride[0], (int)nblk), sm.s_red[0]);
       fh_r64_put(rows_a, t);
       __syncthreads();
       const double S1 = fh_r64_sum8(sm.s_red[0]);
-      if (P.fuse == 2) fh_r64_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255);
-      fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      if (fuse == 2) fh_r64_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255, nrows);
+      fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
-      fh_r64_get(rows_b, wr);
+      fh_r64_get(rows_b, wr, npair);
       __syncthreads();                                   // Y is free for the scratch of the low-rank stages
       if (k == 0) {
         const double stop = fmax(R.rtol * sqrt(S1), R.atol);                    // cg.py:237
@@ -492,7 +739,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
           acc[i] = 0.0;
           if (i < mr) {
             float z[FH_RES_ROWS];
-            fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+            fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
 #pragma unroll
             for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fma(FH_WIDEN(z[e], e), wd[e], acc[i]);
           }
@@ -507,8 +754,9 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
           for (int i0 = 0; i0 < 32; i0 += 4) {
             float z[4][FH_RES_ROWS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (c0 + i0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + i0 + u) * d, z[u]);
+            for (int u = 0; u < 4; ++u) {
+              if (c0 + i0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + i0 + u) * d, z[u], npair);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               acc[i0 + u] = 0.0;
@@ -584,7 +832,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
         if (i < mr) {
           const double c = sc.s_c[i];
           float z[FH_RES_ROWS];
-          fh_strip_get_flat(Zs + (size_t)i * FH_RES_SLICE, z);
+          fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
 #pragma unroll
           for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = fma(c, FH_WIDEN(z[e], e), vv[e]);
         }
@@ -593,8 +841,9 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
         for (int c0 = mr; c0 < m; c0 += 4) {
           float z[4][FH_RES_ROWS];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (c0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + u) * d, z[u]);
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + u) * d, z[u], npair);
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (c0 + u < m) {
@@ -616,14 +865,14 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
         loc = fma(wp[e], vv[e], loc);
         pp = fma(p[e], p[e], pp);
       }
-      fh_r64_post(fma(R.sy2, pp, loc), sm.s_red[1]);
+      fh_r64_post(fma(R.sy2, pp, loc), sm.s_red[1]);      // Parseval: p.Ap = sy2 p.p + w_hat.(Sigma_hat w_hat)
       fh_r64_put(rows_a, vv);
       __syncthreads();                                   // also: the scratch in Y is dead, the transform may use Y again
       if (tid == 0) R.ride[1][s] = fh_r64_sum8(sm.s_red[1]);
-      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
-      if (P.fuse == 2) fh_r64_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255);
-      fh_r64_store_t(rows_b, R.T[1], s);
+      if (fuse == 2) fh_r64_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255, nrows);
+      fh_r64_store_t(rows_b, R.T[1], grow0, npair);
     }
     FH_R64TRACE(8);
     fh_grid_sync(R.grid_counter, bar_target, nblk);
@@ -631,21 +880,35 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     FH_R64TRACE(9);
     {
       double t[FH_RES_ROWS];
-      fh_r64_load_plane(R.T[1] + soff, t);
+      fh_r64_load_plane(R.T[1] + soff, t, npair);
       fh_r64_post(fh_r64_ride_part(R.ride[1], (int)nblk), sm.s_red[2]);
       fh_r64_put(rows_a, t);
       __syncthreads();
       const double pAp = fh_r64_sum8(sm.s_red[2]);
-      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512);
+      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
-      if (P.fuse == 2) fh_r64_conv(rows_b, sm.taps[3], tp[3] >> 8, tp[3] & 255);
-      fh_r64_get(rows_b, t);
-      double rr = 0.0;
+      if (fuse == 2) fh_r64_conv(rows_b, sm.taps[3], tp[3] >> 8, tp[3] & 255, nrows);
+      fh_r64_get(rows_b, t, npair);
       if (R.apply_only) {                                // Sigma v for fh_cov_dot_f64: t is the result
 #pragma unroll
         for (int e = 0; e < FH_RES_ROWS; ++e) x[e] = t[e];
         break;
       }
+      if (fuse >= 3) {
+        // publish t = Sigma A^T p (image space), meet, gather A t for the own measurement elements
+        fh_r64_store(R.T[0] + soff, t, npair);
+        fh_grid_sync(R.grid_counter, bar_target, nblk);
+        if (fuse == 4) {
+          const double q0 = fh_r64_sr_gather_a(R.T[0], gbuf, R.gen, pl, yr0, nyr);
+#pragma unroll
+          for (int e = 0; e < FH_RES_ROWS; ++e) t[e] = 0.0;
+          t[0] = q0;
+        } else {
+          fh_r64_gather_conv(R.T[0], rows_a, gbuf, R.gen, pl, prow0, 0);
+          fh_r64_get(rows_a, t, npair);
+        }
+      }
+      double rr = 0.0;
       if (k == 0) {
 #pragma unroll
         for (int e = 0; e < FH_RES_ROWS; ++e) {        // r0 = b - A_op b     (cg.py:233-235, x0 = b)
@@ -669,9 +932,8 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     FH_R64TRACE(10);
   }
   if (!z_ready) fh_mbar_wait(&sm.bar, 0);
-#pragma unroll
-  for (int h = 0; h < FH_RES_ROWS / 2; ++h)
-    reinterpret_cast<double2*>(R.x_out + soff)[tid + FH_PASS_THREADS * h] = make_double2(x[2 * h], x[2 * h + 1]);
+  if (fuse == 4 && !R.apply_only) { if (yown) R.x_out[yoff + tid] = x[0]; }
+  else fh_r64_store(R.x_out + soff, x, npair);
   if (s == 0 && tid == 0) {
     FhCgScalars* w = P.sc + R.image;
     w->resid2 = resid2;
@@ -771,4 +1033,17 @@ __global__ void __launch_bounds__(256) fh_k_f2d(const float* __restrict__ in, do
 __global__ void __launch_bounds__(256) fh_k_d2f(const double* __restrict__ in, float* __restrict__ out, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
+}
+// space update from float64 inputs: dx = x' - x, de = sigma^2 (mu' - mu_hat) formed in float64, stored as float32
+__global__ void __launch_bounds__(256)
+fh_k_su_diffs64(const double* __restrict__ x, const double* __restrict__ xn, const double* __restrict__ mu, const double* __restrict__ mun,
+                double sig2, float* __restrict__ dx, float* __restrict__ de, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { dx[i] = (float)(xn[i] - x[i]); de[i] = (float)(sig2 * (mun[i] - mu[i])); }
+}
+// time update, last step in float64: mu' = x + sigma'^2 s'
+__global__ void __launch_bounds__(256)
+fh_k_tu_finish64(const double* __restrict__ x, const float* __restrict__ s_new, double sig2n, double* __restrict__ mean, double* __restrict__ score, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const double sv = (double)s_new[i]; score[i] = sv; mean[i] = fma(sig2n, sv, x[i]); }
 }

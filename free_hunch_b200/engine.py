@@ -147,6 +147,12 @@ class CovState:
             _lib.check(_lib.lib().fh_time_update(self._h, None, None, float(sigma_t), float(sigma_tnext), 1, None, None,
                                                  self.ctx.stream()))
             return None, None
+        if torch.is_tensor(x) and x.dtype == torch.float64:
+            x64, s64 = _prep64(self.ctx, x, self.shape), _prep64(self.ctx, score, self.shape)
+            mean, sc = torch.empty_like(x64), torch.empty_like(x64)
+            _lib.check(_lib.lib().fh_time_update_f64(self._h, _ptr(x64), _ptr(s64), float(sigma_t), float(sigma_tnext), 0,
+                                                     _ptr(mean), _ptr(sc), self.ctx.stream()))
+            return mean, sc
         x = self.ctx.prep(x, self.shape)
         score = self.ctx.prep(score, self.shape)
         mean, sc = torch.empty_like(x), torch.empty_like(x)
@@ -155,6 +161,11 @@ class CovState:
         return mean, sc
 
     def space_update(self, mean_at_x, mean_at_xnext, sigma_t, x, xnext, project_to_diagonal=False):
+        if all(torch.is_tensor(t) and t.dtype == torch.float64 for t in (mean_at_x, mean_at_xnext, x, xnext)):
+            a, b, c, d = (_prep64(self.ctx, t, self.shape) for t in (mean_at_x, mean_at_xnext, x, xnext))
+            _lib.check(_lib.lib().fh_space_update_f64(self._h, _ptr(a), _ptr(b), float(sigma_t), _ptr(c), _ptr(d),
+                                                      1 if project_to_diagonal else 0, self.ctx.stream()))
+            return
         a = self.ctx.prep(mean_at_x, self.shape)
         b = self.ctx.prep(mean_at_xnext, self.shape)
         c = self.ctx.prep(x, self.shape)

@@ -86,10 +86,20 @@ int fh_cov_dot_f64(fh_state* st, const double* v_dev, double* out_dev, void* str
 int fh_time_update(fh_state* st, const float* x_dev, const float* score_dev, double sigma_t, double sigma_tnext,
                    int only_covariance, float* mean_out_dev, float* score_out_dev, void* stream);
 
+/* update_time_step with float64 x / score in and float64 mean / score out: mu' = x + sigma'^2 s' is formed in float64
+ * (the reference's x is float64, generate_conditional.py:116, and |x| ~ sigma >> |mu'|). */
+int fh_time_update_f64(fh_state* st, const double* x_dev, const double* score_dev, double sigma_t, double sigma_tnext,
+                       int only_covariance, double* mean_out_dev, double* score_out_dev, void* stream);
+
 /* update_space_step, online_update_bfgs.py:247-312 (+ DCT wrapper :362-368); project_to_diagonal variant
  * when project_to_diagonal != 0 (:274-277). */
 int fh_space_update(fh_state* st, const float* mean_at_x_dev, const float* mean_at_xnext_dev, double sigma_t,
                     const float* x_dev, const float* xnext_dev, int project_to_diagonal, void* stream);
+
+/* update_space_step from float64 inputs: the differences dx = x' - x and de = sigma^2 (mu' - mu_hat) are formed in
+ * float64 before they are rounded to the state's float32. */
+int fh_space_update_f64(fh_state* st, const double* mean_at_x_dev, const double* mean_at_xnext_dev, double sigma_t,
+                        const double* x_dev, const double* xnext_dev, int project_to_diagonal, void* stream);
 
 /* Test hooks of the reference tests (online_update_tests.py:153-155): load Sigma = diag + U U^T - V V^T
  * (U: ku x d rows, V: kv x d rows, identical for all B images) and rebuild everything else

@@ -21,8 +21,12 @@ def E():
     return H.use_emulation()
 
 
-def _state(E, assets, cap, monkeypatch):
-    monkeypatch.setenv("FH_EMU_R64_CAP", str(cap))
+SMEM = {"tables in shared memory": None, "tables through L1": 33296 + 4 * 6144 + 100, "rows from L2": 33296 + 2 * 6144 + 100}
+
+
+def _state(E, assets, variant, monkeypatch):
+    if SMEM[variant]:
+        monkeypatch.setenv("FH_EMU_R64_SMEM", str(SMEM[variant]))
     rs = np.random.RandomState(5)
     var = assets["dct_variance"]
     shape = (1,) + var.shape
@@ -47,9 +51,10 @@ def _state(E, assets, cap, monkeypatch):
     return ctx, st, ora, rs, shape, s1
 
 
-@pytest.mark.parametrize("cap", [32, 6, 3])     # rank 4: tables in shared memory / tables through L1 / two rows from global memory
-def test_res64_solve_and_cov_dot(E, assets, cap, monkeypatch):
-    ctx, st, ora, rs, shape, s1 = _state(E, assets, cap, monkeypatch)
+@pytest.mark.parametrize("variant", list(SMEM))     # rank 4; the shared-memory size picks the instantiation
+def test_res64_solve_and_cov_dot(E, assets, variant, monkeypatch):
+    ctx, st, ora, rs, shape, s1 = _state(E, assets, variant, monkeypatch)
+    cap = 32 if SMEM[variant] is None else 0
     xc = np.clip(rs.standard_normal(shape), -1, 1)
     mu0 = 0.3 * xc
     sy2 = float(np.float32(0.1) * np.float32(0.1))
@@ -80,3 +85,31 @@ def test_res64_solve_and_cov_dot(E, assets, cap, monkeypatch):
             mat_cpu, io = fo.mat_solver(oo, y, mu0, ora, s1, max_rtol=1.0, maxiter=200)
             assert info["niter"][0] == io["niter"], (name, rtol, info["niter"], io["niter"])
             assert info["optimal"][0] and rel_l2(mat, mat_cpu) < 1e-6
+
+
+@pytest.mark.parametrize("which", ["motion_blur", "super_resolution"])
+def test_res64_non_separable_operators(E, assets, which, monkeypatch):
+    """The gathers of the operators that do not fold into the DCT passes (fh_r64_gather_conv: the 217-tap motion PSF as
+    column runs; fh_r64_sr_gather_at / _a: 25 x 25 bicubic PSF with x4 decimation), inside the resident float64 solve:
+    two CG iterations at rank 4 against the float64 oracle's FFT operators."""
+    ctx, st, ora, rs, shape, s1 = _state(E, assets, "tables in shared memory", monkeypatch)
+    xc = np.clip(rs.standard_normal(shape), -1, 1)
+    mu0 = 0.3 * xc
+    sy2 = float(np.float32(0.1) * np.float32(0.1))
+    if which == "motion_blur":
+        op = E.Operator.conv(ctx, assets["motion_ks61_std05"], 1)
+        oo = fo.MotionBlurOracle(assets["motion_ks61_std05"], 0.1, otf_dtype=np.complex128)
+    else:
+        op = E.Operator.conv(ctx, assets["bicubic_x4"], 4)
+        oo = fo.SuperResolutionOracle(assets["bicubic_x4"], 0.1, 4, otf_dtype=np.complex128)
+    ay = oo.A(xc)
+    y = (ay + 0.1 * rs.standard_normal(ay.shape)).astype(np.float32).astype(np.float64)
+    ctx.set_cg_mode(E.CG_RESIDENT)
+    try:
+        mat, info = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, 1.0, maxiter=50, fixed_iters=2)
+    finally:
+        ctx.set_cg_mode(E.CG_AUTO)
+    assert mat.dtype == torch.float64 and ctx.cg_last_mode == E.CG_RESIDENT and info["niter"][0] == 2
+    mat_cpu, io = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=2)
+    assert rel_l2(mat, mat_cpu) < 1e-6, (which, rel_l2(mat, mat_cpu))
+    assert abs(info["residual_norm"][0] - io["residual_norm"]) <= 1e-6 * io["residual_norm"]

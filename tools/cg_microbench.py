@@ -79,9 +79,12 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--profile-kernels", action="store_true")
+    ap.add_argument("--f64", action="store_true", help="float64 y / mu / mat (fh_cg_solve_f64)")  # float64_io
     ap.add_argument("--mode", default="auto", choices=["auto", "streaming", "resident", "resident_f32"])
     args = ap.parse_args()
     ctx, st, op, y, mu, t_time, t_space = build(args)
+    if args.f64:
+        y, mu = y.double(), mu.double()
     B, k = args.batch, st.rank // 2
     ctx.set_cg_mode({"auto": E.CG_AUTO, "streaming": E.CG_STREAMING, "resident": E.CG_RESIDENT, "resident_f32": E.CG_RESIDENT_F32}[args.mode])
     for _ in range(2):

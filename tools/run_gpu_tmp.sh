@@ -1,11 +1,12 @@
 set -x
-rm -f gpurun_out/parity_log.jsonl
-timeout 1200 python -m pytest tests/test_gpu_configs.py -m gpu -q 2>&1 | tail -8
+rm -f gpurun_out/mb64.jsonl gpurun_out/parity_log.jsonl
+for p in 0 4 16 28; do
+  FH_TRACE=1 timeout 120 python tools/cg_microbench.py --pairs $p --operator motion_blur --mode resident --iters 100 --f64 >> gpurun_out/mb64.jsonl 2>> gpurun_out/mb64.err
+done
 python - <<'PY'
 import json
-for l in open('gpurun_out/parity_log.jsonl'):
-    d=json.loads(l)
-    if d['test']!='full_config': continue
-    print(d['cfg'],'final',d['final'],'first',d['first_call'],'worst',d['worst_call'],d['worst_call_index'],'cg',d['cg_total'],d['ref_cg_total'],'same',d['calls_with_same_niter'],'/',d['calls'],'firstdiff',d['first_call_with_other_niter'])
-    print('  errs',d['errs'][:12])
+for l in open('gpurun_out/mb64.jsonl'):
+    d=json.loads(l); print(d['operator'],d['pairs'],round(d['us_per_iteration'],2),d['cg_path'],d['niter'],d.get('trace_us',{}).get('6'))
 PY
+tail -5 gpurun_out/mb64.err
+timeout 1500 python -m pytest tests -m gpu -q -k "motion or rank" 2>&1 | tail -5
