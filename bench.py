@@ -58,7 +58,18 @@ def parse_args():
     ap.add_argument("--blocking-host-reads", action="store_true",
                     help="run the mechanism with the reference's per-call host reads (allclose / std / CG flags) instead of deferring them")
     ap.add_argument("--batched", type=int, default=16, help="also report a B-images-per-GPU step (HBM-bound regime); 0 = off")
+    ap.add_argument("--images", type=int, default=0,
+                    help="sweep mode (BASELINE configs[4]): sample this many images, sharded round-robin over the ranks, with the "
+                         "final NCCL gather of the uint8 results inside the timed region; one step = the whole sweep")
+    ap.add_argument("--no-unet-in-loop", action="store_true", help="skip the measured image with the random-init UNet as the denoiser")
     return ap.parse_args()
+
+
+def bench_config(a):
+    """The `config` object both arms print (identical keys and values: the workload is the same by construction)."""
+    return {"workload": workload_name(a), "operator": a.operator, "num_steps": a.num_steps, "solver": a.solver,
+            "micro_batch": a.batch, "denoiser": "analytic DCT-Gaussian stand-in (exact denoiser of the DCT-diagonal prior)",
+            "images": a.images}
 
 
 def workload_name(a):
@@ -255,28 +266,48 @@ def cpu_images_per_s(a, calls, secs):
 
 
 def run_reference_arm(a, assets):
+    """The reference algorithm on the host cores (oracle/fh_oracle.py: the reference is a set of Python scripts, not an
+    installable package, and /root/reference does not travel to the GPU box -- kind "port").  Step 1 samples a WHOLE
+    image when a short probe says it fits ~150 s (no extrapolation); further steps are bounded prefixes of the same
+    image scaled by the CG-iteration share of step 1's own complete profile."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # W warm-up "steps" are skipped for the CPU arm beyond a single short call budget; each step is a bounded sample
-    per_step = max(5.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + min(a.warmup, 1))))
+    per_step = max(5.0, min(a.cpu_seconds, 240.0 / max(1, a.steps)))
+    est_total = None
     if a.warmup > 0:
-        cpu_reference_sample(assets, a, min(3.0, per_step), cores)
-    vals, samples = [], []
+        calls, complete, secs = cpu_reference_sample(assets, a, 3.0, cores)
+        v0, _ = cpu_images_per_s(a, calls, secs)
+        est_total = 1.0 / max(v0, 1e-9)
+    vals, samples, profile, profile_secs = [], [], None, 0.0
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        calls, complete, secs = cpu_reference_sample(assets, a, per_step, cores)
-        v_, how = cpu_images_per_s(a, calls, secs)
-        vals.append(v_)
-        samples.append(how)
+    for step in range(a.steps):
+        # whole images while they fit ~4 minutes in total; otherwise a bounded prefix scaled by what the SAME calls took
+        # inside step 1's whole image (per-call seconds, not iteration counts: early iterations are the cheap ones)
+        spent = time.perf_counter() - t0
+        whole = (est_total is None or est_total <= 150.0) and (step == 0 or (profile is not None and spent + profile_secs <= 240.0))
+        calls, complete, secs = cpu_reference_sample(assets, a, 1e9 if whole else per_step, cores)
+        if complete:
+            profile = [c["seconds"] for c in calls]
+            profile_secs = secs
+            vals.append(1.0 / secs)
+            samples.append(f"a whole image: {len(calls)} mechanism calls, {sum(c['niter'] for c in calls)} CG iterations in {secs:.1f} s")
+        elif profile is not None:
+            share = sum(profile[:len(calls)]) / sum(profile)
+            vals.append(share / secs)
+            samples.append(f"first {len(calls)} mechanism calls of the same image in {secs:.1f} s, scaled by the time share ({share:.3f}) those calls had in step 1")
+        else:
+            v_, how = cpu_images_per_s(a, calls, secs)
+            vals.append(v_)
+            samples.append(how)
     ms = (time.perf_counter() - t0) / max(1, a.steps) * 1e3
     v = float(np.mean(vals))
-    sample = f"per step ~{per_step:.0f} s of oracle/fh_oracle.py (float64 CG, complex128 state) on {cores} threads: {samples[0]}"
+    sample = f"oracle/fh_oracle.py (float64 CG, complex128 state) on {cores} threads; step 1: {samples[0]}" + (f"; later steps: {samples[-1]}" if len(samples) > 1 else "")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/c128",
-        "data": "synthetic", "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (numpy)"},
+        "data": "synthetic", "config": bench_config(a), "values_per_step": [float(x) for x in vals],
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -297,10 +328,26 @@ def algorithmic_bytes_per_launch(kernel, m_rows, B):
     return table.get(kernel)
 
 
-def algorithmic_bytes_per_cg_iteration(m_rows):
+def algorithmic_bytes_per_cg_iteration(m_rows, operator="gaussian_blur"):
     """one blur / inpainting CG iteration touches p, x, r (read), x, r, p (write), the diagonal of Sigma
-    and the 2k = m low-rank vectors once: (7 + m) image vectors.  (The mask / OTF extra is not counted.)"""
-    return (7 + m_rows) * D_VEC_BYTES
+    and the 2k = m low-rank vectors once: (7 + m) image vectors (the mask / OTF extra is not counted); x4 super-resolution
+    has 1/16-size measurement vectors: (1 + m) image vectors."""
+    return ((1 if operator == "super_resolution" else 7) + m_rows) * D_VEC_BYTES
+
+
+def algorithmic_bytes_of_step(log, operator):
+    """SURVEY.md 8(d), summed over one sampled image: every CG iteration at the rank it ran at, every time update
+    (8k + 12 vectors) and space update (10k + 19) -- the numerator of the STEP-level roofline fraction."""
+    tot, k_prev = 0, 0
+    for r in log:
+        k = int(r["k"])
+        if r.get("time_update"):
+            tot += (8 * k_prev + 12) * D_VEC_BYTES
+        if r.get("space_update"):
+            tot += (10 * k_prev + 19) * D_VEC_BYTES
+        tot += max(r["niter"]) * algorithmic_bytes_per_cg_iteration(2 * k, operator)
+        k_prev = k
+    return tot
 
 def run_b200(a, assets):
     import torch
@@ -322,9 +369,10 @@ def run_b200(a, assets):
     var = assets["dct_variance"]
     t_steps = edm_sigma_steps(a.num_steps)
 
-    def make_problem(step, B):
+    def make_problem(step, B, seed0=None):
         # every step samples NEW images: global image index = (step * world + rank) * B + b  (weak scaling)
-        seed0 = 1000 + (step * world + rank) * B
+        if seed0 is None:
+            seed0 = 1000 + (step * world + rank) * B
         x_clean, noise, ynoise = synth_inputs(assets, a.operator, B, seed0)
         kw = dict(in_shape=(B, 3, 256, 256), sigma_s=0.1, device=dev)
         if a.operator == "inpainting":
@@ -475,6 +523,34 @@ def run_b200(a, assets):
     e2e_value = world * B * a.steps / (e2e_total * 1e-3)
     h2d = int(problems[0][1].nbytes + problems[0][2].nbytes)
     d2h = int(B * 3 * 256 * 256 * 8)
+    # ---- sweep mode (BASELINE configs[4]): N images round-robin over the ranks, no collective in the loop, ONE all-gather of
+    #      the decoded uint8 images at the end (generate_conditional.py:328-340, 557-569) inside the timed region
+    sweep = None
+    if a.images > 0:
+        from free_hunch_b200.outputs import decode_uint8
+        from free_hunch_b200.sharding import gather_images, shard_indices
+        idxs = shard_indices(a.images, rank, world)
+        local = []
+        for gi in idxs:                                      # inputs resident in HBM before the clock starts
+            op_i, y_i, n_i = make_problem(0, 1, seed0=50000 + gi)
+            local.append((op_i, torch.from_numpy(y_i).to(dev), torch.from_numpy(n_i).to(dev)))
+        flush.fill_(1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        imgs, its = [], 0
+        for op_i, y_i, n_i in local:
+            x_i, mech_i = sample(op_i, y_i, n_i)
+            imgs.append(decode_uint8(x_i))
+            its += sum(max(r["niter"]) for r in mech_i.log)
+        mine = torch.cat(imgs) if imgs else torch.empty((0, 3, 256, 256), dtype=torch.uint8, device=dev)
+        allimgs = gather_images(mine, idxs, a.images)
+        s1.record(); s1.synchronize()
+        sweep_ms = reduce_max(s0.elapsed_time(s1))
+        sweep = {"images": a.images, "n_gpus": world, "images_per_s": a.images / (sweep_ms * 1e-3), "ms_total": sweep_ms,
+                 "images_this_rank": len(idxs), "cg_iterations_this_rank": its, "gathered_bytes": int(allimgs.numel()),
+                 "gather": "torch.distributed.all_gather over NCCL (uint8, 196 608 B per image), inside the timed region" if world > 1 else "single rank: local placement",
+                 "checksum": int(allimgs.to(torch.int64).sum().item())}
     # ---- one step with CUDA-event phase timers (the reference's own phase boundaries, conditioning_mechanisms.py:242-271)
     op, y, noise = problems[it]; it += 1
     timer = PhaseTimer(True)
@@ -522,37 +598,51 @@ def run_b200(a, assets):
         """The resident solve is ONE kernel: `iters` iterations per launch, (7 + m) image vectors of algorithmic bytes each."""
         m_rows = state.rank
         ms = E.cg_resident_time(state, op_handle, iters=iters, reps=5)
-        ab = iters * algorithmic_bytes_per_cg_iteration(m_rows)
+        ab = iters * algorithmic_bytes_per_cg_iteration(m_rows, a.operator)
         return ms, ab, ab / (ms * 1e-3) / 1e9, m_rows
 
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
     fold = a.operator in ("gaussian_blur", "inpainting")
     ctx0 = mech.covariance_model.ctx
-    resident = fold and ctx0.cg_last_mode == E.CG_RESIDENT
+    resident = ctx0.cg_last_mode == E.CG_RESIDENT
+    step_bytes = algorithmic_bytes_of_step(mech.log, a.operator)
+    step_frac = step_bytes / (hot_ms * 1e-3) / 1e9 / peak if hot_ms > 0 else None
     if resident:
         iters = 200
         ms, ab, ach, m_rows = resident_roofline(mech.covariance_model.state, mech.forward_operator.op, iters)
+        # the same kernel at rank 0: most iterations of a run happen before the first space update (sigma > 10)
+        st0 = E.CovState(ctx0, 1, E.BASIS_DCT)
+        st0.init(torch.from_numpy(var), float(t_steps[0]) ** 2)
+        ms0 = E.cg_resident_time(st0, mech.forward_operator.op, iters=iters, reps=5)
+        ab0 = iters * algorithmic_bytes_per_cg_iteration(0, a.operator)
+        st0.close()
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01_resident.json")))["kernels"][E.CG_RESIDENT_KERNEL]["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r02_res64.json")))["kernels"][E.CG_RES64_KERNEL]["dram_bytes_per_launch"]
         except (OSError, KeyError):
             pass
-        share = sum(v[1] for k, v in kprof.items() if k.startswith(E.CG_RESIDENT_KERNEL)) / kern_total
-        ctx0.set_cg_mode(E.CG_STREAMING)
-        try:
-            _, stimes, _, _, _ = kernel_roofline(mech.covariance_model.state, mech.forward_operator.op, B)
-        finally:
-            ctx0.set_cg_mode(E.CG_AUTO)
-        roofline.update({"kernel": E.CG_RESIDENT_KERNEL, "achieved": ach, "frac": ach / peak, "traffic": traffic,
+        share = sum(v[1] for k, v in kprof.items() if k.startswith(E.CG_RES64_KERNEL)) / kern_total
+        stimes = {}
+        if fold:
+            ctx0.set_cg_mode(E.CG_STREAMING)
+            try:
+                _, stimes, _, _, _ = kernel_roofline(mech.covariance_model.state, mech.forward_operator.op, B)
+            finally:
+                ctx0.set_cg_mode(E.CG_AUTO)
+        roofline.update({"kernel": E.CG_RES64_KERNEL, "achieved": ach, "frac": ach / peak, "traffic": traffic,
+                         "rank0": {"us_per_cg_iteration": ms0 * 1e3 / iters, "achieved": ab0 / (ms0 * 1e-3) / 1e9, "frac": ab0 / (ms0 * 1e-3) / 1e9 / peak},
+                         "step": {"algorithmic_bytes": step_bytes, "cov_plus_cg_ms": hot_ms, "achieved": step_bytes / (hot_ms * 1e-3) / 1e9,
+                                  "frac": step_frac, "note": "all CG iterations at the rank they ran at + time / space updates (SURVEY 8d) over "
+                                  "the phase-timed covariance + CG time of one sampled image"},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                          "avg_us": ms * 1e3, "iterations_per_launch": iters, "us_per_cg_iteration": ms * 1e3 / iters,
                          "algorithmic_bytes_per_launch": ab, "algorithmic_bytes_per_iteration": ab // iters, "Z_rows": m_rows,
                          "share_of_kernel_time_in_step": share,
                          "streaming_path_kernels_us": {k: round(v * 1e3, 2) for k, v in stimes.items()},
-                         "note": "one cooperative launch per solve: Z (m x 786 KB) stays in shared memory and x/r/p/q in registers, so "
-                                 "the kernel moves ~0 bytes of DRAM; `achieved` divides the contract's algorithmic bytes, (7+m) image "
-                                 "vectors per iteration (SURVEY 8d), by the measured time. The kernel is bound by five grid barriers "
-                                 "and the L2 round trips of the 2-D DCT transposes per iteration, not by HBM"})
+                         "note": "one cooperative launch per solve, float64 arithmetic (the reference's CG precision): Z (m x 786 KB) stays "
+                                 "in shared memory and x/r/p in registers, so the kernel moves ~0 bytes of DRAM; `achieved` divides the "
+                                 "contract's algorithmic bytes ((7+m) image vectors per iteration, SURVEY 8d) by the measured time. "
+                                 "The kernel is bound by its grid-wide exchanges, the FP64 pipe and shared-memory latency, not by HBM"})
     elif fold:
         top, times, ab, ach, m_rows = kernel_roofline(mech.covariance_model.state, mech.forward_operator.op, B)
         traffic = None
@@ -571,14 +661,16 @@ def run_b200(a, assets):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": total_ms / a.steps, "ms_steps": [round(v, 3) for v in ms_steps], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (f64 reductions and k x k algebra)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "denoiser": "analytic DCT-Gaussian stand-in (PyTorch + library DCT); the UNet is outside the hot path",
-                   "l2": "256 MiB flush between steps; every step samples new images", "mechanism_calls": n_calls,
-                   "host_reads": "per call (reference behaviour)" if a.blocking_host_reads else "deferred: one synchronisation per sampled image (FreeHunch.finalize)",
-                   "cg_iterations_per_image": float(np.mean(cg_iters)), "cg_iterations_steps": cg_iters, "final_bfgs_pairs": ranks_k[-1]},
+        "dtype": "f64 CG solve (vectors, DCTs, operators, reductions); f32 storage of the covariance state", "data": "synthetic",
+        "config": bench_config(a),
+        "run": {"l2": "256 MiB flush between steps; every step samples new images", "mechanism_calls": n_calls,
+                "host_reads": "per call (reference behaviour)" if a.blocking_host_reads else "deferred: one synchronisation per sampled image (FreeHunch.finalize)",
+                "cg": "float64 resident kernel (fh_k_cg_res64)" if resident else "float32 streaming iteration",
+                "cg_iterations_per_image": float(np.mean(cg_iters)), "cg_iterations_steps": cg_iters, "final_bfgs_pairs": ranks_k[-1]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_total / a.steps, "ms_steps": [round(v, 3) for v in e2e_ms]},
         "gpu_launches": int(launches),
+        "sweep": sweep,
         "clocks": clk,
         "roofline": roofline,
         "hot_path": {"phase_timed_step_ms": prof_ms, "cov_plus_cg_ms_per_mechanism_call": hot_ms / n_calls,
@@ -648,10 +740,49 @@ def run_b200(a, assets):
             step_ms = total_ms / a.steps
             out["unet"] = {"config": "imagenet256 guided-diffusion UNet, random init, fp16 autocast, batch 1 (free_hunch_b200/denoiser.py)",
                            "params_M": sum(p.numel() for p in den.parameters()) / 1e6, "fwd_plus_vjp_ms_per_call": unet_ms,
-                           "calls_per_image": n_calls,
-                           "images_per_s_with_unet_instead_of_stand_in": 1e3 / (step_ms - standin_ms + n_calls * unet_ms),
-                           "note": "timed separately (north-star); a random-init net is not a denoiser, so it is not put inside the "
-                                   "guided loop: the CG iteration counts it would induce are arbitrary"}
+                           "calls_per_image": n_calls}
+            # CUDA-graph capture of forward + VJP
+            try:
+                from free_hunch_b200.denoiser import GraphedDenoiser
+                gden = GraphedDenoiser(den, xin)
+
+                def gcall():
+                    xg = xin.clone().requires_grad_()
+                    d, _ = gden(xg, 5.1405)
+                    return torch.autograd.grad((w * d).sum(), xg)[0]
+                g_ref, g_got = call(), gcall()
+                for _ in range(3):
+                    gcall()
+                torch.cuda.synchronize()
+                u0.record()
+                for _ in range(10):
+                    gcall()
+                u1.record(); u1.synchronize()
+                out["unet"]["fwd_plus_vjp_ms_per_call_cuda_graph"] = u0.elapsed_time(u1) / 10
+                out["unet"]["cuda_graph_vjp_rel_diff_vs_eager"] = float((g_got - g_ref).norm() / g_ref.norm())
+            except Exception as e:
+                gden = None
+                out["unet"]["cuda_graph_error"] = repr(e)[:300]
+            # one image MEASURED with the random-init UNet as the denoiser inside the guided loop (BASELINE: "images/s on
+            # random-init UNet weights").  A random-init net is not a denoiser: the CG systems it induces are arbitrary, so
+            # the iteration count is reported next to the time.
+            if not a.no_unet_in_loop and B == 1:
+                try:
+                    op, y, noise = problems[a.warmup]
+                    for use, name in ((gden, "cuda_graph"), (den, "eager")):
+                        if use is None:
+                            continue
+                        torch.cuda.synchronize()
+                        u0.record()
+                        mech_u = make_mechanism(op, 1)
+                        x_u = conditional_sampler(mech_u, use, torch.from_numpy(y).to(dev), torch.from_numpy(noise).to(dev), t_steps, solver=a.solver)
+                        u1.record(); u1.synchronize()
+                        ms_u = u0.elapsed_time(u1)
+                        out["unet"][f"in_loop_{name}"] = {"images_per_s": 1e3 / ms_u, "ms_per_image": ms_u,
+                                                         "cg_iterations": sum(max(r["niter"]) for r in mech_u.log),
+                                                         "finite": bool(torch.isfinite(x_u).all())}
+                except Exception as e:
+                    out["unet"]["in_loop_error"] = repr(e)[:300]
             del den
         except Exception as e:                                   # the UNet timing is auxiliary: never fail the bench on it
             out["unet"] = {"error": repr(e)[:200]}

@@ -211,6 +211,14 @@ class FreeHunch(ConditioningMechanism):
         the assumption was wrong.  The arithmetic is the same in both modes."""
         sigma_f = float(sigma.item()) if torch.is_tensor(sigma) else float(sigma)
         x_t = x_t.requires_grad_()
+        # one library call per piece of element-wise glue (fh_mech.cuh) where the tensors are what the sampler hands over
+        # (float64 on the device, DCT basis); anything else takes the PyTorch expressions of the reference
+        fused = bool(self.argv.get("fused_glue", True)) and x_t.is_cuda and x_t.dtype == torch.float64 and \
+            self.covariance_model.state.basis == engine.BASIS_DCT
+        if fused and y.dtype != torch.float64:                      # widen the measurement once per image, not per call
+            if getattr(self, "_y_src", None) is not y:
+                self._y_src, self._y64 = y, y.to(torch.float64)
+            y = self._y64
         with self.timer("denoiser"):
             x_0_mean, _ = model(x_t, sigma)
         cov = self.covariance_model
@@ -218,9 +226,13 @@ class FreeHunch(ConditioningMechanism):
         if self.do_space_updates:
             prev_mean_at_sigma = None
             if len(self.sigmas) != 0 and sigma_f != self.sigmas[-1]:                                     # :241-244
-                score_previous = (self.denoiser_means[-1] - self.xs[-1]) / self.sigmas[-1] ** 2
                 with self.timer("time_update"):
-                    prev_mean_at_sigma, _ = cov.update_time_step(self.xs[-1], self.sigmas[-1], sigma_f, score_previous)
+                    if fused:
+                        prev_mean_at_sigma, _ = cov.state.time_update_from_mean(self.xs[-1], self.denoiser_means[-1], self.sigmas[-1], sigma_f)
+                        cov._sigma = sigma_f
+                    else:
+                        score_previous = (self.denoiser_means[-1] - self.xs[-1]) / self._scalar(self.sigmas[-1] ** 2, x_t)
+                        prev_mean_at_sigma, _ = cov.update_time_step(self.xs[-1], self.sigmas[-1], sigma_f, score_previous)
                 rec["time_update"] = True
             elif len(self.sigmas) != 0:                                                                  # :248-249
                 prev_mean_at_sigma = self.denoiser_means[-1]
@@ -232,8 +244,13 @@ class FreeHunch(ConditioningMechanism):
                     # agree to allclose's tolerance, exactly as in the reference
                     in_window = self.space_step_update_lower_threshold < sigma_f < self.space_step_update_threshold
                     if in_window or not self.use_analytical_score_time_update:
-                        same_x = torch.isclose(x_t.detach(), self.xs[-1]).all()   # device flag, checked in finalize()
+                        if fused:
+                            same_x = engine.mech_notclose(cov.ctx, x_t.detach(), self.xs[-1]).sum() == 0
+                        else:
+                            same_x = torch.isclose(x_t.detach(), self.xs[-1]).all()   # device flag, checked in finalize()
                     x_changed = True
+                elif fused:
+                    x_changed = bool(engine.mech_notclose(cov.ctx, x_t.detach(), self.xs[-1]).any())
                 else:
                     x_changed = not torch.allclose(x_t.detach(), self.xs[-1])
             rec["_same_x"] = same_x
@@ -258,20 +275,31 @@ class FreeHunch(ConditioningMechanism):
             p_y_xt_grad = torch.autograd.grad((mat.detach() * x_0_mean).sum(), x_t)[0]                   # :280
         # :283-288.  The reference runs batch 1; with B independent images per call the VJP-vs-Sigma.mat decision is taken
         # PER IMAGE (a whole-batch statistic would make an image's guidance depend on its batch mates).
-        use_cov = (p_y_xt_grad * s2).flatten(1).std(dim=1) > self.denoiser_mean_error_threshold          # (B,), on the device
-        if self.defer:
-            alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
-            p_y_xt_grad = torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
-            rec["fallback"] = use_cov
-        else:
-            flags = [bool(v) for v in use_cov.tolist()]                                                  # host read, like :283
-            if any(flags):
-                alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2
-                p_y_xt_grad = alt if all(flags) else torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
+        if fused:
+            alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True)                               # Sigma.mat, float64
+            x_0_mean_new, flag = engine.mech_combine(cov.ctx, x_0_mean.detach(), p_y_xt_grad, alt, s2,
+                                                     self.denoiser_mean_error_threshold, self.cond_scaling)
+            if self.defer:
+                rec["fallback"] = flag
             else:
-                p_y_xt_grad = p_y_xt_grad * self.cond_scaling
-            rec["fallback"] = flags[0] if len(flags) == 1 else flags
-        x_0_mean_new = x_0_mean + p_y_xt_grad * s2
+                flags = [bool(v) for v in flag.tolist()]
+                rec["fallback"] = flags[0] if len(flags) == 1 else flags
+        else:
+            s2d = self._scalar(s2, x_t)                  # divisor as a 0-dim device tensor: a true division like the reference's
+            use_cov = (p_y_xt_grad * s2).flatten(1).std(dim=1) > self.denoiser_mean_error_threshold      # (B,), on the device
+            if self.defer:
+                alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2d
+                p_y_xt_grad = torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
+                rec["fallback"] = use_cov
+            else:
+                flags = [bool(v) for v in use_cov.tolist()]                                              # host read, like :283
+                if any(flags):
+                    alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True) * self.cond_scaling / s2d
+                    p_y_xt_grad = alt if all(flags) else torch.where(use_cov.view(-1, 1, 1, 1), alt, p_y_xt_grad * self.cond_scaling)
+                else:
+                    p_y_xt_grad = p_y_xt_grad * self.cond_scaling
+                rec["fallback"] = flags[0] if len(flags) == 1 else flags
+            x_0_mean_new = x_0_mean + p_y_xt_grad * s2
         # :290-292 -- history stays ON DEVICE; only the last entry is ever read, so only it is kept
         self.sigmas.append(sigma_f)
         self.xs = [x_t.detach()]
@@ -280,6 +308,13 @@ class FreeHunch(ConditioningMechanism):
         rec["k"] = cov.vector_count
         self.log.append(rec)
         return x_0_mean_new
+
+    @staticmethod
+    def _scalar(v, like):
+        """A divisor as a 0-dim tensor on `like`'s device.  The reference divides by 0-dim device tensors (sigma.pow(2),
+        t_hat), which PyTorch evaluates as a true division; dividing a CUDA tensor by a Python float is evaluated as a
+        multiplication with the rounded reciprocal, one ulp off -- enough to move a loosely converged CG stop."""
+        return torch.full((), float(v), dtype=like.dtype, device=like.device)
 
     def finalize(self):
         """Deferred mode: ONE synchronisation for the whole run -- decode the CG outcomes and device-side flags into the

@@ -7,6 +7,7 @@
 #include "fh_cg.cuh"
 #include "fh_cg_resident.cuh"
 #include "fh_cg_res64.cuh"
+#include "fh_mech.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -1225,7 +1226,13 @@ static int op_apply64(fh_op* o, const double* in, double* out, int batch, int tr
   const int planes = batch * c->C;
   if (o->kind == FH_OP_INPAINT) FH_FAIL(FH_EINVAL, "op_apply64: the mask is applied by the caller");
   FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
-  if (o->kind == FH_OP_BLUR) {
+  if (o->kind == FH_OP_BLUR && o->separable && c->H % 32 == 0 && c->W % 32 == 0 &&
+      (size_t)((32 + o->nc - 1) * (((32 + o->nr - 1) | 1) + 33)) * sizeof(double) <= 48 * 1024) {
+    FhSepTaps k{o->kr, o->kc, o->nr, o->nc, o->cr, o->cc};
+    const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
+    const size_t smem = (size_t)(th * tw + th * 33) * sizeof(double);
+    FH_LAUNCH(fh_k_conv_sep64, dim3(c->W / 32, c->H / 32, planes), dim3(32, 8), smem, stream, in, out, k, c->H, c->W, transpose);
+  } else if (o->kind == FH_OP_BLUR) {
     if (c->H % 32 || c->W % 32) FH_FAIL(FH_EINVAL, "blur needs image sizes divisible by 32");
     const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;
     const size_t smem = (size_t)th * tw * sizeof(double);
@@ -1681,4 +1688,53 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   *ms_out = ms / reps;
   return FH_OK;
 #endif
+}
+
+// ------------------------------------------------------------------------------------ fused mechanism / sampler glue
+extern "C" int fh_mech_combine(fh_ctx* c, const double* mu, const double* g, const double* sigv, double sigma2, double threshold,
+                               double scale, double* out, int* flag_dev, int batch, void* stream) {
+  if (!c || !mu || !g || !sigv || !out || !flag_dev || batch < 1 || batch > c->max_batch || !(sigma2 > 0)) FH_FAIL(FH_EINVAL, "bad fh_mech_combine arguments");
+  const int nblk = (int)((c->d + FH_MECH_CHUNK - 1) / FH_MECH_CHUNK);
+  // the Gram partials buffer is free between covariance updates: (B, nblk, 3) doubles fit easily
+  double* part = c->gram_partial;
+  FH_LAUNCH(fh_k_mech_stats, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, g, sigma2, part, c->d);
+  FH_LAUNCH(fh_k_mech_combine, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, mu, g, sigv, (const double*)part, nblk, sigma2, threshold, scale, out, flag_dev, c->d);
+  FH_KCHECK();
+  return FH_OK;
+}
+extern "C" int fh_mech_allclose(fh_ctx* c, const double* a, const double* b, int* notclose_dev, int batch, void* stream) {
+  if (!c || !a || !b || !notclose_dev || batch < 1) FH_FAIL(FH_EINVAL, "bad fh_mech_allclose arguments");
+  FH_CUDA(cudaMemsetAsync(notclose_dev, 0, (size_t)batch * sizeof(int), (cudaStream_t)stream));
+  const int nblk = (int)((c->d + FH_MECH_CHUNK - 1) / FH_MECH_CHUNK);
+  FH_LAUNCH(fh_k_mech_allclose, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, a, b, notclose_dev, c->d);
+  FH_KCHECK();
+  return FH_OK;
+}
+// update_time_step fed with the previous evaluation itself: score_prev = (mean_prev - x_prev) / sigma_t^2 (conditioning_mechanisms.py:243)
+extern "C" int fh_time_update_from_mean(fh_state* s, const double* x_prev, const double* mean_prev, double sigma_t, double sigma_tnext,
+                                        double* mean_out, double* score_out, void* stream) {
+  if (!s || !x_prev || !mean_prev || !mean_out || !score_out || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update_from_mean arguments");
+  fh_ctx* c = s->ctx;
+  const long tot = (long)s->B * s->d;
+  const dim3 g((unsigned)((tot + 255) / 256)), b(256);
+  FH_LAUNCH(fh_k_mech_score, g, b, 0, stream, mean_prev, x_prev, sigma_t * sigma_t, c->cgv[0], c->cgv[1], tot);
+  FH_KCHECK();
+  int rc = fh_time_update(s, c->cgv[0], c->cgv[1], sigma_t, sigma_tnext, 0, c->cgv[2], c->cgv[3], stream);
+  if (rc) return rc;
+  FH_LAUNCH(fh_k_tu_finish64, g, b, 0, stream, x_prev, (const float*)c->cgv[3], sigma_tnext * sigma_tnext, mean_out, score_out, tot);
+  FH_KCHECK();
+  return FH_OK;
+}
+extern "C" int fh_sampler_euler(const double* x_hat, const double* den, double t_cur, double h, double* d_cur, double* x_prime, long n, void* stream) {
+  if (!x_hat || !den || !d_cur || !x_prime || n < 1) FH_FAIL(FH_EINVAL, "bad fh_sampler_euler arguments");
+  FH_LAUNCH(fh_k_euler, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, x_hat, den, t_cur, h, d_cur, x_prime, n);
+  FH_KCHECK();
+  return FH_OK;
+}
+extern "C" int fh_sampler_heun(const double* x_hat, const double* d_cur, const double* x_prime, const double* den2, double t_next, double h,
+                               double* x_next, long n, void* stream) {
+  if (!x_hat || !d_cur || !x_prime || !den2 || !x_next || n < 1) FH_FAIL(FH_EINVAL, "bad fh_sampler_heun arguments");
+  FH_LAUNCH(fh_k_heun, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, x_hat, d_cur, x_prime, den2, t_next, h, x_next, n);
+  FH_KCHECK();
+  return FH_OK;
 }

@@ -1047,3 +1047,48 @@ fh_k_tu_finish64(const double* __restrict__ x, const float* __restrict__ s_new, 
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const double sv = (double)s_new[i]; score[i] = sv; mean[i] = fma(sig2n, sv, x[i]); }
 }
+// Separable circular convolution in float64 (the Gaussian PSF is rank 1): out = conv_cols(kc) conv_rows(kr) in, taps at
+// offsets (a - cc) / (b - cr); transpose flips the offsets.  32 x 32 output tile per CTA, halo in shared memory, row pass
+// into a second tile, column pass from it.  grid = (W/32, H/32, planes), block (32, 8).  (The 625-tap dense kernel
+// fh_k_conv_taps64 took 80 us per call for the 25 x 25 Gaussian; this one does 50 taps per pixel.)
+__global__ void __launch_bounds__(256)
+fh_k_conv_sep64(const double* __restrict__ in, double* __restrict__ out, FhSepTaps k, int H, int W, int transpose) {
+  FH_DYN_SMEM(double, sm);
+  const int oy0 = transpose ? -k.cc : -(k.nc - 1 - k.cc), oy1 = transpose ? (k.nc - 1 - k.cc) : k.cc;
+  const int ox0 = transpose ? -k.cr : -(k.nr - 1 - k.cr), ox1 = transpose ? (k.nr - 1 - k.cr) : k.cr;
+  const int th = 32 + (oy1 - oy0), tw = 32 + (ox1 - ox0), tws = tw | 1;
+  double* tile = sm;                      // th x tws
+  double* tmp = sm + th * tws;            // th x 33   (row-convolved)
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < th; r += 8) {
+    int gi = (i0 + oy0 + r) % H; if (gi < 0) gi += H;
+    const double* srow = in + plane + (size_t)gi * W;
+    for (int c = threadIdx.x; c < tw; c += 32) {
+      int gj = (j0 + ox0 + c) % W; if (gj < 0) gj += W;
+      tile[r * tws + c] = srow[gj];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < th * 32; idx += 256) {
+    const int r = idx >> 5, c = idx & 31;
+    double acc = 0.0;
+    for (int bb = 0; bb < k.nr; ++bb) {
+      const int ox = transpose ? (bb - k.cr) : -(bb - k.cr);
+      acc = fma((double)k.kr[bb], tile[r * tws + c + ox - ox0], acc);
+    }
+    tmp[r * 33 + c] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = threadIdx.y + 8 * q;
+    double acc = 0.0;
+    for (int a = 0; a < k.nc; ++a) {
+      const int oy = transpose ? (a - k.cc) : -(a - k.cc);
+      acc = fma((double)k.kc[a], tmp[(r + oy - oy0) * 33 + threadIdx.x], acc);
+    }
+    out[plane + (size_t)(i0 + r) * W + j0 + threadIdx.x] = acc;
+  }
+}

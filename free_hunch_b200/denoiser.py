@@ -170,3 +170,33 @@ class IDDPMLinearPrecond(nn.Module):
 def build_denoiser(config="imagenet256", device="cuda", use_fp16=True):
     net = ADMUNet(**CONFIGS[config]).to(device)
     return IDDPMLinearPrecond(net, use_fp16=use_fp16).to(device).eval()
+
+
+class GraphedDenoiser:
+    """CUDA-graph capture of the denoiser's forward AND its VJP: `torch.cuda.make_graphed_callables`
+    records the forward pass and the backward pass of `den(x, sigma)` once; every later mechanism call replays the two
+    graphs (the VJP when the mechanism calls `autograd.grad(..., x_t)`, conditioning_mechanisms.py:280) instead of
+    issuing the UNet's ~1500 kernels from Python.  sigma travels through a static device scalar, so one capture serves
+    every noise level; x must keep the captured shape.  Returns (D_x, None) like the wrapper it graphs."""
+
+    def __init__(self, den, sample_x):
+        self.den = den
+        self.sig = torch.zeros((), dtype=torch.float64, device=sample_x.device)
+
+        class _Fn(nn.Module):
+            def __init__(self, d):
+                super().__init__()
+                self.d = d
+
+            def forward(self, x, sigma):
+                return self.d(x, sigma)[0]
+        self.fn = _Fn(den)
+        x = sample_x.detach().clone().requires_grad_()
+        self.sig.fill_(1.0)
+        self.graphed = torch.cuda.make_graphed_callables(self.fn, (x, self.sig))
+
+    def __call__(self, x, sigma):
+        self.sig.fill_(float(sigma))
+        # the graph writes its output into a static buffer that the next replay overwrites: the mechanism keeps the
+        # previous call's mean as history, so it gets its own copy (clone is differentiable: the VJP still replays)
+        return self.graphed(x, self.sig).clone(), None

@@ -160,6 +160,14 @@ class CovState:
                                              _ptr(mean), _ptr(sc), self.ctx.stream()))
         return mean, sc
 
+    def time_update_from_mean(self, x_prev, mean_prev, sigma_t, sigma_tnext):
+        """update_time_step with score_prev = (mean_prev - x_prev) / sigma_t^2 formed inside (float64 in / out)."""
+        x64, m64 = _prep64(self.ctx, x_prev, self.shape), _prep64(self.ctx, mean_prev, self.shape)
+        mean, sc = torch.empty_like(x64), torch.empty_like(x64)
+        _lib.check(_lib.lib().fh_time_update_from_mean(self._h, _ptr(x64), _ptr(m64), float(sigma_t), float(sigma_tnext),
+                                                       _ptr(mean), _ptr(sc), self.ctx.stream()))
+        return mean, sc
+
     def space_update(self, mean_at_x, mean_at_xnext, sigma_t, x, xnext, project_to_diagonal=False):
         if all(torch.is_tensor(t) and t.dtype == torch.float64 for t in (mean_at_x, mean_at_xnext, x, xnext)):
             a, b, c, d = (_prep64(self.ctx, t, self.shape) for t in (mean_at_x, mean_at_xnext, x, xnext))
@@ -331,6 +339,46 @@ def cg_solve_async(state, op, y, mu, sigma_y2, rtol, maxiter=5000, fixed_iters=0
     return mat, DeferredCgInfo(info, state.B)
 
 
+def mech_combine(ctx, mu, g, sigv, sigma2, threshold, scale):
+    """(x0_mean_new, flag): conditioning_mechanisms.py:283-288 in one fused call; flag is a (B,) int32 DEVICE tensor
+    (1 = the Sigma.mat branch was taken for that image)."""
+    B = mu.shape[0]
+    mu, g, sigv = (_prep64(ctx, t, mu.shape) for t in (mu, g, sigv))
+    out = torch.empty_like(mu)
+    flag = torch.empty(B, dtype=torch.int32, device=ctx.device)
+    _lib.check(_lib.lib().fh_mech_combine(ctx._h, _ptr(mu), _ptr(g), _ptr(sigv), float(sigma2), float(threshold), float(scale),
+                                          _ptr(out), _ptr(flag), B, ctx.stream()))
+    return out, flag
+
+
+def mech_notclose(ctx, a, b):
+    """(B,) int32 device tensor: 0 where torch.allclose(a_b, b_b) holds (conditioning_mechanisms.py:250)."""
+    B = a.shape[0]
+    a, b = _prep64(ctx, a, a.shape), _prep64(ctx, b, a.shape)
+    flag = torch.empty(B, dtype=torch.int32, device=ctx.device)
+    _lib.check(_lib.lib().fh_mech_allclose(ctx._h, _ptr(a), _ptr(b), _ptr(flag), B, ctx.stream()))
+    return flag
+
+
+def _stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def sampler_euler(x_hat, den, t_cur, h):
+    """(d_cur, x_prime) of generate_conditional.py:146-149 in one launch (float64 CUDA tensors)."""
+    d_cur, x_prime = torch.empty_like(x_hat), torch.empty_like(x_hat)
+    _lib.check(_lib.lib().fh_sampler_euler(_ptr(x_hat), _ptr(den), float(t_cur), float(h), _ptr(d_cur), _ptr(x_prime), x_hat.numel(), _stream_of(x_hat)))
+    return d_cur, x_prime
+
+
+def sampler_heun(x_hat, d_cur, x_prime, den2, t_next, h):
+    """x_next of generate_conditional.py:160-167 in one launch."""
+    x_next = torch.empty_like(x_hat)
+    _lib.check(_lib.lib().fh_sampler_heun(_ptr(x_hat), _ptr(d_cur), _ptr(x_prime), _ptr(den2), float(t_next), float(h), _ptr(x_next),
+                                          x_hat.numel(), _stream_of(x_hat)))
+    return x_next
+
+
 def launch_count(reset=False):
     return int(_lib.lib().fh_launch_count(1 if reset else 0))
 
@@ -354,6 +402,7 @@ def kernel_profile():
 
 CG_KERNELS = ("fh_k_cg_fwd_rows", "fh_k_cg_fwd_cols", "fh_k_cg_inv_cols", "fh_k_cg_inv_rows", "fh_k_cg_xr")
 CG_RESIDENT_KERNEL = "fh_k_cg_resident"
+CG_RES64_KERNEL = "fh_k_cg_res64"
 
 
 def cg_resident_time(state, op, iters=200, reps=5):

@@ -42,20 +42,29 @@ def conditional_sampler(mechanism, net, y, noise, t_steps, solver="heun"):
     # sigma goes to the mechanism as a 0-dim float64 HOST tensor: the mechanism and the denoiser wrapper read it with
     # .item(), which on a device tensor is a full synchronisation per call
     sig = lambda t: torch.tensor(t, dtype=torch.float64)
+    fused = x_next.is_cuda                         # the step algebra as one launch each (fh_mech.cuh; bit-identical to the expressions below)
+    if fused:
+        from . import engine
     for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
         x_hat = x_next
         h = t_next - t_cur
         with torch.enable_grad():
             den = mechanism(x_hat.detach().clone().requires_grad_(), net, y, sig(t_cur)).detach()
-        d_cur = (x_hat - den) / t_cur
-        x_prime = x_hat + h * d_cur
+        if fused:
+            d_cur, x_prime = engine.sampler_euler(x_hat.contiguous(), den.contiguous(), t_cur, h)
+        else:
+            d_cur = (x_hat - den) / t_cur
+            x_prime = x_hat + h * d_cur
         if solver == "euler" or i == n - 1:
-            x_next = x_hat + h * d_cur
+            x_next = x_prime if fused else x_hat + h * d_cur
         else:
             with torch.enable_grad():
                 den2 = mechanism(x_prime.detach().clone().requires_grad_(), net, y, sig(t_next)).detach()
-            d_prime = x_prime / t_next - den2 / t_next
-            x_next = x_hat + h * (0.5 * d_cur + 0.5 * d_prime)
+            if fused:
+                x_next = engine.sampler_heun(x_hat.contiguous(), d_cur, x_prime, den2.contiguous(), t_next, h)
+            else:
+                d_prime = x_prime / t_next - den2 / t_next
+                x_next = x_hat + h * (0.5 * d_cur + 0.5 * d_prime)
     if hasattr(mechanism, "finalize"):
         mechanism.finalize()                       # deferred host reads (one synchronisation), no-op otherwise
     return x_next

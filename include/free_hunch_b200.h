@@ -113,6 +113,26 @@ int fh_state_drop_all(fh_state* st, double sigma, void* stream);
 int fh_state_export(fh_state* st, float* pi_dev, float* Z_dev, double* Gz_dev, double* Gs_dev, float* delta_dev,
                     void* stream);
 
+/* update_time_step fed with the previous evaluation: score_prev = (mean_prev - x_prev) / sigma_t^2 is formed inside
+ * (conditioning_mechanisms.py:243-244); float64 in and out like fh_time_update_f64. */
+int fh_time_update_from_mean(fh_state* st, const double* x_prev_dev, const double* mean_prev_dev, double sigma_t, double sigma_tnext,
+                             double* mean_out_dev, double* score_out_dev, void* stream);
+
+/* ---- element-wise glue of a mechanism call / sampler step, fused (float64, same operation order as the reference's
+ * PyTorch expressions, hence bit-identical to them) --------------------------------------------------------------
+ * fh_mech_combine: conditioning_mechanisms.py:283-288 per image b:
+ *     flag_b = std(g_b * sigma2) > threshold ;  out_b = mu_b + (flag_b ? sigv_b * scale / sigma2 : g_b * scale) * sigma2
+ *   g = the VJP through the denoiser, sigv = Sigma.mat; flag_dev[b] receives the decision (device memory: no host read).
+ * fh_mech_allclose: torch.allclose(a_b, b_b) of :250 per image; notclose_dev[b] = 0 when allclose.
+ * fh_sampler_euler / fh_sampler_heun: generate_conditional.py:146-149 and :160-167. */
+int fh_mech_combine(fh_ctx* ctx, const double* mu_dev, const double* g_dev, const double* sigv_dev, double sigma2, double threshold,
+                    double scale, double* out_dev, int* flag_dev, int batch, void* stream);
+int fh_mech_allclose(fh_ctx* ctx, const double* a_dev, const double* b_dev, int* notclose_dev, int batch, void* stream);
+int fh_sampler_euler(const double* x_hat_dev, const double* den_dev, double t_cur, double h, double* d_cur_dev, double* x_prime_dev,
+                     long n, void* stream);
+int fh_sampler_heun(const double* x_hat_dev, const double* d_cur_dev, const double* x_prime_dev, const double* den2_dev, double t_next,
+                    double h, double* x_next_dev, long n, void* stream);
+
 /* ---- measurement operators ------------------------------------------------------------------- */
 /* Circular convolution with a ks x ks PSF (host pointer, row-major), the FFT operator of
  * measurements.py:140-157,180-198 / utils_sisr.py:22-41 evaluated directly in pixel space:

@@ -581,6 +581,55 @@ def test_mechanism_deferred_host_reads_identical(assets):
         record("mechanism_deferred", op=name, calls=len(logs[1]), cg_iterations=sum(max(r[4]) for r in logs[1]))
 
 
+def test_mechanism_fused_glue_is_bit_identical(assets):
+    """The fused element-wise glue (fh_mech.cuh: score of the previous evaluation, allclose test, std / fallback select /
+    mu + g sigma^2, Euler and Heun step algebra -- one launch each) against the reference's PyTorch expressions
+    (`fused_glue=False`, and a sampler fed CPU-side algebra is not needed: the same loop with torch ops): the float64
+    results are bit-identical, so are the logs."""
+    from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
+    from free_hunch_b200.measurements import get_operator
+    from free_hunch_b200 import sampler as S
+    dev = torch.device("cuda")
+    var = assets["dct_variance"]
+    t_steps = [float(t) for t in S.edm_sigma_steps(10)]
+    rs = np.random.RandomState(17)
+    x_clean = synth_image(var, 23)
+    noise = torch.from_numpy(rs.standard_normal(SHAPE)).to(dev)
+    op = get_operator("gaussian_blur", kernel=assets["gaussian_ks61_std3"], scale_factor=1, in_shape=SHAPE, sigma_s=0.1, device=dev)
+    y = op.A(tt(x_clean).float().to(dev)) + 0.1 * torch.from_numpy(rs.standard_normal(SHAPE)).float().to(dev)
+    net = S.AnalyticDCTGaussianDenoiser64(var, dev)
+
+    def torch_sampler(mech):                       # generate_conditional.py:131-167 with plain torch expressions
+        x_next = noise.to(torch.float64) * t_steps[0]
+        n = len(t_steps) - 1
+        for i, (tc, tn) in enumerate(zip(t_steps[:-1], t_steps[1:])):
+            x_hat, h = x_next, tn - tc
+            tcd, tnd = torch.full((), tc, dtype=torch.float64, device=dev), torch.full((), tn, dtype=torch.float64, device=dev)
+            with torch.enable_grad():
+                den = mech(x_hat.detach().clone().requires_grad_(), net, y, torch.tensor(tc, dtype=torch.float64)).detach()
+            d_cur = (x_hat - den) / tcd            # 0-dim device divisors, as in the reference: true divisions
+            x_prime = x_hat + h * d_cur
+            if i == n - 1:
+                x_next = x_hat + h * d_cur
+            else:
+                with torch.enable_grad():
+                    den2 = mech(x_prime.detach().clone().requires_grad_(), net, y, torch.tensor(tn, dtype=torch.float64)).detach()
+                d_prime = x_prime / tnd - den2 / tnd
+                x_next = x_hat + h * (0.5 * d_cur + 0.5 * d_prime)
+        return x_next
+    outs, logs = [], []
+    for fused in (True, False):
+        mech = choose_conditioning_mechanism("free_hunch")(
+            1.0, op, False, init_denoiser_variance=1, init_noise_variance=torch.tensor(t_steps[0] ** 2, dtype=torch.float64),
+            data_dim=3 * 256 * 256, dct_variance=var, image_base_covariance="dct_diagonal", device=dev, fused_glue=fused)
+        with torch.no_grad():
+            outs.append(S.conditional_sampler(mech, net, y, noise, t_steps, solver="heun") if fused else torch_sampler(mech))
+        logs.append([(r["sigma"], r["time_update"], r["space_update"], r["fallback"], tuple(r["niter"]), r["k"]) for r in mech.log])
+    assert logs[0] == logs[1]
+    assert any(r[3] for r in logs[0]) and not all(r[3] for r in logs[0])        # both branches of the fallback were taken
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_mechanism_deferred_detects_repeated_point(assets):
     """The one assumption of the deferred mode (x_t differs from the previous call) is verified, not trusted."""
     from free_hunch_b200.conditioning_mechanisms import choose_conditioning_mechanism
