@@ -100,9 +100,13 @@ class CovarianceHessianBFGS:
         return out.reshape(shape).to(dtype)
 
     def drop_vectors(self, max_vector_count, sigma):
-        """online_update_bfgs.py:233-245.  Dropping everything is representation independent and supported;
-        keeping the 'last n columns' of the reference's complex sqrtm factors is not (it depends on that
-        factorisation) and is only reachable with a non-default max_vector_count below the live rank."""
+        """online_update_bfgs.py:233-245.  Dropping everything is representation independent and supported.
+        Keeping "the last n columns" is not: after the first time update the reference's U, V are no longer the BFGS pairs
+        but the columns of `P W sqrtm(M)` produced by its Woodbury re-factorisations (:87-119) -- a complex matrix square
+        root mixes every pair into every column, so which part of Sigma the last n columns carry depends on that
+        factorisation history, not on Sigma.  The product keeps no such factors; the request is
+        refused rather than answered with a different truncation.  Only reachable with a non-default max_vector_count
+        below the live rank (config.yaml default 100000 = never)."""
         k = self.state.rank // 2
         if max_vector_count == 0:
             self.state.drop_all(float(sigma))

@@ -712,16 +712,53 @@ static int space_update_from_diffs(fh_state* s, double sigma_t, void* stream) {
   return refresh_core(s, stream);
 }
 
+// project_to_diagonal (online_update_bfgs.py:274-277): the BFGS pair is not appended but folded into the DIAGONAL part
+// of Sigma's representation, diag <- diag + u.u - v.v with u = de sqrt(gamma), v = Sigma dx / sqrt(dx.Sigma dx), i.e.
+//     D' = delta + gamma de^2 - (Sigma dx)^2 / (dx.Sigma dx)          (real also when gamma < 0: only squares enter)
+// while the low-rank part L = delta Z^T Gs Z delta of Sigma stays.  In the precision form Sigma'^-1 = (D' + L)^-1 that is
+//     Z' = (delta / D') Z (row-wise),  pi' = 1 / D' - sigma^-2,  Gz' = -Gs (I + K' Gs)^-1,  K' = Z (delta^2 / D') Z^T
+// (Woodbury with the SAME small algebra as the per-sigma core, roles of Gz and Gs swapped).  The rank does not change.
+// One deliberate difference: the reference appends (u, v) / sigma^2 to its Hessian factors ALSO in this mode (:296-298 run
+// unconditionally), which makes its H inconsistent with its own Sigma; here H always follows from Sigma.
+static int space_update_project(fh_state* s, double sigma_t, void* stream) {
+  fh_ctx* c = s->ctx;
+  const int vec = vec_ok(s->d);
+  int rc;
+  s->var2 = sigma_t * sigma_t;
+  float *dxp = c->scratch[0], *dep = c->scratch[1], *dx = c->scratch[2], *de = c->scratch[3], *sdx = c->scratch[4], *wgt = c->scratch[5];
+  if ((rc = to_basis(s, dxp, dx, stream))) return rc;
+  if ((rc = to_basis(s, dep, de, stream))) return rc;
+  if ((rc = cov_dot_basis(s, dx, sdx, stream))) return rc;                      // Sigma dx in the state's basis
+  // dx.Sigma dx and dx.de: two "rows" against dx
+  FH_LAUNCH(fh_k_dots, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->Z, 0, dx, (const float*)nullptr, (const float*)sdx, (const float*)de, c->dot_partial, s->d, vec);
+  FH_KCHECK();
+  FH_LAUNCH(fh_k_dots_finalize, dim3(s->B), dim3(128), 0, stream, c->dot_partial, fh_nchunks(s->d), 0, 2, (const double*)nullptr, c->csum, (double*)nullptr);
+  FH_KCHECK();
+  // D' and the weights delta^2 / D' (Gram) ; Z rows are rescaled by delta / D' after the Gram
+  FH_LAUNCH(fh_k_su_project, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, s->delta, de, sdx, c->csum, (float)(1.0 / s->sig2), s->pi, wgt, c->scratch[6], s->d, vec);
+  FH_KCHECK();
+  if (s->m > 0) {
+    FhRowPtrs xr{};
+    if ((rc = gram(s, s->m, xr, 0, wgt, stream))) return rc;                    // K' = Z (delta^2 / D') Z^T
+    const size_t smem = (size_t)(2 * FH_MAXM * FH_MAXM + 3 * FH_MAXM) * sizeof(double);
+    FH_LAUNCH(fh_k_core, dim3(s->B), dim3(FH_CORE_THREADS), smem, stream, c->gramK, s->Gs, s->m, c->Gtmp, 0, 0.0, c->coef, c->status);   // -Gs (I + K' Gs)^-1
+    FH_KCHECK();
+    FH_CUDA(cudaMemcpyAsync(s->Gz, c->Gtmp, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    FH_LAUNCH(fh_k_scale_rows, dim3((unsigned)fh_nchunks(s->d), s->B, s->m), dim3(FH_EW_THREADS), 0, stream, s->Z, c->scratch[6], s->d, vec);
+    FH_KCHECK();
+  }
+  return refresh_core(s, stream);
+}
+
 extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float* mean_at_xnext, double sigma_t,
                                const float* x, const float* xnext, int project_to_diagonal, void* stream) {
   if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update arguments");
-  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
-  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  if (!project_to_diagonal && s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
   fh_ctx* c = s->ctx;
   FH_LAUNCH(fh_k_su_diffs, ew_grid(s->d, s->B), dim3(FH_EW_THREADS), 0, stream, x, xnext, mean_at_x, mean_at_xnext,
             (float)(sigma_t * sigma_t), c->scratch[0], c->scratch[1], s->d, vec_ok(s->d));
   FH_KCHECK();
-  return space_update_from_diffs(s, sigma_t, stream);
+  return project_to_diagonal ? space_update_project(s, sigma_t, stream) : space_update_from_diffs(s, sigma_t, stream);
 }
 // The same update from float64 inputs (the reference's x and denoiser means are float64, generate_conditional.py:116):
 // dx = x' - x and de = sigma^2 (mu' - mu_hat) are DIFFERENCES of nearly equal images, so they are formed in float64 and
@@ -729,14 +766,13 @@ extern "C" int fh_space_update(fh_state* s, const float* mean_at_x, const float*
 extern "C" int fh_space_update_f64(fh_state* s, const double* mean_at_x, const double* mean_at_xnext, double sigma_t,
                                    const double* x, const double* xnext, int project_to_diagonal, void* stream) {
   if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update_f64 arguments");
-  if (project_to_diagonal) FH_FAIL(FH_EINVAL, "project_to_diagonal is not implemented in this build");
-  if (s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  if (!project_to_diagonal && s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
   fh_ctx* c = s->ctx;
   const long tot = (long)s->B * s->d;
   FH_LAUNCH(fh_k_su_diffs64, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream, x, xnext, mean_at_x, mean_at_xnext, sigma_t * sigma_t,
             c->scratch[0], c->scratch[1], tot);
   FH_KCHECK();
-  return space_update_from_diffs(s, sigma_t, stream);
+  return project_to_diagonal ? space_update_project(s, sigma_t, stream) : space_update_from_diffs(s, sigma_t, stream);
 }
 
 extern "C" int fh_state_set_cov_vectors(fh_state* s, const float* U, int ku, const float* V, int kv, double sigma, void* stream) {

@@ -603,6 +603,44 @@ fh_k_su_rows(float* __restrict__ Z, int m, const double* __restrict__ coef, cons
   fh_store8(Z + (b * FH_MAXM + m) * (size_t)d, off, d, vec, ev);
 }
 
+// project_to_diagonal (online_update_bfgs.py:274-277): D' = delta + gamma de^2 - (Sigma dx)^2 / (dx.Sigma dx) with
+// gamma = 1 / (dx.de); csum[b][0] = dx.Sigma dx, csum[b][1] = dx.de.  Writes pi' = 1/D' - tau, the Gram weight
+// delta^2 / D' and the row scale delta / D'.
+__global__ void __launch_bounds__(FH_EW_THREADS)
+fh_k_su_project(const float* __restrict__ delta, const float* __restrict__ de, const float* __restrict__ sdx, const double* __restrict__ csum,
+                float tau, float* __restrict__ pi, float* __restrict__ wgt, float* __restrict__ scale, long d, int vec) {
+  const long off = (long)blockIdx.x * FH_CHUNK;
+  const size_t b = (size_t)blockIdx.y;
+  const double dsd = csum[b * (FH_MAXM + 2)], gamma = 1.0 / csum[b * (FH_MAXM + 2) + 1];
+  float dl[8], ev[8], sv[8], p[8], w[8], sc[8];
+  fh_load8(delta + b * d, off, d, vec, dl);
+  fh_load8(de + b * d, off, d, vec, ev);
+  fh_load8(sdx + b * d, off, d, vec, sv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const double D = (double)dl[e] + gamma * (double)ev[e] * (double)ev[e] - (double)sv[e] * (double)sv[e] / dsd;
+    p[e] = (float)(1.0 / D - (double)tau);
+    w[e] = (float)((double)dl[e] * (double)dl[e] / D);
+    sc[e] = (float)((double)dl[e] / D);
+  }
+  fh_store8(pi + b * d, off, d, vec, p);
+  fh_store8(wgt + b * d, off, d, vec, w);
+  fh_store8(scale + b * d, off, d, vec, sc);
+}
+// Z[b][i][:] *= scale[b][:]   (grid.z = row i)
+__global__ void __launch_bounds__(FH_EW_THREADS)
+fh_k_scale_rows(float* __restrict__ Z, const float* __restrict__ scale, long d, int vec) {
+  const long off = (long)blockIdx.x * FH_CHUNK;
+  const size_t b = blockIdx.y;
+  float* row = Z + (b * FH_MAXM + blockIdx.z) * (size_t)d;
+  float z[8], sc[8];
+  fh_load8(row, off, d, vec, z);
+  fh_load8(scale + b * d, off, d, vec, sc);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) z[e] *= sc[e];
+  fh_store8(row, off, d, vec, z);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Measurement operators.
 // Inpainting: out = mask .* in  (mask (MB,H*W) broadcast over channels; MB = 1 or B)

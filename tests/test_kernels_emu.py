@@ -44,11 +44,15 @@ def _score_fn(x, t):
 
 
 def test_reference_unit_test_time_and_space_identity_basis(E):
-    """online_update_tests.py:274-374 (F3-adapted) through the product classes, d = 5."""
+    case_time_and_space_identity_basis("cpu")
+
+
+def case_time_and_space_identity_basis(device):
+    """online_update_tests.py:274-374 (F3-adapted) through the product classes, d = 5.  Shared with tests/test_gpu_unit.py."""
     from free_hunch_b200.covariance import CovarianceHessianBFGS
     g = np.load(H.ROOT + "/tests/golden/unit_tests.npz")
     ts, d = g["t4_ts"], 5
-    bf = CovarianceHessianBFGS(init_denoiser_variance=1, init_noise_variance=ts[0] ** 2, data_dim=d, device="cpu")
+    bf = CovarianceHessianBFGS(init_denoiser_variance=1, init_noise_variance=ts[0] ** 2, data_dim=d, device=device)
     x = torch.from_numpy(g["t4_x0"].astype(np.float64))
     for i in range(8):
         t, tn = ts[i], ts[i + 1]
@@ -71,12 +75,16 @@ def test_reference_unit_test_time_and_space_identity_basis(E):
 
 @pytest.mark.parametrize("pairs", [1, 4])
 def test_reference_unit_test_preseeded_vectors(E, pairs):
+    case_preseeded_vectors("cpu", pairs)
+
+
+def case_preseeded_vectors(device, pairs):
     """online_update_tests.py:71-187: poke vectors_denoiser_cov_{u,v}, rebuild, time update."""
     from free_hunch_b200.covariance import CovarianceHessianBFGS
     g = np.load(H.ROOT + "/tests/golden/unit_tests.npz")
     p = f"t2_{pairs}_"
     d = 15
-    bf = CovarianceHessianBFGS(init_denoiser_variance=1, init_noise_variance=80.0 ** 2, data_dim=d, device="cpu")
+    bf = CovarianceHessianBFGS(init_denoiser_variance=1, init_noise_variance=80.0 ** 2, data_dim=d, device=device)
     bf.vectors_denoiser_cov_u = torch.from_numpy(g[p + "U"]).to(torch.complex128)
     bf.vectors_denoiser_cov_v = torch.from_numpy(g[p + "V"]).to(torch.complex128)
     bf.set_others_corresponding_to_current_denoiser_cov(80.0)
@@ -93,21 +101,26 @@ def test_reference_unit_test_preseeded_vectors(E, pairs):
 
 
 def test_operators_and_cg_small(E, assets, monkeypatch):
-    """Operators (vs the oracle's FFT operators with a float64 OTF) and batched CG on 2 x 64 x 64 images."""
+    case_operators_and_cg_small(E, assets, "cpu", monkeypatch)
+
+
+def case_operators_and_cg_small(E, assets, device, monkeypatch):
+    """Operators (vs the oracle's FFT operators with a float64 OTF) and batched CG on 2 x 64 x 64 images, identity basis."""
     rs = np.random.RandomState(0)
     Hh, C = 64, 2
-    ctx = E.Context("cpu", max_batch=2, channels=C, height=Hh, width=Hh)
+    ctx = E.Context(device, max_batch=2, channels=C, height=Hh, width=Hh)
     x = rs.standard_normal((2, C, Hh, Hh))
     for key in ("gaussian_ks61_std3", "motion_ks61_std05"):
         op = E.Operator.conv(ctx, assets[key], 1)
         oo = fo.GaussianBlurOracle(assets[key], 0.1, image_size=Hh, otf_dtype=np.complex128)
         assert rel_l2(op.apply(torch.tensor(x)), oo.A(x)) < 1e-6
         assert rel_l2(op.apply(torch.tensor(x), transpose=True), oo.AT(x)) < 1e-6
-    # the motion PSF through both pixel-space kernels: the tap list above (few planes), the column-run kernel here
-    monkeypatch.setenv("FH_EMU_CONV_RUNS", "1")
-    assert rel_l2(op.apply(torch.tensor(x)), oo.A(x)) < 1e-6
-    assert rel_l2(op.apply(torch.tensor(x), transpose=True), oo.AT(x)) < 1e-6
-    monkeypatch.delenv("FH_EMU_CONV_RUNS")
+    if monkeypatch is not None:
+        # the motion PSF through both pixel-space kernels: the tap list above (few planes), the column-run kernel here
+        monkeypatch.setenv("FH_EMU_CONV_RUNS", "1")
+        assert rel_l2(op.apply(torch.tensor(x)), oo.A(x)) < 1e-6
+        assert rel_l2(op.apply(torch.tensor(x), transpose=True), oo.AT(x)) < 1e-6
+        monkeypatch.delenv("FH_EMU_CONV_RUNS")
     op = E.Operator.conv(ctx, assets["bicubic_x4"], 4)
     oo = fo.SuperResolutionOracle(assets["bicubic_x4"], 0.1, 4, image_size=Hh, otf_dtype=np.complex128)
     ys = rs.standard_normal((2, C, Hh // 4, Hh // 4))
@@ -149,6 +162,51 @@ def test_operators_and_cg_small(E, assets, monkeypatch):
             assert abs(info["niter"][b] - io["niter"]) <= 1
             assert info["optimal"][b] == io["optimal"]
             assert rel_l2(mat[b], oo.AT(u.reshape(y[b:b + 1].shape))[0]) < 1e-5
+
+
+def case_project_to_diagonal(E, device, dct, assets=None):
+    """update_space_step with project_to_diagonal (online_update_bfgs.py:274-277) on a state that already has a low-rank
+    part: Sigma.v afterwards, and after a further time update, against the oracle (which follows the reference's Sigma side
+    line by line).  Identity basis at 2 x 32 x 32 or the DCT basis at 3 x 256 x 256."""
+    rs = np.random.RandomState(3)
+    if dct:
+        var = assets["dct_variance"]
+        C, Hh = 3, 256
+        ora = fo.CovarianceOracleDCT(var, 400.0, var.size)
+        basis = E.BASIS_DCT
+    else:
+        C, Hh = 2, 32
+        var = np.exp(rs.uniform(np.log(1e-2), np.log(30.0), size=(C, Hh, Hh))).astype(np.float32)
+        ora = fo.CovarianceOracle(var.reshape(-1), 400.0, var.size)
+        basis = E.BASIS_IDENTITY
+    shape = (1, C, Hh, Hh)
+    ctx = E.Context(device, max_batch=1, channels=C, height=Hh, width=Hh)
+    st = E.CovState(ctx, 1, basis)
+    st.init(torch.tensor(var), 400.0)
+    den = lambda z: 0.5 * np.tanh(z) + 0.1 * z
+    x = rs.standard_normal(shape) * 8
+    st.time_update(None, None, 20.0, 8.0, only_covariance=True)
+    ora.update_time_step(np.zeros(shape), 20.0, 8.0, np.zeros(shape), only_covariance=True)
+    for step in range(3):
+        xn = x + 0.3 * rs.standard_normal(shape)
+        m0, m1 = den(x), den(xn)
+        project = step == 2
+        ora.project_to_diagonal = project
+        st.space_update(torch.tensor(m0), torch.tensor(m1), 8.0, torch.tensor(x), torch.tensor(xn), project_to_diagonal=project)
+        ora.update_space_step(m0, m1, 8.0, x, xn)
+        x = xn
+    assert st.rank == 4                                  # the projected pair did not add rows
+    w = rs.standard_normal(shape)
+    e1 = rel_l2(st.cov_dot(torch.tensor(w).float()), ora.denoiser_cov_vector_dot(w))
+    st.time_update(None, None, 8.0, 5.0, only_covariance=True)
+    ora.update_time_step(np.zeros(shape), 8.0, 5.0, np.zeros(shape), only_covariance=True)
+    e2 = rel_l2(st.cov_dot(torch.tensor(w).float()), ora.denoiser_cov_vector_dot(w))
+    assert e1 < 1e-4 and e2 < 1e-4, (e1, e2)
+    return e1, e2
+
+
+def test_project_to_diagonal_identity_basis(E):
+    case_project_to_diagonal(E, "cpu", False)
 
 
 def test_argument_errors(E):
