@@ -55,20 +55,28 @@ __global__ void __launch_bounds__(FH_MECH_THREADS)
 fh_k_mech_combine(const double* __restrict__ mu, const double* __restrict__ g, const double* __restrict__ sigv, const double* __restrict__ part,
                   int nblk, double sigma2, double threshold, double scale, double* __restrict__ out, int* __restrict__ flag_out, long d) {
   __shared__ int s_flag;
+  __shared__ double red[33];
   const size_t b = blockIdx.y;
-  if (threadIdx.x == 0) {
+  {
+    // merge of the chunk statistics (Chan et al.): N = sum n_i, mean = sum n_i mean_i / N, M2 = sum (M2_i + n_i (mean_i - mean)^2)
+    // as three fixed-order block sums (one chunk per thread; a serial merge by one thread took 32 us per launch)
     const double* p = part + b * nblk * 3;
-    double n = p[0], mean = p[1], M2 = p[2];
-    for (int k = 1; k < nblk; ++k) {
-      const double nb = p[3 * k], mb = p[3 * k + 1], Mb = p[3 * k + 2];
-      const double tot = n + nb, delta = mb - mean;
-      mean += delta * (nb / tot);
-      M2 += Mb + delta * delta * (n * nb / tot);
-      n = tot;
+    const bool has = (int)threadIdx.x < nblk;
+    const double ni = has ? p[3 * threadIdx.x] : 0.0, mi = has ? p[3 * threadIdx.x + 1] : 0.0, Mi = has ? p[3 * threadIdx.x + 2] : 0.0;
+    double n = 0.0, wsum = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += FH_MECH_THREADS) { n += p[3 * k]; wsum += p[3 * k] * p[3 * k + 1]; }
+    n = fh_block_sum(n, red);
+    wsum = fh_block_sum(wsum, red);
+    const double mean = wsum / n;
+    double m2 = 0.0;
+    for (int k = threadIdx.x; k < nblk; k += FH_MECH_THREADS) { const double dlt = p[3 * k + 1] - mean; m2 += p[3 * k + 2] + p[3 * k] * dlt * dlt; }
+    (void)ni; (void)mi; (void)Mi;
+    const double M2 = fh_block_sum(m2, red);
+    if (threadIdx.x == 0) {
+      const double sd = sqrt(M2 / (n - 1.0));                               // torch.std: unbiased
+      s_flag = sd > threshold ? 1 : 0;
+      if (blockIdx.x == 0) flag_out[b] = s_flag;
     }
-    const double sd = sqrt(M2 / (n - 1.0));                                 // torch.std: unbiased
-    s_flag = sd > threshold ? 1 : 0;
-    if (blockIdx.x == 0) flag_out[b] = s_flag;
   }
   __syncthreads();
   const int use_cov = s_flag;

@@ -79,16 +79,17 @@ def test_res64_solve_and_cov_dot(E, assets, variant, monkeypatch):
         assert rel_l2(mat, mat_cpu) < (1e-6 if name == "inpainting" else 5e-6), (name, cap, rel_l2(mat, mat_cpu))
         assert abs(info["residual_norm"][0] - io["residual_norm"]) <= 1e-6 * io["residual_norm"]
         if name == "inpainting" and cap == 32:
-            # the residual test: a tolerance the float64 oracle meets at its 5th iteration stops the kernel there too
+            # the residual test: a tolerance the float64 oracle first meets at iteration k <= 8 (the residual of CG started
+            # from x0 = b is not monotone) stops the kernel at the same k
             b = mask * y - mask * mu0
-            _, io5 = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=5)
-            _, io4 = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=4)
-            assert io5["residual_norm"] < io4["residual_norm"]
-            rtol = 0.5 * (io5["residual_norm"] + io4["residual_norm"]) / np.linalg.norm(b)
+            res = [fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=k)[1]["residual_norm"] for k in range(1, 9)]
+            k = 1 + int(np.argmin(res))                    # the first iteration that reaches the smallest residual of the eight
+            above = min(res[:k - 1]) if k > 1 else 2.0 * res[0]
+            rtol = 0.5 * (res[k - 1] + above) / np.linalg.norm(b)
             mat, info = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, rtol, maxiter=200)
-            assert info["niter"][0] == 5 and info["optimal"][0], info
-            mat5, _ = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=5)
-            assert rel_l2(mat, mat5) < 1e-6
+            assert info["niter"][0] == k and info["optimal"][0], (info, k, res)
+            matk, _ = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=k)
+            assert rel_l2(mat, matk) < 1e-6
 
 @pytest.mark.parametrize("which", ["motion_blur", "super_resolution"])
 def test_res64_non_separable_operators(E, assets, which, monkeypatch):

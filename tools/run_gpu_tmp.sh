@@ -1,3 +1,4 @@
 set -x
-python tools/dct_tf32_study.py > gpurun_out/dct_tf32_study_r02.json 2> gpurun_out/dct_tf32.err; cat gpurun_out/dct_tf32_study_r02.json | head -60; tail -3 gpurun_out/dct_tf32.err
-timeout 1500 python -m pytest tests/test_gpu_unit.py -m gpu -q 2>&1 | tail -5
+python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-unet-timing --batched 0 > gpurun_out/plain_bench.log 2>&1 &&
+timeout 800 ncu --metrics gpu__time_duration.sum --clock-control none -s 3300 -c 3400 --csv --log-file gpurun_out/ncu_launches_bench_r02.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-unet-timing --batched 0 > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-300; wc -l gpurun_out/ncu_launches_bench_r02.csv
