@@ -163,8 +163,9 @@ int fh_cg_solve(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev
 /* The same solve without any host read-back: returns once the work is queued on `stream`; the outcome of image b is
  * written to info_dev[b] (device memory) when its solve ends.  This is what lets a sampler run the whole guided loop
  * without a host synchronisation (the reference synchronises twice per CG iteration, cg.py:250,259).  Available where
- * the resident kernel applies (DCT basis, mask or separable blur, batch <= 4 unless FH_CG_RESIDENT is set); otherwise
- * FH_ESTATE -- use fh_cg_solve. */
+ * the resident kernel applies: DCT basis, all four operators (mask, separable blur, 2-D PSF, x4 super-resolution),
+ * batch <= 4 unless FH_CG_RESIDENT is set; otherwise FH_ESTATE -- use fh_cg_solve.  Float32 in and out; the arithmetic
+ * in between is that of fh_cg_solve_f64 unless FH_CG_RESIDENT_F32 is set (mask and separable blur only). */
 typedef struct { double residual_norm; int niter; int optimal; } fh_cg_info;
 int fh_cg_solve_async(fh_state* st, fh_op* op, const float* y_dev, const float* mu_dev, double sigma_y2, double rtol,
                       int maxiter, int fixed_iters, float* mat_out_dev, fh_cg_info* info_dev, void* stream);

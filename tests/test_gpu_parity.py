@@ -531,8 +531,9 @@ def test_mechanism_converged_vs_golden(assets):
     record("mechanism_converged", errs=errs, final=ef, niter=got_n.tolist(), ref_niter=ref_n.tolist(),
            k=mech.covariance_model.vector_count, fallback=[r["fallback"] for r in mech.log])
     assert mech.covariance_model.vector_count == int(g["k_final"])
-    assert ef < 1e-3
-    assert max(errs) < 5e-3
+    assert ef < 1e-4, ef                                               # north-star: final sample within 1e-4 (measured 5.8e-6)
+    assert max(errs) < 2e-4, errs                                      # every mechanism output (measured <= 7.7e-5)
+    assert abs(int(got_n.sum()) - int(ref_n.sum())) <= 0.02 * ref_n.sum(), (got_n, ref_n)     # round 1: 2900 vs 1928 on call 0
 
 
 def test_mechanism_default_rtol_runs(assets):
@@ -547,7 +548,10 @@ def test_mechanism_default_rtol_runs(assets):
     ef = rel_l2(sub(x), g["final"])
     record("mechanism_default", final=ef, niter=got_n.tolist(), ref_niter=ref_n.tolist(), first=rel_l2(outs[0], g["call0_out"]))
     assert mech.covariance_model.vector_count == int(g["k_final"])
-    assert np.all(np.abs(got_n - ref_n) <= np.maximum(5, 0.2 * ref_n)), (got_n, ref_n)
+    # call 0 (sigma = 80, condition number 1e6): the float64 solve stops where the reference stops and agrees with it
+    # (round 1, float32: 32 vs 27 iterations, rel-L2 0.80); later calls are loosely converged and chaotic (module docstring)
+    assert got_n[0] == ref_n[0] and rel_l2(outs[0], g["call0_out"]) < 1e-3, (got_n[0], ref_n[0])
+    assert np.all(np.abs(got_n - ref_n) <= np.maximum(2, 0.05 * ref_n)), (got_n, ref_n)
     assert ef < 5e-2
 
 

@@ -25,12 +25,12 @@ def main():
         r = json.loads(line)
         if r.get("device") != "cuda":
             continue
-        key = "/".join(str(r[k]) for k in ("test", "op", "mode", "iters", "sigma") if k in r)
-        rows[key] = {k: v for k, v in r.items() if k not in ("test", "device", "op", "mode")}
+        key = "/".join(str(r[k]) for k in ("test", "cfg", "op", "mode", "iters", "sigma", "dct") if k in r)
+        rows[key] = {k: v for k, v in r.items() if k not in ("test", "device", "op", "mode", "cfg", "errs") and not (k in ("niter", "ref_niter") and isinstance(v, list) and len(v) > 20)}
     with open(out, "w") as f:
         f.write(f"# {title}\n\nFrom `{src}` (tests/helpers.py::record): relative L2 errors of the CUDA path (through the C ABI, 3x256x256) "
                 "against oracle/fh_oracle.py (float64 / complex128) and the golden vectors produced by the real reference.  "
-                "`mode` = CG implementation (`auto`: resident kernel for the foldable operators, `streaming`: five launches per iteration).\n\n"
+                "`mode` = CG implementation (`auto`: float64 resident kernel fh_k_cg_res64, `streaming`: float32 five-launch iteration, `resident_f32`: the float32 resident kernel of round 1).\n\n"
                 "| test | values |\n|---|---|\n")
         for k, v in rows.items():
             f.write(f"| {k} | " + ", ".join(f"{a}={fmt(b)}" for a, b in v.items()) + " |\n")
