@@ -30,6 +30,7 @@ _SIGNATURES = {
     "fh_ctx_destroy": (c_int, [c_void_p]),
     "fh_ctx_set_cg_mode": (c_int, [c_void_p, c_int]),
     "fh_ctx_cg_last_mode": (c_int, [c_void_p]),
+    "fh_ctx_fused_updates": (c_int, [c_void_p]),
     "fh_dct2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "fh_state_create": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int]),
     "fh_state_destroy": (c_int, [c_void_p]),

@@ -7,6 +7,7 @@
 #include "fh_cg.cuh"
 #include "fh_cg_resident.cuh"
 #include "fh_cg_res64.cuh"
+#include "fh_upd64.cuh"
 #include "fh_mech.cuh"
 
 #include <math.h>
@@ -140,6 +141,9 @@ struct fh_ctx {
   double* d64_y;                      // (max_batch, d) widened y of the float32 entry points
   int r64_smem_max;                   // opt-in shared memory per block: the float64 kernel's Z capacity is what its fixed part, tables and gather staging leave
   int r64_ok;
+  // fused covariance updates (fh_upd64.cuh): one cooperative launch per update and image
+  double *upd_gpart, *upd_K, *upd_dpart;
+  int upd_ok, upd_cap, upd_smem;      // the grid (strips + 2 core CTAs) fits; rows of Z resident per CTA; dynamic shared memory
 };
 
 struct fh_state {
@@ -263,6 +267,12 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
     FH_CUDA(cudaMalloc((void**)&c->d64_out, (size_t)max_batch * c->d * sizeof(double)));
     FH_CUDA(cudaMalloc((void**)&c->d64_y, (size_t)max_batch * c->d * sizeof(double)));
     c->r64_smem_max = 227 * 1024; c->r64_ok = c->res_ok;
+    const size_t nstrip = (size_t)channels * FH_R64_CPP;
+    FH_CUDA(cudaMalloc((void**)&c->upd_gpart, 2 * nstrip * FH_U64_CP * FH_U64_NBLK2 * 64 * sizeof(double)));
+    FH_CUDA(cudaMalloc((void**)&c->upd_K, 2 * (size_t)FH_U64_LD * FH_U64_LD * sizeof(double)));
+    FH_CUDA(cudaMalloc((void**)&c->upd_dpart, nstrip * FH_U64_DP * sizeof(double)));
+    FH_CUDA(cudaMemset(c->upd_dpart, 0, nstrip * FH_U64_DP * sizeof(double)));
+    c->upd_ok = 0; c->upd_cap = 0; c->upd_smem = 0;
   }
   c->trace = nullptr;
   if (getenv("FH_TRACE")) { FH_CUDA(cudaMalloc((void**)&c->trace, 8 * 16 * sizeof(long long))); FH_CUDA(cudaMemset(c->trace, 0, 8 * 16 * sizeof(long long))); }
@@ -308,11 +318,26 @@ extern "C" int fh_ctx_create(fh_ctx** out, int device, int max_batch, int channe
       FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e, fh_k_cg_res64<true, false>, FH_PASS_THREADS, smem_max));
       c->r64_ok = ((long)channels * FH_R64_CPP <= (long)std::min(std::min(a, b), e) * c->sms) ? 1 : 0;
     }
+    if (c->r64_ok) {
+      // fused updates: strips + 2 core CTAs, one CTA per SM; the kernel's static shared memory (Gauss-Jordan staging) counts
+      cudaFuncAttributes fa;
+      FH_CUDA(cudaFuncGetAttributes(&fa, fh_k_upd64));
+      const int room = smem_max - (int)fa.sharedSizeBytes;
+      FH_CUDA(cudaFuncSetAttribute(fh_k_upd64, cudaFuncAttributeMaxDynamicSharedMemorySize, room));
+      c->upd_cap = std::max(0, std::min(FH_RES_MAXM, (room - (int)sizeof(FhRes64Smem)) / (FH_RES_SLICE * (int)sizeof(float))));
+      c->upd_smem = room;
+      int per = 0;
+      FH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fh_k_upd64, FH_PASS_THREADS, room));
+      c->upd_ok = (room >= (int)sizeof(FhUpd64Core) && room >= (int)sizeof(FhRes64Smem) && (long)channels * FH_R64_CPP + 2 <= (long)per * c->sms) ? 1 : 0;
+    }
   }
 #else
   c->res_ok = (height == FH_N && width == FH_N && ((long)channels * height) % FH_RES_ROWS == 0) ? 1 : 0;
   c->r64_ok = c->res_ok;
   if (const char* e = getenv("FH_EMU_R64_SMEM")) c->r64_smem_max = atoi(e);      // CPU emulation: the test shrinks the shared memory to reach the L2 / L1 variants at small rank
+  c->upd_ok = c->r64_ok;
+  c->upd_smem = std::max(c->r64_smem_max, (int)sizeof(FhUpd64Core));
+  c->upd_cap = std::max(0, std::min(FH_RES_MAXM, (c->r64_smem_max - (int)sizeof(FhRes64Smem)) / (FH_RES_SLICE * (int)sizeof(float))));
 #endif
   *out = c;
   return FH_OK;
@@ -324,6 +349,7 @@ extern "C" int fh_ctx_set_cg_mode(fh_ctx* c, int mode) {
   return FH_OK;
 }
 extern "C" int fh_ctx_cg_last_mode(const fh_ctx* c) { return c ? c->cg_last_mode : FH_EINVAL; }
+extern "C" int fh_ctx_fused_updates(const fh_ctx* c) { return c ? c->upd_ok : FH_EINVAL; }
 
 // Debug: copies the 8 x 16 clock64 checkpoints recorded by CTA 0 of the fused CG kernels (FH_TRACE=1) to the host.
 extern "C" int fh_trace_read(fh_ctx* c, long long* out_host) {
@@ -341,6 +367,7 @@ extern "C" int fh_ctx_destroy(fh_ctx* c) {
   for (int i = 0; i < 7; ++i) cudaFree(c->scratch[i]);
   for (int i = 0; i < 6; ++i) cudaFree(c->cgv[i]);
   cudaFree(c->Gtmp); cudaFree(c->strip_dots); cudaFree(c->trace); cudaFree(c->res_ll); cudaFree(c->grid_counter);
+  cudaFree(c->upd_gpart); cudaFree(c->upd_K); cudaFree(c->upd_dpart);
   cudaFree(c->dot_partial); cudaFree(c->csum); cudaFree(c->coef); cudaFree(c->gram_partial); cudaFree(c->gramK);
   cudaFree(c->tw64); cudaFree(c->e512);
   for (int i = 0; i < 2; ++i) { cudaFree(c->r64_T[i]); cudaFree(c->r64_ride[i]); }
@@ -664,13 +691,95 @@ extern "C" int fh_time_update(fh_state* s, const float* x, const float* score, d
   return from_basis(s, c->scratch[3], mean_out, stream);
 }
 
+// ---- fused covariance updates (fh_upd64.cuh): one cooperative launch per update and image --------------------------------
+// Applies to the DCT basis on a device whose SMs hold the strips plus two core CTAs; batches above 4 images keep the
+// batched multi-launch path (its launches cover the whole batch at once).  FH_UPD_LEGACY=1 forces the old path (A/B runs).
+static bool upd64_applies(const fh_state* s) {
+  const char* e = getenv("FH_UPD_LEGACY");                   // read per call: the tests switch it inside one process
+  const int legacy = e ? atoi(e) : 0;
+  const fh_ctx* c = s->ctx;
+  return !legacy && c->upd_ok && s->basis == FH_BASIS_DCT && s->B <= 4;
+}
+static int launch_upd64(fh_ctx* c, FhUpd64 U, int image, cudaStream_t st) {
+  const dim3 grid((unsigned)(c->C * FH_R64_CPP + 2)), block(FH_PASS_THREADS);
+  U.C = c->C; U.d = c->d; U.mr_cap = c->upd_cap;
+  U.T[0] = c->r64_T[0]; U.T[1] = c->r64_T[1];
+  U.gpart = c->upd_gpart; U.K = c->upd_K; U.dpart = c->upd_dpart; U.coef = c->coef + (size_t)image * FH_MAXM;
+  U.status = c->status; U.tw = c->tw64; U.e512 = c->e512;
+  U.grid_counter = c->grid_counter + image;
+  FH_CUDA(cudaMemsetAsync(U.grid_counter, 0, sizeof(unsigned), st));
+  const size_t strip = sizeof(FhRes64Smem) + (size_t)std::min(U.m, c->upd_cap) * FH_RES_SLICE * sizeof(float);
+  const size_t smem = std::max(strip, sizeof(FhUpd64Core));
+  if ((int)smem > c->upd_smem) FH_FAIL(FH_ESTATE, "fused update does not fit shared memory");
+#ifdef FH_EMU
+  emu::launch_coop([&] { fh_k_upd64(U); }, grid, block, smem);
+  ++fh_g_launches;
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (fh_g_prof_on) fh_prof_begin(U.mode == 1 ? "fh_k_upd64(time)" : "fh_k_upd64(space)", st);
+  FH_CUDA(cudaLaunchKernelEx(&cfg, fh_k_upd64, U));
+  if (fh_g_prof_on) fh_prof_end(st);
+  ++fh_g_launches;
+#endif
+  return FH_OK;
+}
+static FhUpd64 upd64_state(fh_state* s, int b) {
+  FhUpd64 U{};
+  U.m = s->m;
+  U.pi = s->pi + (size_t)b * s->d; U.delta = s->delta + (size_t)b * s->d; U.Z = s->Z + (size_t)b * FH_MAXM * s->d;
+  U.Gz = s->Gz + (size_t)b * FH_MAXM * FH_MAXM; U.Gs = s->Gs + (size_t)b * FH_MAXM * FH_MAXM;
+  return U;
+}
+// time update of every image: score = score_in, or (mean_prev - x) / sigma_t^2 when mean_prev is given
+static int time_update_fused(fh_state* s, const double* x, const double* mean_prev, const double* score_in, double sigma_t, double sigma_tnext,
+                             double* mean_out, double* score_out, void* stream) {
+  // the bookkeeping of fh_time_update: Sigma side at the exact new sigma, Hessian side with the reference's float32-rounded shift
+  s->sig2 = sigma_tnext * sigma_tnext;
+  const double var2_old = s->var2;
+  s->var2 = var2_old + (double)(float)(sigma_tnext * sigma_tnext - sigma_t * sigma_t);
+  if (!(s->var2 > 0)) FH_FAIL(FH_ESTATE, "non-positive effective variance after time update");
+  const bool consistent = fabs(s->var2 - s->sig2) <= 1e-7 * s->sig2;
+  for (int b = 0; b < s->B; ++b) {
+    FhUpd64 U = upd64_state(s, b);
+    U.mode = 1; U.consistent = consistent ? 1 : 0;
+    U.x_prev = x + (size_t)b * s->d;
+    U.mean_prev = mean_prev ? mean_prev + (size_t)b * s->d : nullptr;
+    U.score_in = score_in ? score_in + (size_t)b * s->d : nullptr;
+    U.sig2_t = sigma_t * sigma_t; U.var2_old = var2_old; U.var2_new = s->var2; U.sig2_new = s->sig2;
+    U.mean_out = mean_out + (size_t)b * s->d; U.score_out = score_out + (size_t)b * s->d;
+    int rc = launch_upd64(s->ctx, U, b, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return FH_OK;
+}
+static int space_update_fused(fh_state* s, const double* mean_at_x, const double* mean_at_xnext, double sigma_t, const double* x,
+                              const double* xnext, void* stream) {
+  s->var2 = sigma_t * sigma_t;                 // H is rebuilt from Sigma at the true sigma (online_update_bfgs.py:294)
+  for (int b = 0; b < s->B; ++b) {
+    FhUpd64 U = upd64_state(s, b);
+    U.mode = 2; U.sig2 = sigma_t * sigma_t;
+    U.x = x + (size_t)b * s->d; U.xnext = xnext + (size_t)b * s->d;
+    U.mean_at_x = mean_at_x + (size_t)b * s->d; U.mean_at_xnext = mean_at_xnext + (size_t)b * s->d;
+    int rc = launch_upd64(s->ctx, U, b, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  s->m += 2;
+  return FH_OK;
+}
+
 // update_time_step with float64 in and out: the transfer itself runs in the float32 state (DCT, low-rank algebra), but the
 // result mu' = x + sigma'^2 s' is formed in float64 from the float64 x (|x| ~ sigma >> |mu'|: a float32 x would put its
 // rounding error, 6e-8 |x|, straight into mu').
 extern "C" int fh_time_update_f64(fh_state* s, const double* x, const double* score, double sigma_t, double sigma_tnext,
                                   int only_cov, double* mean_out, double* score_out, void* stream) {
   if (only_cov) return fh_time_update(s, nullptr, nullptr, sigma_t, sigma_tnext, 1, nullptr, nullptr, stream);
-  if (!s || !x || !score || !mean_out || !score_out) FH_FAIL(FH_EINVAL, "bad fh_time_update_f64 arguments");
+  if (!s || !x || !score || !mean_out || !score_out || !(sigma_t > 0) || !(sigma_tnext > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update_f64 arguments");
+  if (upd64_applies(s)) return time_update_fused(s, x, nullptr, score, sigma_t, sigma_tnext, mean_out, score_out, stream);
   fh_ctx* c = s->ctx;
   const long tot = (long)s->B * s->d;
   const dim3 g((unsigned)((tot + 255) / 256)), b(256);
@@ -767,6 +876,7 @@ extern "C" int fh_space_update_f64(fh_state* s, const double* mean_at_x, const d
                                    const double* x, const double* xnext, int project_to_diagonal, void* stream) {
   if (!s || !mean_at_x || !mean_at_xnext || !x || !xnext || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_space_update_f64 arguments");
   if (!project_to_diagonal && s->m + 2 > FH_MAXM) FH_FAIL(FH_ERANK, "low-rank capacity %d exhausted", FH_MAXM);
+  if (!project_to_diagonal && upd64_applies(s)) return space_update_fused(s, mean_at_x, mean_at_xnext, sigma_t, x, xnext, stream);
   fh_ctx* c = s->ctx;
   const long tot = (long)s->B * s->d;
   FH_LAUNCH(fh_k_su_diffs64, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, stream, x, xnext, mean_at_x, mean_at_xnext, sigma_t * sigma_t,
@@ -1749,7 +1859,8 @@ extern "C" int fh_mech_allclose(fh_ctx* c, const double* a, const double* b, int
 // update_time_step fed with the previous evaluation itself: score_prev = (mean_prev - x_prev) / sigma_t^2 (conditioning_mechanisms.py:243)
 extern "C" int fh_time_update_from_mean(fh_state* s, const double* x_prev, const double* mean_prev, double sigma_t, double sigma_tnext,
                                         double* mean_out, double* score_out, void* stream) {
-  if (!s || !x_prev || !mean_prev || !mean_out || !score_out || !(sigma_t > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update_from_mean arguments");
+  if (!s || !x_prev || !mean_prev || !mean_out || !score_out || !(sigma_t > 0) || !(sigma_tnext > 0)) FH_FAIL(FH_EINVAL, "bad fh_time_update_from_mean arguments");
+  if (upd64_applies(s)) return time_update_fused(s, x_prev, mean_prev, nullptr, sigma_t, sigma_tnext, mean_out, score_out, stream);
   fh_ctx* c = s->ctx;
   const long tot = (long)s->B * s->d;
   const dim3 g((unsigned)((tot + 255) / 256)), b(256);

@@ -92,6 +92,10 @@ class Context:
     def cg_last_mode(self):
         return _lib.lib().fh_ctx_cg_last_mode(self._h)
 
+    @property
+    def fused_updates_available(self):
+        return _lib.lib().fh_ctx_fused_updates(self._h) == 1
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().fh_ctx_destroy(self._h)

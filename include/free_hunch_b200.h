@@ -59,6 +59,10 @@ int fh_ctx_destroy(fh_ctx* ctx);
 #define FH_CG_RESIDENT_F32 3 /* the float32 predecessor of the resident kernel (kept for comparison; not a parity path) */
 int fh_ctx_set_cg_mode(fh_ctx* ctx, int mode);
 int fh_ctx_cg_last_mode(const fh_ctx* ctx); /* FH_CG_STREAMING or FH_CG_RESIDENT: path of the last DCT-basis solve */
+/* 1 when the float64 entry points of the covariance updates (fh_time_update_f64, fh_time_update_from_mean,
+ * fh_space_update_f64; online_update_bfgs.py:153-192, :247-312) run as ONE cooperative launch per update and image
+ * (DCT basis, at most 4 images per state, a device with one SM per 6-row strip plus two); 0: the multi-launch path. */
+int fh_ctx_fused_updates(const fh_ctx* ctx);
 
 /* Orthonormal 2-D DCT-II (inverse=0) / DCT-III (inverse=1) of `nplanes` 256x256 planes.
  * Replaces torch_dct.dct_2d / idct_2d(norm='ortho'), call sites online_update_bfgs.py:352-374. */

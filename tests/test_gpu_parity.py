@@ -702,3 +702,70 @@ def test_mechanism_other_operators_vs_oracle(assets, which, solver):
         assert [r["space_update"] for r in mech.log] == [r["space_update"] for r in om.log]
     record("mechanism_other_ops", op=which, solver=solver, final=errs, niter=[r["niter"] for r in mech.log], k=mech.covariance_model.vector_count)
     assert max(errs) < 1e-3, errs
+
+
+# ---------------------------------------------------------------------------------------------- fused covariance updates
+def _update_sequence(E, ctx, assets, from_mean, n_max=99):
+    """Time + space updates on the sigma grid of the reference golden (tests/golden/full_size.npz, the sequence of
+    `full_state`); every op continues from the oracle's mean.  (Longer synthetic sequences are no test: without the
+    mechanism's thresholds dx.de turns negative after ~7 closely spaced updates and two float64 implementations of the
+    reference's own algebra -- oracle/fh_oracle.py and tests/algorithm_model.py -- disagree by O(1) from there on.  Ranks
+    32 and 56 are covered through the mechanism in tests/test_gpu_configs.py.)"""
+    var = assets["dct_variance"]
+    sig = list(H.np.load(H.ROOT + "/tests/golden/full_size.npz")["sigmas"])[:n_max + 1]
+    st = E.CovState(ctx, 1, E.BASIS_DCT)
+    st.init(tt(var), S0 ** 2)
+    ora = fo.CovarianceOracleDCT(var, S0 ** 2, var.size)
+    den = lambda x, s: fo.idct2(var.astype(np.float64) / (var + s ** 2) * fo.dct2(x)) + 0.02 * np.tanh(x)
+    w = make_inputs(21, SHAPE)
+    x = synth_image(var, 6) + S0 * make_inputs(22, SHAPE)
+    errs = dict(mean=[], score=[], sigv=[])
+    for i in range(1, len(sig)):
+        s_prev, s = sig[i - 1], sig[i]
+        mu_prev = den(x, s_prev)
+        xn = x + (s - s_prev) * (x - mu_prev) / s_prev + 0.02 * s * make_inputs(400 + i, SHAPE)
+        if s != s_prev:
+            score = (mu_prev - x) / s_prev ** 2
+            if from_mean:
+                mean, sc = st.time_update_from_mean(tt(x), tt(mu_prev), s_prev, s)
+            else:
+                mean, sc = st.time_update(tt(x), tt(score), s_prev, s)
+            mo, so = ora.update_time_step(x, s_prev, s, score)
+            errs["mean"].append(rel_l2(mean, mo))
+            errs["score"].append(rel_l2(sc, so))
+        else:
+            mo = mu_prev
+        mun = den(xn, s)
+        st.space_update(tt(mo), tt(mun), s, tt(x), tt(xn))
+        ora.update_space_step(mo, mun, s, x, xn)
+        errs["sigv"].append(rel_l2(st.cov_dot(tt(w)), ora.denoiser_cov_vector_dot(w)))
+        x = xn
+    assert st.rank == 2 * (len(sig) - 1)
+    return errs
+
+
+def test_fused_updates_vs_oracle_and_multi_launch_path(E, ctx, assets, monkeypatch):
+    """fh_k_upd64: one cooperative launch per update, float64 transfer -- against the oracle, and against the multi-launch
+    float32 path it replaces (FH_UPD_LEGACY=1, what batches above 4 images still take)."""
+    if not ctx.fused_updates_available:
+        pytest.skip("fused updates need one SM per strip plus two")
+    n0 = E.launch_count()
+    fused = _update_sequence(E, ctx, assets, from_mean=True)
+    n_fused = E.launch_count() - n0
+    monkeypatch.setenv("FH_UPD_LEGACY", "1")
+    n0 = E.launch_count()
+    legacy = _update_sequence(E, ctx, assets, from_mean=True)
+    n_legacy = E.launch_count() - n0
+    monkeypatch.delenv("FH_UPD_LEGACY")
+    record("fused_updates", launches_fused=n_fused, launches_legacy=n_legacy,
+           **{f"fused_{k}": max(v) for k, v in fused.items()}, **{f"legacy_{k}": max(v) for k, v in legacy.items()})
+    for k, v in fused.items():
+        assert max(v) < 1e-4, (k, v)
+    assert n_fused < n_legacy / 3
+    assert max(fused["mean"]) <= 2 * max(legacy["mean"]) + 1e-7
+
+
+def test_fused_time_update_score_entry(E, ctx, assets):
+    errs = _update_sequence(E, ctx, assets, from_mean=False, n_max=3)
+    for k, v in errs.items():
+        assert max(v) < 1e-4, (k, v)

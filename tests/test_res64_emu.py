@@ -117,3 +117,48 @@ def test_res64_non_separable_operators(E, assets, which, monkeypatch):
     mat_cpu, io = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=2)
     assert rel_l2(mat, mat_cpu) < 1e-6, (which, rel_l2(mat, mat_cpu))
     assert abs(info["residual_norm"][0] - io["residual_norm"]) <= 1e-6 * io["residual_norm"]
+
+
+@pytest.mark.parametrize("variant", ["tables in shared memory", "rows from L2"])
+def test_fused_updates_vs_oracle(E, assets, variant, monkeypatch):
+    """fh_k_upd64 (fh_upd64.cuh): the time and space updates as one cooperative launch each, float64 transfer.  Mean and score
+    of every time update against the oracle (update_time_step, online_update_bfgs.py:153-192) at ranks 0, 2 and 4, Sigma.v
+    after every space update, and two time updates in a row at small sigma, where the reference's float32-rounded shift of
+    diag(H^-1) (:172) makes the Hessian-side variance drift from the Sigma-side one (second core CTA)."""
+    if SMEM[variant]:
+        monkeypatch.setenv("FH_EMU_R64_SMEM", str(SMEM[variant]))
+    rs = np.random.RandomState(11)
+    var = assets["dct_variance"]
+    shape = (1,) + var.shape
+    sig = [80.2878, 8.463, 1.31, 0.052, 0.0211, 0.0093]
+    ctx = E.Context("cpu", max_batch=1)
+    st = E.CovState(ctx, 1, E.BASIS_DCT)
+    st.init(torch.tensor(var), sig[0] ** 2)
+    ora = fo.CovarianceOracleDCT(var, sig[0] ** 2, var.size)
+    den0 = fo.analytic_dct_gaussian_denoiser(var)
+    den = lambda x, s: den0(x, s)[0] + 0.02 * np.tanh(x)
+    w = rs.standard_normal(shape)
+    x = rs.standard_normal(shape) * sig[0]
+    n0 = E.launch_count()
+    for i in range(1, len(sig)):
+        s_prev, s = sig[i - 1], sig[i]
+        mu_prev = den(x, s_prev)
+        if i % 2:
+            mean, sc = st.time_update(torch.tensor(x), torch.tensor((mu_prev - x) / s_prev ** 2), s_prev, s)
+        else:
+            mean, sc = st.time_update_from_mean(torch.tensor(x), torch.tensor(mu_prev), s_prev, s)
+        mo, so = ora.update_time_step(x, s_prev, s, (mu_prev - x) / s_prev ** 2)
+        assert rel_l2(mean, mo) < 1e-6 and rel_l2(sc, so) < 1e-6, (i, rel_l2(mean, mo), rel_l2(sc, so))
+        if i >= 4:
+            continue                                     # time updates only: var2 accumulates float32-rounded shifts
+        xn = x + (s - s_prev) * (x - mu_prev) / s_prev + 0.02 * s * rs.standard_normal(shape)
+        mun = den(xn, s)
+        st.space_update(torch.tensor(mo), torch.tensor(mun), s, torch.tensor(x), torch.tensor(xn))
+        ora.update_space_step(mo, mun, s, x, xn)
+        assert st.rank == 2 * i
+        e = rel_l2(st.cov_dot(torch.tensor(w)), ora.denoiser_cov_vector_dot(w))
+        assert e < 1e-6, (i, e)
+        x = xn
+    # one launch (+ the barrier counter's memset, not a launch) per update; 3 Sigma.v launches
+    assert E.launch_count() - n0 == 5 + 3 + 3, E.launch_count() - n0
+    assert rel_l2(st.cov_dot(torch.tensor(w)), ora.denoiser_cov_vector_dot(w)) < 1e-6
