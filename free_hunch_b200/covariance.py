@@ -202,3 +202,41 @@ class CovarianceHessianBFGSDCT(CovarianceHessianBFGS):
 
     def inverse_transform(self, x):
         return self.ctx.dct2(x, inverse=True)
+
+
+class DCTVarianceAccumulator:
+    """The prior the DCT-basis model starts from: per-coefficient variance of the orthonormal 2-D DCT over a set of images
+    (do_frequency_analysis.py:26-72, which writes `dct_variance.pt`).  Batches of (N, 3, 256, 256) images in [-1, 1] go through
+    `fh_dct2` on the device; the sums of the coefficients and of their squares are kept on the device in float64 (the
+    reference sums in float32 on the CPU; over its 500 images the two agree to float32 rounding).
+    variance() = E[c^2] - E[c]^2 as float32, `save(data_dir)` writes the file CovarianceHessianBFGSDCT loads."""
+
+    def __init__(self, ctx, image_shape=(3, 256, 256)):
+        self.ctx = ctx
+        self.sum = torch.zeros(image_shape, dtype=torch.float64, device=ctx.device)
+        self.sum_sq = torch.zeros_like(self.sum)
+        self.count = 0
+
+    def update(self, images, limit=None):
+        """Adds a batch; with `limit`, only as many images as keep the total at or below it (:36-39).  Returns the total."""
+        if limit is not None:
+            images = images[: max(0, int(limit) - self.count)]
+        if images.shape[0] == 0:
+            return self.count
+        c = self.ctx.dct2(images.to(torch.float32)).to(torch.float64)
+        self.sum += c.sum(dim=0)
+        self.sum_sq += (c * c).sum(dim=0)
+        self.count += int(images.shape[0])
+        return self.count
+
+    def variance(self):
+        if self.count == 0:
+            raise ValueError("no images accumulated")
+        mean = self.sum / self.count
+        return (self.sum_sq / self.count - mean * mean).to(torch.float32)
+
+    def save(self, data_dir):
+        os.makedirs(data_dir, exist_ok=True)
+        path = os.path.join(data_dir, "dct_variance.pt")
+        torch.save(self.variance().cpu(), path)
+        return path
