@@ -131,6 +131,62 @@ class ADMUNet(nn.Module):
         if not randomize_output:
             nn.init.zeros_(self.out_conv.weight); nn.init.zeros_(self.out_conv.bias)
 
+    def load_reference_state_dict(self, sd, legacy_attention_order=True):
+        """Loads a state dict of the reference's UNetModel (training/openai_unet.py:395-686; the published ADM / DPS
+        checkpoints have this layout).  Key map: input_blocks.N.{0,1} -> down[N].{block,attn}; middle_block.{0,1,2} ->
+        mid[0].block, mid[0].attn, mid[1].block; output_blocks.N.j -> the j-th module of up[N] in the order ResBlock,
+        attention, up-sampling ResBlock; inside a ResBlock in_layers.{0,2} / emb_layers.1 / out_layers.{0,3} /
+        skip_connection -> norm1, conv1 / emb / norm2, conv2 / skip; proj_out -> proj; out.{0,2} -> out_norm, out_conv.
+        The reference's default QKVAttentionLegacy (:327-353) lays the 3C rows of `qkv` out as [head][q,k,v][channel];
+        this class uses [q,k,v][head][channel], so the rows are permuted on the way in."""
+        res_map = {"in_layers.0": "norm1", "in_layers.2": "conv1", "emb_layers.1": "emb", "out_layers.0": "norm2",
+                   "out_layers.3": "conv2", "skip_connection": "skip"}
+
+        def sub(prefix):
+            return {k[len(prefix):]: torch.as_tensor(v) for k, v in sd.items() if k.startswith(prefix)}
+
+        def load_module(mod, prefix):
+            part = sub(prefix)
+            if isinstance(mod, ResBlock):
+                out = {}
+                for k, v in part.items():
+                    head, leaf = k.rsplit(".", 1)
+                    out[f"{res_map[head]}.{leaf}"] = v
+                part = out
+            elif isinstance(mod, AttentionBlock):
+                out = {}
+                for k, v in part.items():
+                    k = k.replace("proj_out.", "proj.")
+                    if k.startswith("qkv.") and legacy_attention_order:
+                        c = v.shape[0] // 3
+                        v = v.reshape(mod.heads, 3, c // mod.heads, *v.shape[1:]).transpose(0, 1).reshape(v.shape)
+                    out[k] = v
+                part = out
+            mod.load_state_dict(part, strict=True)
+            return len(part)
+
+        used = load_module(self.time_embed, "time_embed.")
+        for n, st in enumerate(self.down):
+            used += load_module(st.block, f"input_blocks.{n}.0.")
+            if st.attn is not None:
+                used += load_module(st.attn, f"input_blocks.{n}.1.")
+        used += load_module(self.mid[0].block, "middle_block.0.")
+        used += load_module(self.mid[0].attn, "middle_block.1.")
+        used += load_module(self.mid[1].block, "middle_block.2.")
+        for n, stages in enumerate(self.up):
+            j = 0
+            for st in stages:
+                used += load_module(st.block, f"output_blocks.{n}.{j}.")
+                j += 1
+                if st.attn is not None:
+                    used += load_module(st.attn, f"output_blocks.{n}.{j}.")
+                    j += 1
+        used += load_module(self.out_norm, "out.0.")
+        used += load_module(self.out_conv, "out.2.")
+        if used != len(sd):
+            raise KeyError(f"reference state dict has {len(sd)} entries, {used} were consumed")
+        return self
+
     def forward(self, x, timesteps):
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(x.dtype))
         hs, h = [], x
