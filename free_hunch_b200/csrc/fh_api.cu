@@ -154,6 +154,9 @@ struct fh_state {
   double sig2;                        // sigma^2 of the Sigma side (exact: the reference's Sigma^-1 shifts are ~1e-7 accurate)
   float *pi, *delta, *Z;              // (B,d), (B,d), (B,FH_MAXM,d)
   double *Gz, *Gs;                    // (B,FH_MAXM,FH_MAXM)
+  int* hint;                          // (B) iterations of each image's previous float64 CG solve on this state, 0 after init: the next
+                                      // solve reads it to choose its arithmetic path (Zt mode of fh_k_cg_res64) -- a function of the
+                                      // state's own history, so a batch and its images solved one by one take the same path
 };
 
 struct fh_op {
@@ -445,7 +448,7 @@ extern "C" int fh_dct2(fh_ctx* c, const float* in, float* out, int nplanes, int 
 
 // ------------------------------------------------------------------------------------------- state
 static void state_free_buffers(fh_state* p) {
-  cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs);
+  cudaFree(p->pi); cudaFree(p->delta); cudaFree(p->Z); cudaFree(p->Gz); cudaFree(p->Gs); cudaFree(p->hint);
   free(p);
 }
 // A pool slot for a state of `batch` images: a free one, else one parked for a different batch size (evicted).
@@ -463,6 +466,8 @@ static int state_alloc(fh_ctx* c, fh_state* s, int batch) {
   FH_CUDA(cudaMalloc((void**)&s->Z, (size_t)batch * c->max_rank * c->d * sizeof(float) + 16));
   FH_CUDA(cudaMalloc((void**)&s->Gz, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
   FH_CUDA(cudaMalloc((void**)&s->Gs, (size_t)batch * FH_MAXM * FH_MAXM * sizeof(double)));
+  FH_CUDA(cudaMalloc((void**)&s->hint, (size_t)batch * sizeof(int)));
+  FH_CUDA(cudaMemset(s->hint, 0, (size_t)batch * sizeof(int)));
   return FH_OK;
 }
 
@@ -475,7 +480,7 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
     fh_state* p = c->state_pool[i];
     if (p && p->B == batch) {                               // reuse the buffers of a destroyed state (no cudaMalloc)
       c->state_pool[i] = nullptr;
-      s->pi = p->pi; s->delta = p->delta; s->Z = p->Z; s->Gz = p->Gz; s->Gs = p->Gs;
+      s->pi = p->pi; s->delta = p->delta; s->Z = p->Z; s->Gz = p->Gz; s->Gs = p->Gs; s->hint = p->hint;
       free(p);
       *out = s;
       return FH_OK;
@@ -575,6 +580,7 @@ extern "C" int fh_state_init(fh_state* s, const float* var_dev, double init_nois
   FH_KCHECK();
   FH_CUDA(cudaMemsetAsync(s->Gz, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
   FH_CUDA(cudaMemsetAsync(s->Gs, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  FH_CUDA(cudaMemsetAsync(s->hint, 0, (size_t)s->B * sizeof(int), (cudaStream_t)stream));
   return refresh_delta(s, stream);
 }
 
@@ -1322,6 +1328,10 @@ static int launch_res64(fh_ctx* c, const FhCgFused& P, FhCgRes64 R, cudaStream_t
   R.ll_dots = c->res_ll + 2 * half;
   R.ll_sum = R.ll_dots + FH_MAXM * nblk;
   R.tw = c->tw64; R.e512 = c->e512;
+  {
+    const char* e = getenv("FH_R64_ZT");              // 0: never, 1: always, 2 (default): from the previous solve's iteration count
+    R.zt_mode = e ? atoi(e) : 2;                     // R.niter_hint: set by the caller from the state
+  }
   const unsigned need = (unsigned)P.last_allowed + 3u;
   if (c->res_seq > 0xffffffffu - need - 1u) {
     FH_CUDA(cudaMemsetAsync(c->res_ll, 0, c->res_ll_bytes, st));
@@ -1342,7 +1352,12 @@ static int launch_res64(fh_ctx* c, const FhCgFused& P, FhCgRes64 R, cudaStream_t
   const bool tabs = P.m <= cap_tabs;
   const bool big = !tabs && P.m > cap;
   R.mr_cap = cap;
-  const size_t smem = sizeof(FhRes64Smem) + (tabs ? sizeof(FhRes64Tabs) : 0) + (size_t)R.gen.gbuf_bytes + (size_t)std::min(P.m, cap) * slice;
+  // Zt mode with float64 rows: twice the slots, while they fit beside the tables (rank <= 15)
+  bool allow_wide = true;                            // FH_R64_ZT=3 / 4: modes 2 / 1 with float32 rows at every rank (A/B runs)
+  if (R.zt_mode == 3) { R.zt_mode = 2; allow_wide = false; } else if (R.zt_mode == 4) { R.zt_mode = 1; allow_wide = false; }
+  R.zt_wide = (allow_wide && R.zt_mode != 0 && !R.apply_only && P.m > 0 && 2 * P.m <= cap_tabs && 2 * P.m <= FH_RES_MAXM) ? 1 : 0;
+  const size_t smem = sizeof(FhRes64Smem) + (tabs ? sizeof(FhRes64Tabs) : 0) + (size_t)R.gen.gbuf_bytes +
+                      (size_t)(R.zt_wide ? 2 * P.m : std::min(P.m, cap)) * slice;
 #ifdef FH_EMU
   (void)st;
   if (tabs) emu::launch_coop([&] { fh_k_cg_res64<false, true>(P, R); }, grid, block, smem);
@@ -1425,7 +1440,7 @@ static int cg_solve_res64(fh_state* s, fh_op* o, FhCgFused P, const double* y, c
     FhCgRes64 R{};
     R.gen = gen;
     R.bvec = bv + (size_t)b * n; R.x_out = xout + (size_t)b * n;
-    R.rtol = rtol; R.atol = 0.0; R.sy2 = sigma_y2; R.use_stop = use_stop; R.image = b;
+    R.rtol = rtol; R.atol = 0.0; R.sy2 = sigma_y2; R.use_stop = use_stop; R.image = b; R.niter_hint = s->hint + b;
     R.info_out = info_dev ? info_dev + b : nullptr;
     if ((rc = launch_res64(c, P, R, st))) return rc;
   }
@@ -1807,7 +1822,7 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   R.bvec = c->cgv[0]; R.x_out = c->cgv[5]; R.rtol = 1.0; R.atol = 0.0; R.use_stop = 0; R.image = 0;
   R.timing = 1;                         // a converged workspace must not end the run early (the arithmetic is the same)
   FhCgRes64 R64{};
-  R64.bvec = c->d64[0]; R64.x_out = c->d64[1]; R64.rtol = 1.0; R64.atol = 0.0; R64.sy2 = 0.01; R64.use_stop = 0; R64.image = 0;
+  R64.bvec = c->d64[0]; R64.x_out = c->d64[1]; R64.rtol = 1.0; R64.atol = 0.0; R64.sy2 = 0.01; R64.use_stop = 0; R64.image = 0; R64.niter_hint = s->hint;
   R64.timing = 1;
   R64.gen = res64_gen(o, s->m, c->r64_smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs));
   cudaEvent_t e0, e1;

@@ -38,6 +38,7 @@
 // (halo rows wrap around inside ONE plane) would otherwise need two segments in the two straddling CTAs, which the whole
 // grid would wait for at the next barrier.
 #define FH_R64_CPP ((FH_N + FH_RES_ROWS - 1) / FH_RES_ROWS)          // CTAs per plane (43)
+#define FH_R64_ZT_MIN_ITERS 6                        // Zt mode is not worth its prologue below this many expected iterations
 
 struct FhRes64Smem {
   double2 X[FH_RES_ROWS / 2][FH_R64_LD];             // FFT ping-pong; X doubles as the strip's input rows, Y as its output
@@ -48,6 +49,7 @@ struct FhRes64Smem {
   // global access of the kernel bypasses L1), which costs 1.7 us per iteration (measured) and is used only above rank 30.
   double taps[4][FH_RES_TAPS];                       // row A^T, column A^T, column A, row A (centre padded to a multiple of 4)
   double s_red[4][8];                                // block-sum slots: ride 1, p.Ap partial, ride 2, r.r partial
+  double s_keep[3][FH_RES_MAXM];                     // Zt mode (survives the transforms): totals of Zt.h(r'), Z delta w_hat(p), coef
   fh_mbar_t bar;
   unsigned long long pad_;
 };
@@ -87,6 +89,9 @@ struct FhCgRes64 {
   FhR64Gen gen;                // non-separable operator (mode 0: none)
   int apply_only;              // 1: no solve -- x_out = Sigma bvec (one pass of the loop without operator, fh_cov_dot_f64)
   int mr_cap;                  // rows of Z that fit in shared memory
+  int zt_mode;                 // Zt mode (see the kernel): 0 off, 1 on, 2 decided from *niter_hint (iterations of the image's previous solve)
+  int zt_wide;                 // the launch reserved 2 m row slots: Zt mode keeps its rows as float64 (no widening in the two low-rank loops)
+  int* niter_hint;             // device word of this image: written at the end of every solve, read at the start of the next
   FhCgInfo* info_out;
   const double2* tw;           // device tables (FH_R64_TW, FH_N entries)
   const double2* e512;
@@ -356,6 +361,27 @@ __device__ __forceinline__ double fh_warp_transpose_sum32_d(double (&v)[32]) {
   }
   return v[0];
 }
+// 8 values per lane -> lane l ends with the warp total of v[4 b4 + 2 b3 + b2] (b_k = bit k of l): three halving exchanges,
+// two butterfly steps.  The row loops of the low-rank stages run over chunks of 8 rows with this instead of one fully
+// unrolled pass over 32 (fh_warp_transpose_sum32_d): the unrolled bodies had grown the kernel to 250 KB of SASS, more
+// than the instruction caches hold, and every iteration walks most of it.
+__device__ __forceinline__ double fh_warp_transpose_sum8_d(double (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16, w = 4; w >= 1; o >>= 1, w >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const double send = hi ? v[k] : v[k + w];
+      const double keep = hi ? v[k + w] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+#define FH_R64_T8_ROW(lane) (((lane) >> 2) & 7)        // which of the 8 values lane `lane` holds after fh_warp_transpose_sum8_d
 // Block sums without barriers of their own: every warp posts its total into an 8-entry slot BEFORE a __syncthreads the
 // caller needs anyway, and whoever needs the block total adds the 8 entries in a fixed order AFTER it (bit-identical in
 // every thread; a slot is rewritten one pass later, many barriers after its last read).
@@ -579,6 +605,34 @@ __device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigne
 // grid = 43 CTAs per plane (cooperative), block = 256, dynamic shared memory = FhRes64Smem [+ tables] [+ gather staging]
 // + min(m, mr_cap) * 6 KB.  BIG = false: every row of Z resident.  BIG = true: rows >= mr_cap are re-read from L2.
 // TABS = true: twiddle tables in shared memory (costs two rows of Z); false: read through L1.
+// First hop of the dot exchange, one warp: row i of the low-rank products is owned by CTA i * (grid / orows); its owner
+// sums the grid's partials in a fixed order and publishes the total.
+__device__ __forceinline__ void fh_r64_dots_hop1(const uint4* ll_dots, uint4* ll_sum, int s, int nblk, int m, int orows, unsigned seq) {
+  const int lane = threadIdx.x & 31;
+  const int own_step = nblk / orows > 0 ? nblk / orows : 1;
+  if (s % own_step == 0 && s / own_step < m) {
+    const int i = s / own_step;
+    const uint4* col = ll_dots + (size_t)i * nblk;
+    double t = 0.0;
+    for (int k0 = lane; k0 < nblk; k0 += 128) {
+      if (k0 + 96 < nblk) {
+        uint4 v[4];
+        fh_ll_wait<4>(col + k0, 32, seq, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t += fh_u2d(v[u].x, v[u].z);
+      } else {
+        for (int kk = k0; kk < nblk; kk += 32) {
+          uint4 v[1];
+          fh_ll_wait<1>(col + kk, 0, seq, v);
+          t += fh_u2d(v[0].x, v[0].z);
+        }
+      }
+    }
+    t = fh_warp_sum(t);
+    if (lane == 0) fh_ll_put_double(ll_sum + (size_t)i * FH_LL_SPREAD, t, seq);
+  }
+}
+
 template <bool BIG, bool TABS>
 __global__ void __launch_bounds__(FH_PASS_THREADS, 1)
 fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
@@ -667,6 +721,47 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
   int niter = 0, optimal = 0;
   bool z_ready = (mr == 0);
   __syncthreads();
+  // ---- Zt mode: the resident rows become Zt_i = column-IDCT(delta o z_i), the low-rank factor in the HALF-transformed
+  // domain the strip holds between the two transposes.  By Parseval Z (delta w_hat) = Zt . h (h = the strip before the
+  // column DCT) and column-IDCT(delta Z^T c) = Zt^T c, so the partial dots are posted BEFORE the forward column transform
+  // and the correction is added AFTER the inverse one: the two-hop exchange of the dots (2.7 - 4.6 us) runs while the
+  // strip does both transforms, polled by warp 7, which the 192-thread transforms leave idle.  By linearity the dots are
+  // taken of the new RESIDUAL and follow the direction as t(p') = t(r') + beta t(p).  Costs m strip transforms per solve:
+  // used when the image's previous solve ran long enough (every CTA reads the same word: a uniform decision).
+  bool zt = false;
+  if (!BIG && m > 0 && !R.apply_only) {
+    if (R.zt_mode == 1) zt = true;
+    else if (R.zt_mode == 2 && R.niter_hint) zt = *reinterpret_cast<volatile const int*>(R.niter_hint) >= max(FH_R64_ZT_MIN_ITERS, (5 * m) >> 3);
+  }
+  double beta = 0.0, lr_pAp = 0.0;
+  const bool wide = !BIG && zt && R.zt_wide;
+  double* Zd = reinterpret_cast<double*>(Zs);
+  if (!BIG && zt) {
+    fh_mbar_wait(&sm.bar, 0);
+    z_ready = true;
+    if (tid < FH_RES_MAXM) sm.s_keep[1][tid] = 0.0;
+    // wide: row i moves from its float32 slot [6 i, 6 i + 6) KB to the float64 slot [12 i, 12 i + 12) KB, last row first
+    // (the float64 slot of row i starts at or behind the end of the float32 rows below it)
+    for (int ii = 0; ii < m; ++ii) {
+      const int i = wide ? m - 1 - ii : ii;
+      float z[FH_RES_ROWS];
+      double v[FH_RES_ROWS];
+      fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) v[e] = (double)z[e] * (double)dl[e];
+      fh_r64_put(rows_a, v);
+      __syncthreads();
+      fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
+      __syncthreads();
+      fh_r64_get(rows_b, v, npair);
+#pragma unroll
+      for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+        if (wide) reinterpret_cast<double2*>(Zd + (size_t)i * FH_RES_SLICE)[tid + FH_PASS_THREADS * h] = make_double2(v[2 * h], v[2 * h + 1]);   // zeros beyond the strip's rows
+        else if (h < npair) reinterpret_cast<float2*>(Zs + (size_t)i * FH_RES_SLICE)[tid + FH_PASS_THREADS * h] = make_float2((float)v[2 * h], (float)v[2 * h + 1]);
+      }
+    }
+    __syncthreads();
+  }
 
 #define FH_R64TRACE(slot) do { if (k == 3) FH_TRACE(P, 6, slot); } while (0)
   for (int k = 0;; ++k) {
@@ -707,6 +802,54 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
       __syncthreads();
       const double S1 = fh_r64_sum8(sm.s_red[0]);
       if (fuse == 2) fh_r64_conv(rows_a, sm.taps[1], tp[1] >> 8, tp[1] & 255, nrows);
+      if (!BIG && zt) {
+        // Zt . h(r'): partials posted now, summed by the owners' warp 7 while warps 0..5 run the column transform
+        double hh[FH_RES_ROWS];
+        fh_r64_get(rows_a, hh, npair);
+        if (wide) {
+          for (int c0 = 0; c0 < m; c0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc[u] = 0.0;
+              if (c0 + u < m) {
+#pragma unroll
+                for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+                  const double2 zz = reinterpret_cast<const double2*>(Zd + (size_t)(c0 + u) * FH_RES_SLICE)[tid + FH_PASS_THREADS * h];
+                  acc[u] = fma(zz.y, hh[2 * h + 1], fma(zz.x, hh[2 * h], acc[u]));
+                }
+              }
+            }
+            const double tot = fh_warp_transpose_sum8_d(acc);
+            if ((lane & 3) == 0 && c0 + FH_R64_T8_ROW(lane) < m) sc.s_w[warp][c0 + FH_R64_T8_ROW(lane)] = tot;
+          }
+        } else {
+          for (int c0 = 0; c0 < m; c0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              acc[u] = 0.0;
+              if (c0 + u < m) {
+                float z[FH_RES_ROWS];
+                fh_r64_getf(Zs + (size_t)(c0 + u) * FH_RES_SLICE, z, npair);
+#pragma unroll
+                for (int e = 0; e < FH_RES_ROWS; ++e) acc[u] = fma(FH_WIDEN(z[e], e), hh[e], acc[u]);
+              }
+            }
+            const double tot = fh_warp_transpose_sum8_d(acc);
+            if ((lane & 3) == 0 && c0 + FH_R64_T8_ROW(lane) < m) sc.s_w[warp][c0 + FH_R64_T8_ROW(lane)] = tot;
+          }
+        }
+        __syncthreads();
+        if (tid < m) {
+          double t2 = 0.0;
+#pragma unroll
+          for (int wv = 0; wv < FH_PASS_THREADS / 32; ++wv) t2 += sc.s_w[wv][tid];
+          fh_ll_put_double(R.ll_dots + (size_t)tid * nblk + s, t2, seq);
+        }
+        __syncthreads();                                 // the scratch in Y is read: the transform may overwrite it
+        if (warp == FH_PASS_THREADS / 32 - 1) fh_r64_dots_hop1(R.ll_dots, R.ll_sum, s, (int)nblk, m, FH_RES_MAXM, seq);
+      }
       fh_dct64_core<false, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
       fh_r64_get(rows_b, wr, npair);
@@ -719,7 +862,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
         for (int e = 0; e < FH_RES_ROWS; ++e) { p[e] = x[e]; wp[e] = wr[e]; }
       } else {
         resid2 = S1;
-        double beta = 0.0;
+        beta = 0.0;
         if (k >= 2) {                                                          // end of CG iteration k - 1 (cg.py:258-263)
           niter = k - 1;
           const bool converged = (stop2 >= 0.0) && (S1 <= stop2);
@@ -737,47 +880,44 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     double vv[FH_RES_ROWS];
 #pragma unroll
     for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = wp[e];
-    if (m > 0) {
+    if (m > 0 && !(!BIG && zt)) {
       if (!z_ready) { fh_mbar_wait(&sm.bar, 0); z_ready = true; }
       double wd[FH_RES_ROWS];
 #pragma unroll
       for (int e = 0; e < FH_RES_ROWS; ++e) wd[e] = wp[e] * (double)dl[e];
-      {
-        double acc[32];
+      for (int c0 = 0; c0 < mr; c0 += 8) {
+        double acc[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          acc[i] = 0.0;
-          if (i < mr) {
+        for (int u = 0; u < 8; ++u) {
+          acc[u] = 0.0;
+          if (c0 + u < mr) {
             float z[FH_RES_ROWS];
-            fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
+            fh_r64_getf(Zs + (size_t)(c0 + u) * FH_RES_SLICE, z, npair);
 #pragma unroll
-            for (int e = 0; e < FH_RES_ROWS; ++e) acc[i] = fma(FH_WIDEN(z[e], e), wd[e], acc[i]);
+            for (int e = 0; e < FH_RES_ROWS; ++e) acc[u] = fma(FH_WIDEN(z[e], e), wd[e], acc[u]);
           }
         }
-        const double tot = fh_warp_transpose_sum32_d(acc);
-        if (lane < mr) sc.s_w[warp][lane] = tot;
+        const double tot = fh_warp_transpose_sum8_d(acc);
+        if ((lane & 3) == 0 && c0 + FH_R64_T8_ROW(lane) < mr) sc.s_w[warp][c0 + FH_R64_T8_ROW(lane)] = tot;
       }
       if (BIG) {
-        for (int c0 = mr; c0 < m; c0 += 32) {            // rows that did not fit: straight from L2, 4 rows (12 loads) in flight
-          double acc[32];
+        for (int c0 = mr; c0 < m; c0 += 8) {             // rows that did not fit: straight from L2, 8 rows (24 loads) in flight
+          float z[8][FH_RES_ROWS];
 #pragma unroll
-          for (int i0 = 0; i0 < 32; i0 += 4) {
-            float z[4][FH_RES_ROWS];
+          for (int u = 0; u < 8; ++u) {
+            if (c0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + u) * d, z[u], npair);
+          }
+          double acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (c0 + i0 + u < m) fh_r64_get_z_l2(zsrc + (size_t)(c0 + i0 + u) * d, z[u], npair);
-            }
+          for (int u = 0; u < 8; ++u) {
+            acc[u] = 0.0;
+            if (c0 + u < m) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              acc[i0 + u] = 0.0;
-              if (c0 + i0 + u < m) {
-#pragma unroll
-                for (int e = 0; e < FH_RES_ROWS; ++e) acc[i0 + u] = fma(FH_WIDEN(z[u][e], e), wd[e], acc[i0 + u]);
-              }
+              for (int e = 0; e < FH_RES_ROWS; ++e) acc[u] = fma(FH_WIDEN(z[u][e], e), wd[e], acc[u]);
             }
           }
-          const double tot = fh_warp_transpose_sum32_d(acc);
-          if (c0 + lane < m) sc.s_w[warp][c0 + lane] = tot;
+          const double tot = fh_warp_transpose_sum8_d(acc);
+          if ((lane & 3) == 0 && c0 + FH_R64_T8_ROW(lane) < m) sc.s_w[warp][c0 + FH_R64_T8_ROW(lane)] = tot;
         }
       }
       __syncthreads();
@@ -790,29 +930,8 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
       FH_R64TRACE(4);
       {
         constexpr int OROWS = BIG ? FH_MAXM : FH_RES_MAXM;
-        const int own_step = (int)nblk / OROWS > 0 ? (int)nblk / OROWS : 1;
         if (warp == 0) {
-          if (s % own_step == 0 && s / own_step < m) {
-            const int i = s / own_step;
-            const uint4* col = R.ll_dots + (size_t)i * nblk;
-            double t = 0.0;
-            for (int k0 = lane; k0 < (int)nblk; k0 += 128) {
-              if (k0 + 96 < (int)nblk) {
-                uint4 v[4];
-                fh_ll_wait<4>(col + k0, 32, seq, v);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) t += fh_u2d(v[u].x, v[u].z);
-              } else {
-                for (int kk = k0; kk < (int)nblk; kk += 32) {
-                  uint4 v[1];
-                  fh_ll_wait<1>(col + kk, 0, seq, v);
-                  t += fh_u2d(v[0].x, v[0].z);
-                }
-              }
-            }
-            t = fh_warp_sum(t);
-            if (lane == 0) fh_ll_put_double(R.ll_sum + (size_t)i * FH_LL_SPREAD, t, seq);
-          }
+          fh_r64_dots_hop1(R.ll_dots, R.ll_sum, s, (int)nblk, m, OROWS, seq);
 #pragma unroll
           for (int g = 0; g < (BIG ? 2 : 1); ++g) {
             const int row = lane + 32 * g;
@@ -837,15 +956,13 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
         __syncthreads();
       }
       FH_R64TRACE(6);
+#pragma unroll 4
+      for (int i = 0; i < mr; ++i) {
+        const double c = sc.s_c[i];
+        float z[FH_RES_ROWS];
+        fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < mr) {
-          const double c = sc.s_c[i];
-          float z[FH_RES_ROWS];
-          fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
-#pragma unroll
-          for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = fma(c, FH_WIDEN(z[e], e), vv[e]);
-        }
+        for (int e = 0; e < FH_RES_ROWS; ++e) vv[e] = fma(c, FH_WIDEN(z[e], e), vv[e]);
       }
       if (BIG) {
         for (int c0 = mr; c0 < m; c0 += 4) {
@@ -879,8 +996,56 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
       fh_r64_put(rows_a, vv);
       __syncthreads();                                   // also: the scratch in Y is dead, the transform may use Y again
       if (tid == 0) R.ride[1][s] = fh_r64_sum8(sm.s_red[1]);
+      if (!BIG && zt && warp == FH_PASS_THREADS / 32 - 1) {
+        // second hop, overlapped with the inverse column transform: the totals of Zt . h(r')
+        double tot = 0.0;
+        if (lane < m) {
+          uint4 v[1];
+          fh_ll_wait<1>(R.ll_sum + (size_t)lane * FH_LL_SPREAD, 0, seq, v);
+          tot = fh_u2d(v[0].x, v[0].z);
+        }
+        sm.s_keep[0][lane] = tot;
+      }
       fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
+      if (!BIG && zt) {
+        if (tid < FH_RES_MAXM) sm.s_keep[1][tid] = fma(beta, sm.s_keep[1][tid], sm.s_keep[0][tid]);      // t(p') = t(r') + beta t(p)
+        __syncthreads();
+        double a = 0.0;
+#pragma unroll
+        for (int u = 0; u < NG; ++u) a += gs[u] * sm.s_keep[1][(cpart + CP * u) & (FH_RES_MAXM - 1)];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (cpart == 0 && ci < FH_RES_MAXM) sm.s_keep[2][ci] = a;                                       // coef = Gs t(p')
+        __syncthreads();
+        lr_pAp = fh_warp_sum(sm.s_keep[1][lane] * sm.s_keep[2][lane]);                                  // t . Gs t, the same in every warp and CTA
+        double cv[FH_RES_ROWS];
+        fh_r64_get(rows_b, cv, npair);
+        if (wide) {
+#pragma unroll 4
+          for (int i = 0; i < m; ++i) {
+            const double c = sm.s_keep[2][i];
+#pragma unroll
+            for (int h = 0; h < FH_RES_ROWS / 2; ++h) {
+              const double2 zz = reinterpret_cast<const double2*>(Zd + (size_t)i * FH_RES_SLICE)[tid + FH_PASS_THREADS * h];
+              cv[2 * h] = fma(c, zz.x, cv[2 * h]);
+              cv[2 * h + 1] = fma(c, zz.y, cv[2 * h + 1]);
+            }
+          }
+        } else {
+#pragma unroll 4
+          for (int i = 0; i < m; ++i) {
+            const double c = sm.s_keep[2][i];
+            float z[FH_RES_ROWS];
+            fh_r64_getf(Zs + (size_t)i * FH_RES_SLICE, z, npair);
+#pragma unroll
+            for (int e = 0; e < FH_RES_ROWS; ++e) cv[e] = fma(c, FH_WIDEN(z[e], e), cv[e]);
+          }
+        }
+        fh_r64_put(rows_b, cv);                            // every thread rewrites exactly the elements it read
+        __syncthreads();
+      }
       if (fuse == 2) fh_r64_conv(rows_b, sm.taps[2], tp[2] >> 8, tp[2] & 255, nrows);
       fh_r64_store_t(rows_b, R.T[1], grow0, npair);
     }
@@ -894,7 +1059,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
       fh_r64_post(fh_r64_ride_part(R.ride[1], (int)nblk), sm.s_red[2]);
       fh_r64_put(rows_a, t);
       __syncthreads();
-      const double pAp = fh_r64_sum8(sm.s_red[2]);
+      const double pAp = fh_r64_sum8(sm.s_red[2]) + lr_pAp;
       fh_dct64_core<true, TABS>(rows_a, rows_b, sm.X, sm.Y, tw, e512, npair);
       __syncthreads();
       if (fuse == 2) fh_r64_conv(rows_b, sm.taps[3], tp[3] >> 8, tp[3] & 255, nrows);
@@ -952,6 +1117,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     w->optimal = optimal;
     fh_set_done(w, niter + 1);
     if (R.info_out) { R.info_out->residual_norm = sqrt(resid2); R.info_out->niter = niter; R.info_out->optimal = optimal; }
+    if (!R.apply_only && R.niter_hint) *R.niter_hint = niter;
   }
 }
 

@@ -21,7 +21,7 @@ def E():
     return H.use_emulation()
 
 
-SMEM = {"tables in shared memory": None, "tables through L1": 33296 + 4 * 6144 + 100, "rows from L2": 33296 + 2 * 6144 + 100}
+SMEM = {"tables in shared memory": None, "tables through L1": 34064 + 4 * 6144 + 100, "rows from L2": 34064 + 2 * 6144 + 100}
 
 
 def _state(E, assets, variant, monkeypatch):
@@ -91,11 +91,43 @@ def test_res64_solve_and_cov_dot(E, assets, variant, monkeypatch):
             matk, _ = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=k)
             assert rel_l2(mat, matk) < 1e-6
 
-@pytest.mark.parametrize("which", ["motion_blur", "super_resolution"])
+@pytest.mark.parametrize("variant", ["tables in shared memory", "tables through L1"])
+def test_res64_zt_mode(E, assets, variant, monkeypatch):
+    """Zt mode of fh_k_cg_res64 (FH_R64_ZT=1 forces it; by default the previous solve's iteration count decides): the
+    resident rows are replaced by column-IDCT(delta z_i) in the prologue, the dots are taken before the forward column
+    transform and the correction is added after the inverse one -- same iterates as the plain mode and the oracle."""
+    monkeypatch.setenv("FH_R64_ZT", "1")
+    test_res64_solve_and_cov_dot(E, assets, variant, monkeypatch)
+
+
+def test_res64_zt_mode_follows_the_previous_solve(E, assets, monkeypatch):
+    ctx, st, ora, rs, shape, s1 = _state(E, assets, "tables in shared memory", monkeypatch)
+    xc = np.clip(rs.standard_normal(shape), -1, 1)
+    mu0 = 0.3 * xc
+    sy2 = float(np.float32(0.1) * np.float32(0.1))
+    mask = (rs.uniform(size=(256, 256)) > 0.7).astype(np.float32)
+    op = E.Operator.inpaint(ctx, mask)
+    oo = fo.InpaintingOracle(np.broadcast_to(mask, shape), 0.1)
+    y = ((xc + 0.1 * rs.standard_normal(shape)) * mask).astype(np.float32).astype(np.float64)
+    outs = []
+    for it in (7, 4, 4):         # 7 iterations -> the next solve runs in Zt mode (>= 6); that one reports 4 -> the third is plain again
+        mat, info = E.cg_solve(st, op, torch.tensor(y), torch.tensor(mu0), sy2, 1.0, maxiter=50, fixed_iters=it)
+        assert info["niter"][0] == it
+        outs.append(mat)
+    ref, _ = fo.mat_solver(oo, y, mu0, ora, s1, fixed_iters=4)
+    assert rel_l2(outs[1], ref) < 1e-6 and rel_l2(outs[2], ref) < 1e-6
+    assert not torch.equal(outs[1], outs[2])                 # two different arithmetic paths (same operator to float32 storage rounding)
+    assert rel_l2(outs[1], outs[2]) < 1e-6
+
+
+@pytest.mark.parametrize("which", ["motion_blur", "super_resolution", "motion_blur_zt"])
 def test_res64_non_separable_operators(E, assets, which, monkeypatch):
     """The gathers of the operators that do not fold into the DCT passes (fh_r64_gather_conv: the 217-tap motion PSF as
     column runs; fh_r64_sr_gather_at / _a: 25 x 25 bicubic PSF with x4 decimation), inside the resident float64 solve:
     two CG iterations at rank 4 against the float64 oracle's FFT operators."""
+    if which.endswith("_zt"):
+        monkeypatch.setenv("FH_R64_ZT", "1")
+        which = which[:-3]
     ctx, st, ora, rs, shape, s1 = _state(E, assets, "tables in shared memory", monkeypatch)
     xc = np.clip(rs.standard_normal(shape), -1, 1)
     mu0 = 0.3 * xc
