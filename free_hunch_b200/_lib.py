@@ -50,6 +50,8 @@ _SIGNATURES = {
     "fh_space_update": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_state_set_cov_vectors": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]),
     "fh_state_drop_all": (c_int, [c_void_p, c_double, c_void_p]),
+    "fh_state_gram": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "fh_state_recombine": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "fh_state_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fh_op_create_conv": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int, c_int]),
     "fh_op_create_inpaint": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int]),

@@ -230,6 +230,7 @@ class FreeHunch(ConditioningMechanism):
                     if fused:
                         prev_mean_at_sigma, _ = cov.state.time_update_from_mean(self.xs[-1], self.denoiser_means[-1], self.sigmas[-1], sigma_f)
                         cov._sigma = sigma_f
+                        cov._track("time_update")                  # factor history of drop_vectors (max_vector_count only)
                     else:
                         score_previous = (self.denoiser_means[-1] - self.xs[-1]) / self._scalar(self.sigmas[-1] ** 2, x_t)
                         prev_mean_at_sigma, _ = cov.update_time_step(self.xs[-1], self.sigmas[-1], sigma_f, score_previous)

@@ -59,6 +59,11 @@ class CovarianceHessianBFGS:
         self._sigma = float(np.sqrt(float(init_noise_variance)))
         self.state.init(var, float(init_noise_variance))
         self._pending_u = self._pending_v = None
+        # factor history for drop_vectors(0 < n < k): only when a finite max_vector_count can ever trigger it
+        self._trackers = None
+        if max_vector_count is not None and 0 < max_vector_count < engine.MAX_RANK // 2 and not project_to_diagonal:
+            from .ref_factors import ReferenceFactorTracker
+            self._trackers = [ReferenceFactorTracker() for _ in range(batch)]
         if init_denoiser_cov_u is not None:                     # online_update_bfgs.py:16-18,37
             self.vectors_denoiser_cov_u = init_denoiser_cov_u
             self.set_others_corresponding_to_current_denoiser_cov(self._sigma)
@@ -79,10 +84,12 @@ class CovarianceHessianBFGS:
         self._sigma = float(sigma_tnext)
         if only_covariance:
             self.state.time_update(None, None, sigma_t, sigma_tnext, only_covariance=True)
+            self._track("time_update")
             x = x_t.detach()
             return x.clone(), x.clone()                         # online_update_bfgs.py:187-188
         mean, score = self.state.time_update(self._to_batch(x_t.detach()), self._to_batch(score_t.detach()),
                                              float(sigma_t), float(sigma_tnext))
+        self._track("time_update")
         return mean.reshape(shape).to(dtype), score.reshape(shape).to(dtype)
 
     def update_space_step(self, denoiser_mean_at_x, denoiser_mean_at_xnext, sigma_t, x, xnext):
@@ -91,6 +98,8 @@ class CovarianceHessianBFGS:
         self.state.space_update(self._to_batch(denoiser_mean_at_x.detach()), self._to_batch(denoiser_mean_at_xnext.detach()),
                                 float(sigma_t), self._to_batch(x.detach()), self._to_batch(xnext.detach()),
                                 project_to_diagonal=self.project_to_diagonal)
+        if not self.project_to_diagonal:
+            self._track("space_update")
         if self.max_vector_count is not None:                   # online_update_bfgs.py:309-310
             self.drop_vectors(self.max_vector_count, sigma_t)
 
@@ -100,18 +109,33 @@ class CovarianceHessianBFGS:
         return out.reshape(shape).to(dtype)
 
     def drop_vectors(self, max_vector_count, sigma):
-        """online_update_bfgs.py:233-245.  Dropping everything is representation independent and supported.
-        Keeping "the last n columns" is not: after the first time update the reference's U, V are no longer the BFGS pairs
-        but the columns of `P W sqrtm(M)` produced by its Woodbury re-factorisations (:87-119) -- a complex matrix square
-        root mixes every pair into every column, so which part of Sigma the last n columns carry depends on that
-        factorisation history, not on Sigma.  The product keeps no such factors; the request is
-        refused rather than answered with a different truncation.  Only reachable with a non-default max_vector_count
-        below the live rank (config.yaml default 100000 = never)."""
+        """online_update_bfgs.py:233-245.  n = 0 forgets the low-rank part.  0 < n < k keeps "the last n columns" of
+        the reference's factors U, V -- columns of its own Woodbury / sqrtm re-factorisations (:87-119), which the product
+        does not store.  With `max_vector_count` set, `ref_factors.ReferenceFactorTracker` carries their coefficients over
+        the rows of Z (one m x m Gram read per update), and a drop moves the state to the basis of the kept columns
+        (`fh_state_recombine`), which bounds the rank at 2 n + 2 like the reference's memory.  Refused (NotImplementedError)
+        where the kept columns are complex: the reference then continues with a complex 'covariance' and takes real
+        parts of its products, which no real-valued state reproduces."""
         k = self.state.rank // 2
         if max_vector_count == 0:
             self.state.drop_all(float(sigma))
+            for t in self._trackers or ():
+                t.reset()
         elif k > max_vector_count:
-            raise NotImplementedError("drop_vectors(0 < n < rank) depends on the reference's sqrtm factorisation")
+            if self._trackers is None:
+                raise NotImplementedError("drop_vectors(0 < n < rank) needs the factor history: construct the model with "
+                                          "max_vector_count set")
+            K = self.state.gram().cpu().numpy()
+            drops = [t.drop(int(max_vector_count), K[b]) for b, t in enumerate(self._trackers)]
+            self.state.recombine(np.stack([d[0] for d in drops]), np.stack([d[1] for d in drops]))
+
+    def _track(self, what):
+        """Keeps the reference's factor coefficients in step with the state (only when max_vector_count is set)."""
+        if self._trackers is None or self.state.rank == 0:
+            return
+        K = self.state.gram().cpu().numpy()
+        for b, t in enumerate(self._trackers):
+            getattr(t, what)(K[b])
 
     @property
     def vector_count(self):

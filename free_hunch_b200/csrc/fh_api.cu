@@ -938,6 +938,34 @@ extern "C" int fh_state_drop_all(fh_state* s, double sigma, void* stream) {
   return FH_OK;
 }
 
+extern "C" int fh_state_gram(fh_state* s, double* K_out, void* stream) {
+  if (!s || !K_out) FH_FAIL(FH_EINVAL, "bad fh_state_gram arguments");
+  if (s->m == 0) return FH_OK;
+  fh_ctx* c = s->ctx;
+  FhRowPtrs xr{};
+  int rc = gram(s, s->m, xr, 0, s->delta, stream);
+  if (rc) return rc;
+  for (int b = 0; b < s->B; ++b)
+    for (int i = 0; i < s->m; ++i)
+      FH_CUDA(cudaMemcpyAsync(K_out + ((size_t)b * s->m + i) * s->m, c->gramK + (size_t)b * FH_GRAM_LD * FH_GRAM_LD + (size_t)i * FH_GRAM_LD,
+                              (size_t)s->m * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return FH_OK;
+}
+
+extern "C" int fh_state_recombine(fh_state* s, int m_new, const double* T, const double* Gz_new, void* stream) {
+  if (!s || !T || !Gz_new || m_new < 1 || m_new > s->m) FH_FAIL(FH_EINVAL, "bad fh_state_recombine arguments (rank %d -> %d)", s ? s->m : -1, m_new);
+  FH_LAUNCH(fh_k_recombine, dim3((unsigned)fh_nchunks(s->d), s->B), dim3(256), 0, stream, s->Z, s->m, m_new, T, s->d);
+  FH_KCHECK();
+  FH_CUDA(cudaMemsetAsync(s->Gz, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  FH_CUDA(cudaMemsetAsync(s->Gs, 0, (size_t)s->B * FH_MAXM * FH_MAXM * sizeof(double), (cudaStream_t)stream));
+  for (int b = 0; b < s->B; ++b)
+    for (int i = 0; i < m_new; ++i)
+      FH_CUDA(cudaMemcpyAsync(s->Gz + ((size_t)b * FH_MAXM + i) * FH_MAXM, Gz_new + ((size_t)b * m_new + i) * m_new,
+                              (size_t)m_new * sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  s->m = m_new;
+  return refresh_core(s, stream);
+}
+
 extern "C" int fh_state_export(fh_state* s, float* pi, float* Z, double* Gz, double* Gs, float* delta, void* stream) {
   if (!s) FH_FAIL(FH_EINVAL, "null state");
   fh_ctx* c = s->ctx;

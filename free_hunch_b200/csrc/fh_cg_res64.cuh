@@ -327,7 +327,17 @@ __device__ __forceinline__ void fh_r64_conv(double* sm_rows, const double* __res
   __syncthreads();
 }
 // like fh_res_stage_taps, widened to float64
+// Taps below 1e-18 of the largest one are left out at both ends: in a float64 sum they are under half an ulp of the
+// result (the reference's 61-tap Gaussian of std 3 has 3 such taps per side: 64 -> 56 padded taps per convolution, and
+// the four convolutions of an iteration run at the issue rate of the FP64 pipe).
 __device__ __forceinline__ int fh_r64_stage_taps(double* s_taps, const float* __restrict__ k, int n, int c, int forward) {
+  float mx = 0.f;
+  for (int i = 0; i < n; ++i) mx = fmaxf(mx, fabsf(k[i]));
+  const float thr = mx * 1e-18f;
+  int lo = 0, hi = n - 1;
+  while (lo < c && fabsf(k[lo]) <= thr) ++lo;
+  while (hi > c && fabsf(k[hi]) <= thr) --hi;
+  k += lo; n = hi - lo + 1; c -= lo;
   const int cen = forward ? n - 1 - c : c;
   const int sh = (4 - (cen & 3)) & 3;
   const int n4 = (n + sh + 3) & ~3;

@@ -305,6 +305,27 @@ fh_k_gram_reduce(const double* __restrict__ partial, int nparts, int R, double* 
   }
 }
 
+// Change of the low-rank basis, in place:  Z'[i][e] = sum_j T[j][i] Z[j][e]   (T: (B, m, m_new) row-major, float64).
+// Every thread owns whole columns e, so reading all m rows of a column before writing its m_new rows is race-free;
+// float64 accumulation, float32 storage like every row of Z.  grid = (chunks, B), block 256.  Rare (fh_state_recombine).
+__global__ void __launch_bounds__(256)
+fh_k_recombine(float* __restrict__ Z, int m, int m_new, const double* __restrict__ T, long d) {
+  __shared__ double sT[FH_MAXM * FH_MAXM];
+  const size_t b = blockIdx.y;
+  for (int i = threadIdx.x; i < m * m_new; i += blockDim.x) sT[i] = T[b * (size_t)m * m_new + i];
+  __syncthreads();
+  float* Zb = Z + b * FH_MAXM * d;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < d; e += (long)gridDim.x * blockDim.x) {
+    float z[FH_MAXM];
+    for (int j = 0; j < m; ++j) z[j] = Zb[(size_t)j * d + e];
+    for (int i = 0; i < m_new; ++i) {
+      double a = 0.0;
+      for (int j = 0; j < m; ++j) a = fma(sT[j * m_new + i], (double)z[j], a);
+      Zb[(size_t)i * d + e] = (float)a;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp64 small algebra, one CTA (256 threads) per image, all matrices <= 64 x 64 in shared memory.
 // Gauss-Jordan inverse with partial pivoting of the n x n matrix A (row-major, ld = FH_MAXM) into Ainv.

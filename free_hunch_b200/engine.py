@@ -195,6 +195,23 @@ class CovState:
     def drop_all(self, sigma):
         _lib.check(_lib.lib().fh_state_drop_all(self._h, float(sigma), self.ctx.stream()))
 
+    def gram(self):
+        """K = Z diag(delta) Z^T at the state's current sigma: (B, m, m) float64 on the device."""
+        m = self.rank
+        K = torch.empty(self.B, m, m, dtype=torch.float64, device=self.ctx.device)
+        if m:
+            _lib.check(_lib.lib().fh_state_gram(self._h, _ptr(K), self.ctx.stream()))
+        return K
+
+    def recombine(self, T, Gz_new):
+        """Z <- T^T Z per image (T: (B, m, m_new)), core of Sigma^-1 <- Gz_new ((B, m_new, m_new)); rank <- m_new."""
+        T = torch.as_tensor(T, dtype=torch.float64).to(self.ctx.device).contiguous()
+        Gz_new = torch.as_tensor(Gz_new, dtype=torch.float64).to(self.ctx.device).contiguous()
+        B, m, m_new = T.shape
+        if B != self.B or m != self.rank or tuple(Gz_new.shape) != (B, m_new, m_new):
+            raise ValueError("recombine: T must be (B, rank, m_new) and Gz_new (B, m_new, m_new)")
+        _lib.check(_lib.lib().fh_state_recombine(self._h, m_new, _ptr(T), _ptr(Gz_new), self.ctx.stream()))
+
     def export(self):
         """(pi, Z, Gz, Gs, delta) as tensors; Z is (B, m, d), Gz/Gs are (B, m, m) float64."""
         m, B, d, dev = self.rank, self.B, self.ctx.d, self.ctx.device

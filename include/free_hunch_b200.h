@@ -112,6 +112,15 @@ int fh_state_set_cov_vectors(fh_state* st, const float* U_dev, int ku, const flo
                              void* stream);
 /* drop_vectors(0, sigma), online_update_bfgs.py:235-239: forget the low-rank part of Sigma at `sigma`. */
 int fh_state_drop_all(fh_state* st, double sigma, void* stream);
+/* drop_vectors(0 < n < k, sigma), online_update_bfgs.py:241-245: "keep the last n columns" of the reference's factors
+ * U, V of Sigma.  Those columns are combinations of the state's rows -- the host tracks their m x k coefficient
+ * matrices (free_hunch_b200/ref_factors.py restates the reference's two Woodbury re-factorisations, :87-119, on them),
+ * for which it needs  K = Z diag(delta) Z^T  ((B, m, m) float64, device) at the state's current sigma ... */
+int fh_state_gram(fh_state* st, double* K_out_dev, void* stream);
+/* ... and when it drops, the state moves to the basis of the kept columns:  Z <- T^T Z  (T: (B, m, m_new) float64,
+ * device, row-major), Sigma^-1 = diag(pi + 1/sigma^2) + Z^T Gz_new Z  (Gz_new: (B, m_new, m_new) float64, device),
+ * rank <- m_new, Sigma's core rebuilt.  (set_others_corresponding_to_current_denoiser_cov, :327-330.) */
+int fh_state_recombine(fh_state* st, int m_new, const double* T_dev, const double* Gz_new_dev, void* stream);
 /* Export for get_dense_matrices (online_update_bfgs.py:320-325): pi (B,d) f32, Z (B,m,d) f32,
  * Gz (B,m,m) f64, Gs (B,m,m) f64, delta (B,d) f32; any pointer may be NULL. */
 int fh_state_export(fh_state* st, float* pi_dev, float* Z_dev, double* Gz_dev, double* Gs_dev, float* delta_dev,

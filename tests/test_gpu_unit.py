@@ -49,6 +49,14 @@ def test_project_to_diagonal(E, assets, dct):
     record("project_to_diagonal", dct=dct, sigv_after_update=e1, sigv_after_time_update=e2)
 
 
+@pytest.mark.parametrize("dct", [False, True])
+def test_drop_vectors_keeps_the_reference_columns(E, assets, dct):
+    """drop_vectors(0 < n < k), online_update_bfgs.py:233-245: max_vector_count = 2 over 5 (identity) / 4 (DCT) space
+    updates, Sigma.v against the oracle's truncated factor model after every update."""
+    errs = cases.case_drop_vectors("cuda", dct, assets, steps=4 if dct else 5)
+    record("drop_vectors", dct=dct, sigv_errs=[float(e) for e in errs])
+
+
 def test_dense_vs_memory_efficient_d3072(E):
     """configs[3], dense leg: 6 alternating time + space updates at d = 3 x 32 x 32 on both representations."""
     rs = np.random.RandomState(7)

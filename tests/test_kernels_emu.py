@@ -205,6 +205,71 @@ def case_project_to_diagonal(E, device, dct, assets=None):
     return e1, e2
 
 
+def case_drop_vectors(device, dct, assets=None, max_vector_count=2, steps=4):
+    """drop_vectors(0 < n < k) (online_update_bfgs.py:233-245, called from :309-310) through the product classes: the
+    reference keeps the last n columns of ITS factors; the product follows them with ref_factors.ReferenceFactorTracker
+    and moves the state to their basis.  Sigma.v after every update against the oracle (which restates the reference's
+    factor algebra line by line), and the rank stays bounded.  Identity basis at 2 x 16 x 16 or DCT at 3 x 256 x 256."""
+    from free_hunch_b200.covariance import CovarianceHessianBFGS, CovarianceHessianBFGSDCT
+    rs = np.random.RandomState(3)
+    if dct:
+        var = assets["dct_variance"]
+        C, Hh = 3, 256
+        ora = fo.CovarianceOracleDCT(var, 400.0, var.size, max_vector_count=max_vector_count)
+        cov = CovarianceHessianBFGSDCT(None, 400.0, var.size, max_vector_count=max_vector_count,
+                                       dct_variance=torch.tensor(var), device=device)
+    else:
+        C, Hh = 2, 16
+        var = np.exp(rs.uniform(np.log(1e-2), np.log(30.0), size=(C, Hh, Hh))).astype(np.float32)
+        ora = fo.CovarianceOracle(var.reshape(-1), 400.0, var.size, max_vector_count=max_vector_count)
+        cov = CovarianceHessianBFGS(var.reshape(-1), 400.0, var.size, max_vector_count=max_vector_count, device=device,
+                                    image_shape=(C, Hh, Hh))
+    shape = (1, C, Hh, Hh)
+    den = lambda z: 0.5 * np.tanh(z) + 0.1 * z
+    sigs = [20.0, 8.0, 6.0, 5.0, 4.0, 3.0]
+    x = rs.standard_normal(shape) * 8
+    zero = np.zeros(shape)
+    errs = []
+    for i in range(steps):
+        s, sn = sigs[i], sigs[i + 1]
+        ora.update_time_step(zero, s, sn, zero, only_covariance=True)
+        cov.update_time_step(torch.tensor(zero), s, sn, torch.tensor(zero), only_covariance=True)
+        xn = x + 0.3 * rs.standard_normal(shape)
+        m0, m1 = den(x), den(xn)
+        ora.update_space_step(m0, m1, sn, x, xn)
+        cov.update_space_step(torch.tensor(m0), torch.tensor(m1), sn, torch.tensor(x), torch.tensor(xn))
+        assert cov.vector_count == ora.cov_u.shape[1] == min(i + 1, max_vector_count)
+        w = rs.standard_normal(shape)
+        errs.append(rel_l2(cov.denoiser_cov_vector_dot(torch.tensor(w).float()), ora.denoiser_cov_vector_dot(w)))
+        x = xn
+    assert max(errs) < 1e-4, errs
+    return errs
+
+
+def test_drop_vectors_identity_basis(E):
+    case_drop_vectors("cpu", False)
+
+
+def test_drop_vectors_dct_basis(E, assets):
+    case_drop_vectors("cpu", True, assets, steps=3)
+
+
+def test_drop_vectors_needs_the_factor_history(E):
+    """Without max_vector_count at construction there is no factor history to truncate: loud refusal, not a guess."""
+    from free_hunch_b200.covariance import CovarianceHessianBFGS
+    cov = CovarianceHessianBFGS(np.ones(64, np.float32), 400.0, 64, device="cpu", image_shape=(1, 8, 8))
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((1, 1, 8, 8))
+    for _ in range(2):
+        xn = x + 0.3 * rs.standard_normal(x.shape)
+        cov.update_space_step(torch.tensor(0.5 * np.tanh(x)), torch.tensor(0.5 * np.tanh(xn)), 20.0, torch.tensor(x), torch.tensor(xn))
+        x = xn
+    with pytest.raises(NotImplementedError, match="factor history"):
+        cov.drop_vectors(1, 20.0)
+    cov.drop_vectors(0, 20.0)
+    assert cov.vector_count == 0
+
+
 def test_project_to_diagonal_identity_basis(E):
     case_project_to_diagonal(E, "cpu", False)
 
