@@ -43,6 +43,9 @@ _SIGNATURES = {
     "fh_time_update_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "fh_time_update_from_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "fh_mech_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_void_p]),
+    "fh_mech_flag": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_int, c_void_p]),
+    "fh_cov_dot_f64_if": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fh_mech_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_mech_allclose": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "fh_sampler_euler": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_long, c_void_p]),
     "fh_sampler_heun": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_long, c_void_p]),

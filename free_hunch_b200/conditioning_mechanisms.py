@@ -273,13 +273,15 @@ class FreeHunch(ConditioningMechanism):
             mat, info = self.mat_solver(y, x_0_mean.detach(), sigma_t=sigma_f, return_info=True)        # :268
         s2 = sigma_f ** 2
         with self.timer("denoiser"):
-            p_y_xt_grad = torch.autograd.grad((mat.detach() * x_0_mean).sum(), x_t)[0]                   # :280
+            # :280 is grad((mat.detach() * x_0_mean).sum(), x_t): the same VJP with mat as the cotangent -- the sum's
+            # backward multiplies mat by 1.0, so the result is bit-identical and four element-wise launches shorter
+            p_y_xt_grad = torch.autograd.grad(x_0_mean, x_t, grad_outputs=mat.detach().to(x_0_mean.dtype))[0]
         # :283-288.  The reference runs batch 1; with B independent images per call the VJP-vs-Sigma.mat decision is taken
         # PER IMAGE (a whole-batch statistic would make an image's guidance depend on its batch mates).
         if fused:
-            alt = cov.denoiser_cov_vector_dot(mat.detach(), use_cuda=True)                               # Sigma.mat, float64
-            x_0_mean_new, flag = engine.mech_combine(cov.ctx, x_0_mean.detach(), p_y_xt_grad, alt, s2,
-                                                     self.denoiser_mean_error_threshold, self.cond_scaling)
+            # Sigma.mat (float64) is formed only for the images that take that branch, as in the reference's `if`
+            x_0_mean_new, flag = engine.mech_combine_lazy(cov.state, x_0_mean.detach(), p_y_xt_grad, mat.detach(), s2,
+                                                          self.denoiser_mean_error_threshold, self.cond_scaling)
             if self.defer:
                 rec["fallback"] = flag
             else:

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/free_hunch_b200.h"
@@ -176,6 +177,14 @@ static void state_free_buffers(fh_state* p);
 static inline dim3 ew_grid(long d, int B) { return dim3((unsigned)fh_nchunks(d), (unsigned)B, 1); }
 static inline int vec_ok(long d) { return (d % 4 == 0) ? 1 : 0; }
 
+// back-off of the host poll on mapped memory (streaming CG): a pause instruction per probe, the core is yielded after
+// ~1000 probes (a solve iteration is 100-250 us at the batch sizes that take this path)
+static inline void fh_host_relax(long spins) {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+  if (spins > 1000 && (spins & 63) == 0) std::this_thread::yield();
+}
 extern "C" const char* fh_last_error(void) { return g_err.c_str(); }
 extern "C" int fh_version(void) { return 100; }
 extern "C" long long fh_launch_count(int reset) {
@@ -1416,7 +1425,8 @@ static int op_apply64(fh_op* o, const double* in, double* out, int batch, int tr
   if (o->kind == FH_OP_INPAINT) FH_FAIL(FH_EINVAL, "op_apply64: the mask is applied by the caller");
   FhTaps t{o->t_dy, o->t_dx, o->t_w, o->nt, o->ymin, o->ymax, o->xmin, o->xmax};
   if (o->kind == FH_OP_BLUR && o->separable && c->H % 32 == 0 && c->W % 32 == 0 &&
-      (size_t)((32 + o->nc - 1) * (((32 + o->nr - 1) | 1) + 33)) * sizeof(double) <= 48 * 1024) {
+      o->nr <= FH_MAX_SEP_TAPS && o->nc <= FH_MAX_SEP_TAPS &&
+      (size_t)((32 + o->nc - 1) * (((32 + o->nr - 1) | 1) + 33)) * sizeof(double) <= 46 * 1024) {
     FhSepTaps k{o->kr, o->kc, o->nr, o->nc, o->cr, o->cc};
     const int th = 32 + o->nc - 1, tw = (32 + o->nr - 1) | 1;
     const size_t smem = (size_t)(th * tw + th * 33) * sizeof(double);
@@ -1488,7 +1498,13 @@ static int cg_solve_res64(fh_state* s, fh_op* o, FhCgFused P, const double* y, c
 // Sigma v in float64 (denoiser_cov_vector_dot, online_update_bfgs.py:370-374, for a float64 v): one pass of the resident
 // float64 kernel without operator -- 2-D DCT, delta (w_hat + Z^T Gs Z delta w_hat), inverse DCT, all float64.  The mechanism
 // needs it because mu + Sigma mat cancels to ~1 % of its terms at high sigma (a float32 product costs two digits there).
-extern "C" int fh_cov_dot_f64(fh_state* s, const double* v, double* out, void* stream) {
+static int cov_dot_f64(fh_state* s, const double* v, double* out, const int* only_if, void* stream);
+extern "C" int fh_cov_dot_f64(fh_state* s, const double* v, double* out, void* stream) { return cov_dot_f64(s, v, out, nullptr, stream); }
+extern "C" int fh_cov_dot_f64_if(fh_state* s, const double* v, double* out, const int* flag_dev, void* stream) {
+  if (!flag_dev) FH_FAIL(FH_EINVAL, "fh_cov_dot_f64_if needs the device flags");
+  return cov_dot_f64(s, v, out, flag_dev, stream);
+}
+static int cov_dot_f64(fh_state* s, const double* v, double* out, const int* only_if, void* stream) {
   if (!s || !v || !out) FH_FAIL(FH_EINVAL, "bad fh_cov_dot_f64 arguments");
   fh_ctx* c = s->ctx;
   if (s->basis != FH_BASIS_DCT || !c->r64_ok) FH_FAIL(FH_ESTATE, "fh_cov_dot_f64 needs the DCT basis and the resident float64 kernel");
@@ -1504,6 +1520,7 @@ extern "C" int fh_cov_dot_f64(fh_state* s, const double* v, double* out, void* s
     FhCgRes64 R{};
     R.bvec = v + (size_t)b * s->d; R.x_out = out + (size_t)b * s->d;
     R.rtol = 1.0; R.atol = 0.0; R.sy2 = 0.0; R.use_stop = 0; R.image = b; R.apply_only = 1;
+    R.only_if = only_if;
     int rc = launch_res64(c, P, R, st);
     if (rc) return rc;
   }
@@ -1624,6 +1641,7 @@ static int cg_solve_fused(fh_state* s, fh_op* o, const float* y, const float* mu
         ready = ready && (dn || c->mirror_host[2 * b] >= it - FH_RUNAHEAD);
       }
       if (all || ready) break;
+      fh_host_relax(spins);                                         // pause; yield the core after a while (no hot spin)
       if (spins > 200000000L) {                                     // ~seconds: something is wrong, fall back to a hard sync
         FH_CUDA(cudaStreamSynchronize(st));
         break;
@@ -1853,6 +1871,13 @@ extern "C" int fh_cg_resident_time(fh_state* s, fh_op* o, int iters, int reps, f
   R64.bvec = c->d64[0]; R64.x_out = c->d64[1]; R64.rtol = 1.0; R64.atol = 0.0; R64.sy2 = 0.01; R64.use_stop = 0; R64.image = 0; R64.niter_hint = s->hint;
   R64.timing = 1;
   R64.gen = res64_gen(o, s->m, c->r64_smem_max - (int)sizeof(FhRes64Smem) - (int)sizeof(FhRes64Tabs));
+  // its own right-hand side (the workspace may hold anything, e.g. a converged solve's b), in the measurement space
+  {
+    const long nb = s->d;
+    if (f64) FH_LAUNCH(fh_k_fill_pattern<double>, dim3((unsigned)((nb + 255) / 256)), dim3(256), 0, stream, c->d64[0], nb);
+    else FH_LAUNCH(fh_k_fill_pattern<float>, dim3((unsigned)((nb + 255) / 256)), dim3(256), 0, stream, c->cgv[0], nb);
+    FH_KCHECK();
+  }
   cudaEvent_t e0, e1;
   FH_CUDA(cudaEventCreate(&e0)); FH_CUDA(cudaEventCreate(&e1));
   int rc = FH_OK;
@@ -1887,7 +1912,27 @@ extern "C" int fh_mech_combine(fh_ctx* c, const double* mu, const double* g, con
   // the Gram partials buffer is free between covariance updates: (B, nblk, 3) doubles fit easily
   double* part = c->gram_partial;
   FH_LAUNCH(fh_k_mech_stats, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, g, sigma2, part, c->d);
-  FH_LAUNCH(fh_k_mech_combine, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, mu, g, sigv, (const double*)part, nblk, sigma2, threshold, scale, out, flag_dev, c->d);
+  FH_LAUNCH(fh_k_mech_combine, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, mu, g, sigv, (const double*)part, nblk, sigma2, threshold, scale, out, flag_dev, c->d, (const int*)nullptr);
+  FH_KCHECK();
+  return FH_OK;
+}
+
+// The same in two steps, so that Sigma.mat (fh_cov_dot_f64_if) runs only for the images that take that branch -- like the
+// reference, which forms it inside the `if` (conditioning_mechanisms.py:283-286) -- without a host read of the decision.
+extern "C" int fh_mech_flag(fh_ctx* c, const double* g, double sigma2, double threshold, int* flag_dev, int batch, void* stream) {
+  if (!c || !g || !flag_dev || batch < 1 || batch > c->max_batch || !(sigma2 > 0)) FH_FAIL(FH_EINVAL, "bad fh_mech_flag arguments");
+  const int nblk = (int)((c->d + FH_MECH_CHUNK - 1) / FH_MECH_CHUNK);
+  double* part = c->gram_partial;
+  FH_LAUNCH(fh_k_mech_stats, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, g, sigma2, part, c->d);
+  FH_LAUNCH(fh_k_mech_flag, dim3(batch), dim3(FH_MECH_THREADS), 0, stream, (const double*)part, nblk, threshold, flag_dev);
+  FH_KCHECK();
+  return FH_OK;
+}
+extern "C" int fh_mech_apply(fh_ctx* c, const double* mu, const double* g, const double* sigv, double sigma2, double scale,
+                             const int* flag_dev, double* out, int batch, void* stream) {
+  if (!c || !mu || !g || !sigv || !out || !flag_dev || batch < 1 || batch > c->max_batch || !(sigma2 > 0)) FH_FAIL(FH_EINVAL, "bad fh_mech_apply arguments");
+  const int nblk = (int)((c->d + FH_MECH_CHUNK - 1) / FH_MECH_CHUNK);
+  FH_LAUNCH(fh_k_mech_combine, dim3(nblk, batch), dim3(FH_MECH_THREADS), 0, stream, mu, g, sigv, (const double*)nullptr, nblk, sigma2, 0.0, scale, out, (int*)nullptr, c->d, flag_dev);
   FH_KCHECK();
   return FH_OK;
 }

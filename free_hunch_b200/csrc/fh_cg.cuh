@@ -24,9 +24,6 @@
 
 #define FH_MAX_SEP_TAPS 64       // taps are staged zero-padded to a multiple of 4
 #define FH_ZROUND_FLOATS 8192    // floats per TMA round: 32 / ROWS rows of Z, each a strip-wide slice of ROWS*256 floats (32 KB)
-#define ZROUND_FLOATS 8192    // floats per TMA round: 32 / ROWS rows of Z, each a strip-wide slice of ROWS*256 floats
-#define FH_ZSTAGES 2            // rounds in flight (double buffer): 2 * 32 KB = 64 KB of dynamic shared memory
-#define FH_ZBUF_BYTES (FH_ZSTAGES * ZROUND_FLOATS * 4)
 
 struct FhCgFused {
   int B, C, m;                    // images, channels, rows of Z

@@ -51,13 +51,18 @@ fh_k_mech_stats(const double* __restrict__ g, double sigma2, double* __restrict_
 }
 // out = mu + (std(v) > threshold ? sigv * scale : g * scale * sigma^2)   per image (conditioning_mechanisms.py:283-288);
 // flag_out[b] = the decision.  Every CTA merges the chunk statistics itself (same order, same result everywhere).
+// `flag_in` != null: the decision was taken before (fh_k_mech_flag) -- then sigv is only read where the flag is set, which is
+// what lets the caller skip the Sigma.mat product for the other images.
 __global__ void __launch_bounds__(FH_MECH_THREADS)
 fh_k_mech_combine(const double* __restrict__ mu, const double* __restrict__ g, const double* __restrict__ sigv, const double* __restrict__ part,
-                  int nblk, double sigma2, double threshold, double scale, double* __restrict__ out, int* __restrict__ flag_out, long d) {
+                  int nblk, double sigma2, double threshold, double scale, double* __restrict__ out, int* __restrict__ flag_out, long d,
+                  const int* __restrict__ flag_in) {
   __shared__ int s_flag;
   __shared__ double red[33];
   const size_t b = blockIdx.y;
-  {
+  if (flag_in) {
+    if (threadIdx.x == 0) s_flag = flag_in[b];
+  } else {
     // merge of the chunk statistics (Chan et al.): N = sum n_i, mean = sum n_i mean_i / N, M2 = sum (M2_i + n_i (mean_i - mean)^2)
     // as three fixed-order block sums (one chunk per thread; a serial merge by one thread took 32 us per launch)
     const double* p = part + b * nblk * 3;
@@ -91,6 +96,23 @@ fh_k_mech_combine(const double* __restrict__ mu, const double* __restrict__ g, c
       out[j] = fh_add(mu[j], fh_mul(pg, sigma2));
     }
   }
+}
+// The decision alone, one CTA per image: flag[b] = std(g sigma^2) > threshold from the chunk statistics (the same merge, in
+// the same order, as in fh_k_mech_combine).
+__global__ void __launch_bounds__(FH_MECH_THREADS)
+fh_k_mech_flag(const double* __restrict__ part, int nblk, double threshold, int* __restrict__ flag_out) {
+  __shared__ double red[33];
+  const size_t b = blockIdx.x;
+  const double* p = part + b * nblk * 3;
+  double n = 0.0, wsum = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += FH_MECH_THREADS) { n += p[3 * k]; wsum += p[3 * k] * p[3 * k + 1]; }
+  n = fh_block_sum(n, red);
+  wsum = fh_block_sum(wsum, red);
+  const double mean = wsum / n;
+  double m2 = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += FH_MECH_THREADS) { const double dlt = p[3 * k + 1] - mean; m2 += p[3 * k + 2] + p[3 * k] * dlt * dlt; }
+  const double M2 = fh_block_sum(m2, red);
+  if (threadIdx.x == 0) flag_out[b] = sqrt(M2 / (n - 1.0)) > threshold ? 1 : 0;
 }
 // score of the previous evaluation, conditioning_mechanisms.py:243: (mean_prev - x_prev) / sigma_prev^2, as float32 for the state
 __global__ void __launch_bounds__(FH_MECH_THREADS)

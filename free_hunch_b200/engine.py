@@ -372,6 +372,27 @@ def mech_combine(ctx, mu, g, sigv, sigma2, threshold, scale):
     return out, flag
 
 
+def mech_combine_lazy(state, mu, g, mat, sigma2, threshold, scale):
+    """conditioning_mechanisms.py:283-288 with Sigma.mat formed only where it is used, like the reference's `if`: the
+    decision is taken on the device (fh_mech_flag), the Sigma.mat launch exits at once for images whose flag is 0
+    (fh_cov_dot_f64_if), fh_mech_apply combines.  Returns (x0_mean_new, flag) like mech_combine; no host read."""
+    ctx = state.ctx
+    B = mu.shape[0]
+    mu, g, mat = (_prep64(ctx, t, mu.shape) for t in (mu, g, mat))
+    flag = torch.empty(B, dtype=torch.int32, device=ctx.device)
+    _lib.check(_lib.lib().fh_mech_flag(ctx._h, _ptr(g), float(sigma2), float(threshold), _ptr(flag), B, ctx.stream()))
+    sigv = torch.empty_like(mat)
+    rc = _lib.lib().fh_cov_dot_f64_if(state._h, _ptr(mat), _ptr(sigv), _ptr(flag), ctx.stream())
+    if rc == FH_ESTATE:                      # no float64 resident kernel for this state: the unconditional product
+        sigv = state.cov_dot(mat)
+    else:
+        _lib.check(rc)
+    out = torch.empty_like(mu)
+    _lib.check(_lib.lib().fh_mech_apply(ctx._h, _ptr(mu), _ptr(g), _ptr(sigv), float(sigma2), float(scale), _ptr(flag),
+                                        _ptr(out), B, ctx.stream()))
+    return out, flag
+
+
 def mech_notclose(ctx, a, b):
     """(B,) int32 device tensor: 0 where torch.allclose(a_b, b_b) holds (conditioning_mechanisms.py:250)."""
     B = a.shape[0]

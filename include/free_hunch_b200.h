@@ -140,6 +140,13 @@ int fh_time_update_from_mean(fh_state* st, const double* x_prev_dev, const doubl
  * fh_sampler_euler / fh_sampler_heun: generate_conditional.py:146-149 and :160-167. */
 int fh_mech_combine(fh_ctx* ctx, const double* mu_dev, const double* g_dev, const double* sigv_dev, double sigma2, double threshold,
                     double scale, double* out_dev, int* flag_dev, int batch, void* stream);
+/* The same in two steps: fh_mech_flag takes the decision (device memory), fh_cov_dot_f64_if forms Sigma.mat only for the
+ * images whose flag is set -- the reference computes it inside the `if` (:283-286) -- and fh_mech_apply combines.  An
+ * image whose flag is 0 costs one early-exit launch instead of a Sigma.v product, still without a host read. */
+int fh_mech_flag(fh_ctx* ctx, const double* g_dev, double sigma2, double threshold, int* flag_dev, int batch, void* stream);
+int fh_cov_dot_f64_if(fh_state* st, const double* v_dev, double* out_dev, const int* flag_dev, void* stream);
+int fh_mech_apply(fh_ctx* ctx, const double* mu_dev, const double* g_dev, const double* sigv_dev, double sigma2, double scale,
+                  const int* flag_dev, double* out_dev, int batch, void* stream);
 int fh_mech_allclose(fh_ctx* ctx, const double* a_dev, const double* b_dev, int* notclose_dev, int batch, void* stream);
 int fh_sampler_euler(const double* x_hat_dev, const double* den_dev, double t_cur, double h, double* d_cur_dev, double* x_prime_dev,
                      long n, void* stream);
@@ -196,7 +203,9 @@ int fh_cg_solve_f64_async(fh_state* st, fh_op* op, const double* y_dev, const do
  * 3 inv_rows, 4 xr.  Only for operators that fold into the DCT passes (inpainting, separable blur). */
 int fh_cg_kernel_time(fh_state* st, fh_op* op, int which, int reps, float* ms_out, void* stream);
 /* The same for the resident solve (FH_CG_RESIDENT): average device time (ms) of `reps` launches that each run exactly
- * `iters` CG iterations of image 0 at the state's current rank. */
+ * `iters` CG iterations of image 0 at the state's current rank.  The entry point fills its own right-hand side (a fixed
+ * pseudo-random pattern) and uses sigma_y^2 = 0.01 (the reference's noise level 0.1, measurement config); convergence
+ * does not end a launch early. */
 int fh_cg_resident_time(fh_state* st, fh_op* op, int iters, int reps, float* ms_out, void* stream);
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 long long fh_launch_count(int reset);
