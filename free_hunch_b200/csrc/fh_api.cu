@@ -1435,13 +1435,14 @@ static int op_apply64(fh_op* o, const double* in, double* out, int batch, int tr
     if (c->H % 32 || c->W % 32) FH_FAIL(FH_EINVAL, "blur needs image sizes divisible by 32");
     const int th = 32 + (o->ymax - o->ymin), tw = (32 + (o->xmax - o->xmin)) | 1;
     const size_t smem = (size_t)th * tw * sizeof(double);
-    if (smem > 48 * 1024) FH_FAIL(FH_EINVAL, "PSF support too large for the float64 convolution tile");
+    if (smem > 42 * 1024) FH_FAIL(FH_EINVAL, "PSF support too large for the float64 convolution tile");   // + 6 KB of staged taps
     FH_LAUNCH(fh_k_conv_taps64, dim3(c->W / 32, c->H / 32, planes), dim3(32, 8), smem, stream, in, out, t, c->H, c->W, transpose);
   } else if (!transpose) {
     const int n = (c->H / o->sf) * (c->W / o->sf);
-    FH_LAUNCH(fh_k_sr_forward64, dim3((n + 255) / 256, planes), dim3(256), 0, stream, in, out, t, c->H, c->W, o->sf);
+    FH_LAUNCH(fh_k_sr_forward64, dim3((n + 7) / 8, planes), dim3(256), 0, stream, in, out, t, c->H, c->W, o->sf);   // a warp per pixel
   } else {
     const int n = c->H * c->W;
+    if (o->ymax - o->ymin + 1 > FH_SR_PSF_MAX || o->xmax - o->xmin + 1 > FH_SR_PSF_MAX) FH_FAIL(FH_EINVAL, "PSF support too large for the float64 super-resolution transpose");
     FH_LAUNCH(fh_k_sr_transpose64, dim3((n + 255) / 256, planes), dim3(256), 0, stream, in, out, t, c->H, c->W, o->sf);
   }
   FH_KCHECK();

@@ -426,6 +426,7 @@ __device__ __forceinline__ double fh_widen_alu(float f) {
 // A CTA owns rows [grow0, grow0 + nrows) of one plane.  A^T r and A t need rows of OTHER CTAs, so the operand is first
 // published to global memory (it stays in L2), the grid synchronises, and every CTA gathers its halo back into shared
 // memory.  Two extra grid barriers per iteration compared with the mask / separable blur, which fold into the DCT passes.
+#define FH_TAPS64_CHUNK 512       // taps staged per round in fh_k_conv_taps64 (6 KB of static shared memory)
 #define FH_R64_SRP 28             // padded PSF row length of the x4 SR gathers (25 taps + 3 zeros: b0 + 4 t never leaves the row)
 
 // 16-byte asynchronous copies global -> shared past L1 (the published planes are rewritten every iteration by other CTAs:
@@ -1140,62 +1141,109 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
 __global__ void __launch_bounds__(256)
 fh_k_conv_taps64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int transpose) {
   FH_DYN_SMEM(double, sm);
+  // taps staged per CTA in chunks of FH_TAPS64_CHUNK: (offset inside the tile, float64 weight) -- the first version read
+  // dy / dx / w from global memory and widened the weight inside the loop (38 us per call for the 217-tap motion PSF)
+  __shared__ int s_off[FH_TAPS64_CHUNK];
+  __shared__ double s_w[FH_TAPS64_CHUNK];
   const int oy0 = transpose ? taps.ymin : -taps.ymax, oy1 = transpose ? taps.ymax : -taps.ymin;
   const int ox0 = transpose ? taps.xmin : -taps.xmax, ox1 = transpose ? taps.xmax : -taps.xmin;
   const int th = 32 + (oy1 - oy0), tw = 32 + (ox1 - ox0);
   const int tws = tw | 1;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const size_t plane = (size_t)blockIdx.z * H * W;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  for (int r = threadIdx.y; r < th; r += 8) {
-    int gi = (i0 + oy0 + r) % H; if (gi < 0) gi += H;
-    const double* srow = in + plane + (size_t)gi * W;
-    for (int c = threadIdx.x; c < tw; c += 32) {
-      int gj = (j0 + ox0 + c) % W; if (gj < 0) gj += W;
-      sm[r * tws + c] = srow[gj];
+  for (int base = tid; base < th * tws; base += 256 * 8) {        // 8 halo loads in flight per thread
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + 256 * u, r = idx / tws, c = idx - r * tws;
+      v[u] = 0.0;
+      if (r < th && c < tw) {
+        int gi = (i0 + oy0 + r) % H, gj = (j0 + ox0 + c) % W;
+        gi += (gi < 0) ? H : 0; gj += (gj < 0) ? W : 0;
+        v[u] = in[plane + (size_t)gi * W + gj];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + 256 * u;
+      if (idx < th * tws) sm[idx] = v[u];
     }
   }
-  __syncthreads();
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const double* base = sm + threadIdx.y * tws + threadIdx.x;
-  for (int t = 0; t < taps.n; ++t) {
-    const int oy = transpose ? taps.dy[t] : -taps.dy[t];
-    const int ox = transpose ? taps.dx[t] : -taps.dx[t];
-    const double wv = (double)taps.w[t];
-    const double* p = base + (oy - oy0) * tws + (ox - ox0);
+  for (int t0 = 0; t0 < taps.n; t0 += FH_TAPS64_CHUNK) {
+    const int nt = min(FH_TAPS64_CHUNK, taps.n - t0);
+    __syncthreads();                                              // tile complete / previous chunk consumed
+    for (int t = tid; t < nt; t += 256) {
+      const int oy = transpose ? taps.dy[t0 + t] : -taps.dy[t0 + t];
+      const int ox = transpose ? taps.dx[t0 + t] : -taps.dx[t0 + t];
+      s_off[t] = (oy - oy0) * tws + (ox - ox0);
+      s_w[t] = (double)taps.w[t0 + t];
+    }
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+      const double wv = s_w[t];
+      const double* p = base + s_off[t];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = fma(wv, p[8 * q * tws], acc[q]);
+      for (int q = 0; q < 4; ++q) acc[q] = fma(wv, p[8 * q * tws], acc[q]);
+    }
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) out[plane + (size_t)(i0 + threadIdx.y + 8 * q) * W + j0 + threadIdx.x] = acc[q];
 }
-// Super-resolution in float64: forward = conv then [0::sf, 0::sf]; transpose = zero insertion then conv^T (utils_sisr.py:44-61).
+// x4 super-resolution in float64, once per solve (right-hand side b = y - A mu and result A^T u; utils_sisr.py:44-61).
+//   forward:   out[I][J] = sum_t w_t in[(sf I - dy_t) mod H][(sf J - dx_t) mod W]          (blur, then keep every sf-th pixel)
+//   transpose: out[i][j] = sum_t w_t up(in)[(i + dy_t) mod H][(j + dx_t) mod W],  up = zero insertion
+// The first versions walked the whole tap list per output with one accumulator (625 dependent FMAs and as many index
+// loads; the transpose tested every tap for divisibility by sf): 60 and 211 us per call, 16 ms of a 70 ms image.
+// forward: one WARP per measurement pixel, the taps spread over its lanes, shuffle reduction.
 __global__ void __launch_bounds__(256)
 fh_k_sr_forward64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int sf) {
   const int h = H / sf, w = W / sf;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const size_t p = blockIdx.y;
-  if (idx >= h * w) return;
+  if (idx >= h * w) return;                                   // warp-uniform
   const int I = idx / w, J = idx % w;
   const double* src = in + p * (size_t)H * W;
   double acc = 0.0;
-  for (int t = 0; t < taps.n; ++t) {
+  for (int t = lane; t < taps.n; t += 32) {
     const int gi = (sf * I - taps.dy[t] + H) & (H - 1), gj = (sf * J - taps.dx[t] + W) & (W - 1);
     acc = fma((double)taps.w[t], src[(size_t)gi * W + gj], acc);
   }
-  out[p * (size_t)h * w + idx] = acc;
+  acc = fh_warp_sum(acc);
+  if (lane == 0) out[p * (size_t)h * w + idx] = acc;
 }
+// transpose: the PSF as a dense (ymax - ymin + 1) x (xmax - xmin + 1) float64 array in shared memory; an output pixel visits
+// only the taps of its own polyphase component (dy = -i, dx = -j mod sf: 1 / sf^2 of them), in the tap list's row-major order.
+#define FH_SR_PSF_MAX 33
 __global__ void __launch_bounds__(256)
 fh_k_sr_transpose64(const double* __restrict__ in, double* __restrict__ out, FhTaps taps, int H, int W, int sf) {
+  __shared__ double s_psf[FH_SR_PSF_MAX * FH_SR_PSF_MAX];
+  const int ph = taps.ymax - taps.ymin + 1, pw = taps.xmax - taps.xmin + 1;
+  for (int t = threadIdx.x; t < ph * pw; t += blockDim.x) s_psf[t] = 0.0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < taps.n; t += blockDim.x) s_psf[(taps.dy[t] - taps.ymin) * pw + (taps.dx[t] - taps.xmin)] = (double)taps.w[t];
+  __syncthreads();
   const int h = H / sf, w = W / sf;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t p = blockIdx.y;
   if (idx >= H * W) return;
   const int i = idx / W, j = idx % W;
   const double* src = in + p * (size_t)h * w;
+  // first offsets with (i + dy) and (j + dx) divisible by sf
+  int dy0 = taps.ymin + ((((-i - taps.ymin) % sf) + sf) % sf);
+  int dx0 = taps.xmin + ((((-j - taps.xmin) % sf) + sf) % sf);
   double acc = 0.0;
-  for (int t = 0; t < taps.n; ++t) {
-    const int gi = (i + taps.dy[t] + H) & (H - 1), gj = (j + taps.dx[t] + W) & (W - 1);
-    if ((gi % sf) == 0 && (gj % sf) == 0) acc = fma((double)taps.w[t], src[(size_t)(gi / sf) * w + gj / sf], acc);
+  for (int dy = dy0; dy <= taps.ymax; dy += sf) {
+    const int gi = ((i + dy + H) & (H - 1)) / sf;
+    const double* prow = s_psf + (dy - taps.ymin) * pw - taps.xmin;
+    const double* srow = src + (size_t)gi * w;
+    for (int dx = dx0; dx <= taps.xmax; dx += sf) {
+      const int gj = ((j + dx + W) & (W - 1)) / sf;
+      acc = fma(prow[dx], srow[gj], acc);
+    }
   }
   out[p * (size_t)H * W + idx] = acc;
 }
