@@ -509,7 +509,9 @@ def run_b200(a, assets):
         flush.fill_(1)
         barrier()
         t0 = time.perf_counter()
-        x, _ = sample(op, y_pin.to(dev, non_blocking=True), n_pin.to(dev, non_blocking=True))
+        # `mech` is rebound like in the device-resident arm: holding the last mechanism of that arm AND the previous pass's
+        # would keep three covariance states alive and make the first timed pass allocate one (cudaMalloc in the loop)
+        x, mech = sample(op, y_pin.to(dev, non_blocking=True), n_pin.to(dev, non_blocking=True))
         out_pin.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
         if k >= 0:

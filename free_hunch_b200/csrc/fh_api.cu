@@ -100,7 +100,8 @@ extern "C" int fh_prof_report(char* buf, int buflen) { if (buf && buflen > 0) bu
     if (_e != cudaSuccess) FH_FAIL(FH_ECUDA, "kernel launch failed: %s", cudaGetErrorString(_e)); \
   } while (0)
 
-#define FH_STATE_POOL 2                // parked states per context (one image's state is ~60 MB)
+#define FH_STATE_POOL 3                // parked states per context (one image's state is ~60 MB)
+#define FH_STATE_SPARES 2              // spare buffer sets allocated together with a state that missed the pool
 struct fh_ctx {
   int device, max_batch, C, H, W, max_rank;
   long d;
@@ -497,16 +498,18 @@ extern "C" int fh_state_create(fh_ctx* c, fh_state** out, int batch, int basis) 
   }
   int rc = state_alloc(c, s, batch);
   if (rc) { state_free_buffers(s); cudaGetLastError(); return rc; }      // partial allocation: nothing leaks
-  // A sampler typically builds the next image's state while it still holds the previous one: allocate a spare set of
-  // buffers together with the first state, so that the second image does not pay ~100 ms of cudaMalloc in its loop.
-  {
-    const int i = pool_slot_for(c, batch);
-    if (i >= 0) {
-      fh_state* spare = (fh_state*)calloc(1, sizeof(fh_state));
-      spare->ctx = c; spare->B = batch; spare->basis = basis; spare->d = c->d;
-      if (state_alloc(c, spare, batch) == FH_OK) c->state_pool[i] = spare;
-      else { state_free_buffers(spare); cudaGetLastError(); }
-    }
+  // A sampler typically builds the next image's state while it still holds the previous one (or two: a caller that keeps
+  // the last mechanism for its log while the next image is sampled): allocate spare sets of buffers together with a state
+  // that missed the pool, so that the following images do not pay cudaMalloc inside their loop -- ~2 ms per state as a
+  // rule, but 100 - 340 ms every now and then on a busy box (measured: bench.py's first end-to-end step).
+  for (int k = 0; k < FH_STATE_SPARES; ++k) {
+    int i = -1;
+    for (int j = 0; j < FH_STATE_POOL; ++j) if (!c->state_pool[j]) { i = j; break; }
+    if (i < 0) break;
+    fh_state* spare = (fh_state*)calloc(1, sizeof(fh_state));
+    spare->ctx = c; spare->B = batch; spare->basis = basis; spare->d = c->d;
+    if (state_alloc(c, spare, batch) == FH_OK) c->state_pool[i] = spare;
+    else { state_free_buffers(spare); cudaGetLastError(); break; }
   }
   *out = s;
   return FH_OK;
