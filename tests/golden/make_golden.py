@@ -559,7 +559,7 @@ def export_assets():
 if __name__ == "__main__":
     ob, cm, rcg, ms, sisr = import_reference()
     which = sys.argv[1:] or ["unit", "small", "misc", "assets", "full", "mech", "mech_tight"]
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(int(os.environ.get("FH_GOLDEN_THREADS", os.cpu_count())))
     if "assets" in which: export_assets()
     if "unit" in which: golden_unit(ob)
     if "small" in which: golden_dct_small(ob)
