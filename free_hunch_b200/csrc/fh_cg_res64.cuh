@@ -549,26 +549,64 @@ __device__ __forceinline__ void fh_r64_sr_gather_at(const double* ysrc, double* 
   const int nI = ((row0 + FH_RES_ROWS - 1 + (G.ks - 1 - c)) >> 2) - Ilo + 1;    // <= 10
   const double* yp = ysrc + (size_t)pl * (FH_N / 4) * (FH_N / 4);
   __syncthreads();
-  for (int idx = tid; idx < nI * 64; idx += FH_PASS_THREADS)
-    ys[idx] = fh_ldcg(yp + (size_t)((Ilo + (idx >> 6)) & 63) * 64 + (idx & 63));
+  {
+    // <= 640 values: all three loads of a thread in flight together (as a loop each load waited for the store of the one
+    // before it: three L2 round trips instead of one)
+    double v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int idx = tid + FH_PASS_THREADS * u;
+      v[u] = idx < nI * 64 ? fh_ldcg(yp + (size_t)((Ilo + (idx >> 6)) & 63) * 64 + (idx & 63)) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int idx = tid + FH_PASS_THREADS * u;
+      if (idx < nI * 64) ys[idx] = v[u];
+    }
+  }
   __syncthreads();
   const int j = tid;
   const int b0 = (4 - ((j - c) & 3)) & 3;
   int qt[7];
 #pragma unroll
   for (int t = 0; t < 7; ++t) qt[t] = ((j + b0 + 4 * t - c) >> 2) & 63;
-  for (int e = 0; e < nrows; ++e) {
+  // All 6 rows of the strip at once: 6 independent accumulator chains (the first version walked the rows one after another
+  // with ONE accumulator -- 49 dependent DFMAs per output, 294 per thread, at the latency of the FP64 pipe: 20 us of a 45 us
+  // iteration).  Row e takes the taps a = a0[e] + 4 u; per output the order of the sum is unchanged (a ascending, t
+  // ascending), so the results are bit-identical.  Rows beyond nrows (the last strip of a plane) are computed on whatever
+  // the staging area holds and never stored.
+  int a0[FH_RES_ROWS];
+  const double* yb[FH_RES_ROWS];
+  double acc[FH_RES_ROWS];
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e) {
     const int i = row0 + e;
-    const int a0 = (4 - ((i - c) & 3)) & 3;
-    double acc = 0.0;
-    for (int a = a0; a < G.ks; a += 4) {
-      const double* yr = ys + (size_t)(((i + a - c) >> 2) - Ilo) * 64;
+    a0[e] = (4 - ((i - c) & 3)) & 3;
+    yb[e] = ys + (size_t)(((i + a0[e] - c) >> 2) - Ilo) * 64;              // + 64 per round: a grows by 4
+    acc[e] = 0.0;
+  }
+  const int nfull = G.ks >> 2;                                             // rounds in which every row's tap row a0 + 4 u exists (a0 <= 3)
+  for (int u = 0; u < nfull; ++u) {
+#pragma unroll
+    for (int e = 0; e < FH_RES_ROWS; ++e) {
+      const double* yr = yb[e] + u * 64;
+      const double* kr = spsf + (a0[e] + 4 * u) * FH_R64_SRP + b0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) acc[e] = fma(kr[4 * t], yr[qt[t]], acc[e]);   // taps beyond ks are zero
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e) {
+    for (int a = a0[e] + 4 * nfull; a < G.ks; a += 4) {
+      const double* yr = ys + (size_t)(((row0 + e + a - c) >> 2) - Ilo) * 64;
       const double* kr = spsf + a * FH_R64_SRP + b0;
 #pragma unroll
-      for (int t = 0; t < 7; ++t) acc = fma(kr[4 * t], yr[qt[t]], acc);    // taps beyond ks are zero
+      for (int t = 0; t < 7; ++t) acc[e] = fma(kr[4 * t], yr[qt[t]], acc[e]);
     }
-    out_rows[e * FH_R64_RS + FH_R64_POS(j)] = acc;
   }
+#pragma unroll
+  for (int e = 0; e < FH_RES_ROWS; ++e)
+    if (e < nrows) out_rows[e * FH_R64_RS + FH_R64_POS(j)] = acc[e];
   __syncthreads();
 }
 // mode 4, A: the CTA's own measurement rows [yr0, yr0 + nyr) of plane pl from the published image tsrc   (utils_sisr.py:55-61)
@@ -599,11 +637,26 @@ __device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigne
       fh_cp_wait<0>();
     }
     __syncthreads();
-    double acc = 0.0;
-    for (int q = part; q < G.ks * G.ks; q += 16) {
-      const int a = q / G.ks, b = q - a * G.ks;
-      acc = fma(spsf[a * FH_R64_SRP + b], tile[(2 * c - a) * TW + 4 * el + 2 * c - b], acc);
+    // lane `part` of an element's 16 takes columns b = part and part + 16 of every PSF row: four independent accumulators
+    // (even / odd rows x the two columns) and no index division -- the first version walked q = part, part + 16, ... with
+    // one accumulator and q / ks per tap: 39 dependent DFMAs per step at the latency of the FP64 pipe.
+    double ac0 = 0.0, ac1 = 0.0, ac2 = 0.0, ac3 = 0.0;
+    const bool two = part + 16 < G.ks;
+    const bool one = part < G.ks;
+    {
+      const double* kp = spsf + part;
+      const double* tp0 = tile + (2 * c) * TW + 4 * el + 2 * c - part;
+      int a = 0;
+      for (; a + 1 < G.ks; a += 2) {
+        if (one) { ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0); ac1 = fma(kp[(a + 1) * FH_R64_SRP], tp0[-(a + 1) * TW], ac1); }
+        if (two) { ac2 = fma(kp[a * FH_R64_SRP + 16], tp0[-a * TW - 16], ac2); ac3 = fma(kp[(a + 1) * FH_R64_SRP + 16], tp0[-(a + 1) * TW - 16], ac3); }
+      }
+      if (a < G.ks) {
+        if (one) ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0);
+        if (two) ac2 = fma(kp[a * FH_R64_SRP + 16], tp0[-a * TW - 16], ac2);
+      }
     }
+    double acc = (ac0 + ac1) + (ac2 + ac3);
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
