@@ -1355,7 +1355,8 @@ static FhR64Gen res64_gen(const fh_op* o, int m = 0, int smem_room = 180 * 1024)
     }
   } else if (o->kind == FH_OP_SR && c->H == 256 && c->W == 256 && o->sf == 4 && o->ks <= FH_SR_KS && ((o->ks / 2) & 3) == 0) {
     G.mode = 4; G.psf = o->psf_dense; G.ks = o->ks;
-    G.gbuf_bytes = (int)(((size_t)(FH_SR_KS * FH_R64_SRP + 10 * 64 + 128 + 2 * FH_SR_KS * (64 + 24)) * sizeof(double) + 15) & ~(size_t)15);
+    // PSF rows, 10 measurement rows (A^T), 128 results, the image windows of the (at most two) runs of vertically adjacent groups (A)
+    G.gbuf_bytes = (int)(((size_t)(FH_SR_KS * FH_R64_SRP + 10 * 64 + 128 + FH_R64_SR_WROWS * (64 + 24)) * sizeof(double) + 15) & ~(size_t)15);
   }
   return G;
 }

@@ -609,43 +609,52 @@ __device__ __forceinline__ void fh_r64_sr_gather_at(const double* ysrc, double* 
     if (e < nrows) out_rows[e * FH_R64_RS + FH_R64_POS(j)] = acc[e];
   __syncthreads();
 }
-// mode 4, A: the CTA's own measurement rows [yr0, yr0 + nyr) of plane pl from the published image tsrc   (utils_sisr.py:55-61)
-//   y[I][J] = sum_{a,b} k[a][b] t[(4 I - a + c) & 255][(4 J - b + c) & 255];  thread t < 64 nyr gets element (yr0 + t / 64, t % 64)
-// 16 measurement columns per step: their 25 x 88 image window is staged (double-buffered), 16 threads share an element.
-__device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigned char* gbuf, const FhR64Gen& G, int pl, int yr0, int nyr) {
+// mode 4, A: the CTA's own measurement elements of plane pl from the published image tsrc   (utils_sisr.py:55-61)
+//   y[I][J] = sum_{a,b} k[a][b] t[(4 I - a + c) & 255][(4 J - b + c) & 255]
+// Ownership: the 64 x 64 plane in 256 GROUPS of 16 elements, group g = (column block g >> 6, row g & 63) -- column-major, so
+// that the 5 or 6 consecutive groups [g0, g0 + ng) of a CTA are vertical neighbours whose 25-row image windows overlap in 21
+// rows: ONE window of (4 (n - 1) + 25) x 88 values per run of n groups inside a column block (at most two runs), staged by
+// cp.async, instead of a 25 x 88 window per group (the first version owned whole measurement rows: 4 or 8 windows per CTA,
+// each exposing its L2 round trip, 13.6 MB through L2 per iteration -- 10.8 of the 29.5 us of an iteration on the CTAs
+// with two rows).  Thread t < 16 ng owns element (group g0 + t / 16, column 16 (g >> 6) + t % 16); 16 threads share the
+// taps of an element.  Returns the thread's own element.
+#define FH_R64_SR_WROWS (4 * 6 - 8 + 2 * FH_SR_KS)                          // rows of both windows together: 4 (n - 1) + 25 each, n1 + n2 <= 6
+__device__ __forceinline__ int fh_r64_sr_yindex(int g, int el) { return 64 * (g & 63) + 16 * (g >> 6) + el; }
+__device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigned char* gbuf, const FhR64Gen& G, int pl, int g0, int ng) {
   const int tid = threadIdx.x;
   const int c = G.ks / 2;
   double* spsf = reinterpret_cast<double*>(gbuf);
-  double* qy = spsf + FH_SR_KS * FH_R64_SRP + 10 * 64;                     // [2][64] results
+  double* qy = spsf + FH_SR_KS * FH_R64_SRP + 10 * 64;                     // [128] results
   constexpr int TW = 64 + 2 * 12, NPC = TW / 2;
-  double* tile0 = qy + 128;                                                // [2][25][88] image windows
+  double* tile0 = qy + 128;                                                // [FH_R64_SR_WROWS][88]: the windows of the two runs, back to back
   const double* plane = tsrc + (size_t)pl * FH_N * FH_N;
   const int el = tid >> 4, part = tid & 15;
-  const int nstep = 4 * nyr;
+  // runs: [g0, gm) and [gm, g0 + ng), gm = the column-block boundary inside the range (or its end)
+  const int gend = g0 + ng;
+  const int gm = min(gend, ((g0 >> 6) + 1) << 6);
   __syncthreads();
-  fh_r64_stage_tile(tile0, TW, plane, 4 * yr0 - c, -c, FH_SR_KS, NPC);
+  fh_r64_stage_tile(tile0, TW, plane, 4 * (g0 & 63) - c, 64 * (g0 >> 6) - c, 4 * (gm - g0 - 1) + FH_SR_KS, NPC);
   fh_cp_commit();
-  for (int st = 0; st < nstep; ++st) {
-    const int yr = st >> 2, ch = st & 3;
-    double* tile = tile0 + (size_t)(st & 1) * FH_SR_KS * TW;
-    if (st + 1 < nstep) {
-      const int yr1 = (st + 1) >> 2, ch1 = (st + 1) & 3;
-      fh_r64_stage_tile(tile0 + (size_t)((st + 1) & 1) * FH_SR_KS * TW, TW, plane, 4 * (yr0 + yr1) - c, 64 * ch1 - c, FH_SR_KS, NPC);
-      fh_cp_commit();
-      fh_cp_wait<1>();
-    } else {
-      fh_cp_wait<0>();
-    }
+  const int rows0 = 4 * (gm - g0 - 1) + FH_SR_KS;
+  if (gm < gend) fh_r64_stage_tile(tile0 + rows0 * TW, TW, plane, 4 * (gm & 63) - c, 64 * (gm >> 6) - c, 4 * (gend - gm - 1) + FH_SR_KS, NPC);
+  fh_cp_commit();
+  const bool two = part + 16 < G.ks;
+  const bool one = part < G.ks;
+  for (int run = 0; run < 2; ++run) {
+    const int ga = run ? gm : g0, gb = run ? gend : gm;
+    if (ga >= gb) break;
+    if (run == 0) fh_cp_wait<1>(); else fh_cp_wait<0>();
     __syncthreads();
-    // lane `part` of an element's 16 takes columns b = part and part + 16 of every PSF row: four independent accumulators
-    // (even / odd rows x the two columns) and no index division -- the first version walked q = part, part + 16, ... with
-    // one accumulator and q / ks per tap: 39 dependent DFMAs per step at the latency of the FP64 pipe.
-    double ac0 = 0.0, ac1 = 0.0, ac2 = 0.0, ac3 = 0.0;
-    const bool two = part + 16 < G.ks;
-    const bool one = part < G.ks;
-    {
+    const double* tile = tile0 + (size_t)run * rows0 * TW;
+    for (int g = ga; g < gb; ++g) {
+      // lane `part` of an element's 16 takes columns b = part and part + 16 of every PSF row: four independent accumulators
+      // (even / odd rows x the two columns) and no index division -- the first version walked q = part, part + 16, ... with
+      // one accumulator and q / ks per tap
+      double ac0 = 0.0, ac1 = 0.0, ac2 = 0.0, ac3 = 0.0;
       const double* kp = spsf + part;
-      const double* tp0 = tile + (2 * c) * TW + 4 * el + 2 * c - part;
+      const double* tp0 = tile + (4 * (g - ga) + 2 * c) * TW + 4 * el + 2 * c - part;
+      // (fully unrolling this loop over the 25 PSF rows was measured slower: 5.8 -> 6.6 us per gather at rank 0, 12.9 -> 19.8
+      // at rank 32 -- the kernel is already at the limit of the instruction cache)
       int a = 0;
       for (; a + 1 < G.ks; a += 2) {
         if (one) { ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0); ac1 = fma(kp[(a + 1) * FH_R64_SRP], tp0[-(a + 1) * TW], ac1); }
@@ -655,16 +664,16 @@ __device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigne
         if (one) ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0);
         if (two) ac2 = fma(kp[a * FH_R64_SRP + 16], tp0[-a * TW - 16], ac2);
       }
+      double acc = (ac0 + ac1) + (ac2 + ac3);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (part == 0) qy[16 * (g - g0) + el] = acc;
     }
-    double acc = (ac0 + ac1) + (ac2 + ac3);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (part == 0) qy[yr * 64 + 16 * ch + el] = acc;
-    __syncthreads();                                                       // the window is restaged two steps later
   }
-  return tid < 64 * nyr ? qy[tid] : 0.0;
+  __syncthreads();
+  return tid < 16 * ng ? qy[tid] : 0.0;
 }
 
 // grid = 43 CTAs per plane (cooperative), block = 256, dynamic shared memory = FhRes64Smem [+ tables] [+ gather staging]
@@ -726,9 +735,10 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
   const size_t soff = (size_t)grow0 * FH_N;
   const int fuse = R.gen.mode ? R.gen.mode : P.fuse;
   // measurement-space ownership: the strip itself, except x4 super-resolution (64 x 64 planes: 1 or 2 rows per CTA)
-  const int yr0 = (cc * (FH_N / 4)) / FH_R64_CPP, nyr = ((cc + 1) * (FH_N / 4)) / FH_R64_CPP - yr0;
-  const size_t yoff = (size_t)pl * (FH_N / 4) * (FH_N / 4) + (size_t)yr0 * (FH_N / 4);       // fuse == 4 only
-  const bool yown = tid < 64 * nyr;
+  // (the 4096 elements of a 64 x 64 plane in 256 column-major groups of 16, 5 or 6 groups per CTA: fh_r64_sr_gather_a)
+  const int yg0 = (cc * 256) / FH_R64_CPP, yng = ((cc + 1) * 256) / FH_R64_CPP - yg0;
+  const bool yown = tid < 16 * yng;
+  const size_t yidx = (size_t)pl * (FH_N / 4) * (FH_N / 4) + (size_t)fh_r64_sr_yindex(yg0 + (yown ? tid >> 4 : 0), tid & 15);   // fuse == 4 only
 
   if (R.only_if && R.only_if[R.image] == 0) return;   // uniform over the grid: no CTA reaches a grid barrier
   // ---- prologue ----
@@ -768,12 +778,12 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     for (int u = 0; u < NG; ++u) gs[u] = (cpart + CP * u < m) ? g[cpart + CP * u] : 0.0;
   }
   unsigned bar_target = 0;
-  // CG vectors of the measurement space.  fuse 1..3: the strip (6 per thread).  fuse 4: element 0 of threads < 64 nyr.
+  // CG vectors of the measurement space.  fuse 1..3: the strip (6 per thread).  fuse 4: element 0 of threads < 16 yng.
   double x[FH_RES_ROWS], r[FH_RES_ROWS], p[FH_RES_ROWS], wp[FH_RES_ROWS];
   if (fuse == 4) {
 #pragma unroll
     for (int e = 0; e < FH_RES_ROWS; ++e) x[e] = 0.0;
-    if (yown) x[0] = R.bvec[yoff + tid];
+    if (yown) x[0] = R.bvec[yidx];
   } else {
     fh_r64_load(R.bvec + soff, x, npair);
   }
@@ -836,13 +846,15 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     FH_R64TRACE(0);
     if (fuse >= 3) {
       // publish r (measurement space) and meet: the r.r partial rides on this barrier instead of the next one
-      if (fuse == 4) { if (yown) R.T[1][yoff + tid] = r[0]; }
+      if (fuse == 4) { if (yown) R.T[1][yidx] = r[0]; }
       else fh_r64_store(R.T[1] + soff, r, npair);
       __syncthreads();
       if (tid == 0) R.ride[0][s] = fh_r64_sum8(sm.s_red[3]);
       fh_grid_sync(R.grid_counter, bar_target, nblk);
+      FH_R64TRACE(11);
       if (fuse == 4) fh_r64_sr_gather_at(R.T[1], rows_a, gbuf, R.gen, pl, prow0, nrows);
       else fh_r64_gather_conv(R.T[1], rows_a, gbuf, R.gen, pl, prow0, 1);
+      FH_R64TRACE(12);
     } else {
       double w[FH_RES_ROWS];
 #pragma unroll
@@ -1138,9 +1150,11 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
       if (fuse >= 3) {
         // publish t = Sigma A^T p (image space), meet, gather A t for the own measurement elements
         fh_r64_store(R.T[0] + soff, t, npair);
+        FH_R64TRACE(13);
         fh_grid_sync(R.grid_counter, bar_target, nblk);
+        FH_R64TRACE(14);
         if (fuse == 4) {
-          const double q0 = fh_r64_sr_gather_a(R.T[0], gbuf, R.gen, pl, yr0, nyr);
+          const double q0 = fh_r64_sr_gather_a(R.T[0], gbuf, R.gen, pl, yg0, yng);
 #pragma unroll
           for (int e = 0; e < FH_RES_ROWS; ++e) t[e] = 0.0;
           t[0] = q0;
@@ -1148,6 +1162,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
           fh_r64_gather_conv(R.T[0], rows_a, gbuf, R.gen, pl, prow0, 0);
           fh_r64_get(rows_a, t, npair);
         }
+        FH_R64TRACE(15);
       }
       double rr = 0.0;
       if (k == 0) {
@@ -1173,7 +1188,7 @@ fh_k_cg_res64(FhCgFused P, FhCgRes64 R) {
     FH_R64TRACE(10);
   }
   if (!z_ready) fh_mbar_wait(&sm.bar, 0);
-  if (fuse == 4 && !R.apply_only) { if (yown) R.x_out[yoff + tid] = x[0]; }
+  if (fuse == 4 && !R.apply_only) { if (yown) R.x_out[yidx] = x[0]; }
   else fh_r64_store(R.x_out + soff, x, npair);
   if (s == 0 && tid == 0) {
     FhCgScalars* w = P.sc + R.image;
