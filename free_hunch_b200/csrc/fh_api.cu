@@ -1333,20 +1333,27 @@ static size_t res64_conv_gbuf(const fh_op* o, int cw) {
 }
 // The non-separable operators' description for the float64 kernel at rank m (mode 0 when the operator folds into the DCT
 // passes or has no gathers here: the caller then falls back to the streaming float32 iteration).  The 2-D PSF gather
-// trades shared memory against L2 round trips: one chunk = one round trip (~2 us), and every 6 KB given to it is a row of
-// Z that has to be re-read from L2 in every iteration (~0.7 us per row, measured) -- the chunk width minimising the sum.
+// trades shared memory against L2 round trips: every further chunk is a round trip more, and every 6 KB given to the staging
+// is a row of Z that has to be re-read from L2 in every iteration -- the chunk width minimising the (measured) sum.
 static FhR64Gen res64_gen(const fh_op* o, int m = 0, int smem_room = 180 * 1024) {
   FhR64Gen G{};
   if (!o) return G;
   const fh_ctx* c = o->ctx;
   if (o->kind == FH_OP_BLUR && !o->separable && o->nruns > 0 && o->nruns <= 64 && o->nrun_taps <= 2048) {
     double best = 1e30;
+    const char* force = getenv("FH_R64_CW");                 // A/B runs: force the chunk width (256, 128, 64, 32)
     for (int cw = 256; cw >= 32; cw >>= 1) {
+      if (force && atoi(force) != cw) continue;
       const size_t bytes = res64_conv_gbuf(o, cw);
       if ((long)bytes > (long)smem_room) continue;
       const int cap = std::min(FH_RES_MAXM, (int)((smem_room - (long)bytes) / (FH_RES_SLICE * 4)));
-      const int nch = FH_N / cw;
-      const double cost = 2.0 * (4.5 + nch * 2.2) + 0.7 * std::max(0, m - cap);
+      // us per iteration relative to one 256-column chunk with every row resident, fitted to measurements at ranks 0 .. 56
+      // (FH_R64_CW A/B runs): a second chunk costs 3.0, four chunks 14.3; leaving the all-resident instantiation costs ~1.5
+      // and 0.3 per re-read row for the first 8 rows, little beyond.  256 columns win everywhere except for ranks 11 .. 16,
+      // where 128 columns keep every row resident (rank 56: 64.3 against 69.0 us with the previous model's choice of 128).
+      const int nch = FH_N / cw, nl2 = std::max(0, m - cap);
+      const double cost = (nch == 1 ? 0.0 : nch == 2 ? 3.0 : nch == 4 ? 14.3 : 35.0) +
+                          (nl2 > 0 ? 1.5 + 0.3 * std::min(nl2, 8) + 0.05 * std::max(0, nl2 - 8) : 0.0);
       if (cost < best) { best = cost; G.cw = cw; G.gbuf_bytes = (int)bytes; }
     }
     if (G.cw) {

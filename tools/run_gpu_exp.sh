@@ -1,7 +1,7 @@
-# experiment harness: per-iteration time of the float64 resident kernel (x4 SR, motion blur)
-for cfg in "super_resolution 0" "motion_blur 0" "motion_blur 8" "motion_blur 28"; do
-  set -- $cfg
-  FH_TRACE=1 python tools/cg_microbench.py --f64 --batch 1 --pairs $2 --operator $1 --iters 200 --reps 3 2>/dev/null | python -c "
+for p in 4 8 28; do python tools/cg_microbench.py --f64 --batch 1 --pairs $p --operator motion_blur --iters 200 --reps 3 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1 pairs', d['pairs'], 'us/it', round(d['us_per_iteration'],2), d['cg_path'], 'niter', d['niter'], d.get('trace_us',{}).get('6'))"
-done
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('auto pairs', d['pairs'], 'us/it', round(d['us_per_iteration'],2))"; done
+python -m pytest tests -m gpu -q -x -k "motion or config" 2>&1 | tail -3
+python bench.py --operator motion_blur --solver euler --num-steps 100 --batch 1 --steps 3 --warmup 3 --no-cpu-baseline --no-unet-timing --no-unet-in-loop --batched 0 > gpurun_out/bench_r02_motion_blur_b1.json 2>/dev/null; python -c "
+import json
+d=json.loads(open('gpurun_out/bench_r02_motion_blur_b1.json').read().strip().splitlines()[-1]); print('motion b1 value', round(d['value'],2), 'e2e', round(d['e2e']['value'],2), d['hot_path']['phases_ms'], d['roofline']['us_per_cg_iteration'])"
