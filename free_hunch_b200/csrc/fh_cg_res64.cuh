@@ -652,30 +652,39 @@ __device__ __forceinline__ double fh_r64_sr_gather_a(const double* tsrc, unsigne
     if (run == 0) fh_cp_wait<1>(); else fh_cp_wait<0>();
     __syncthreads();
     const double* tile = tile0 + (size_t)run * rows0 * TW;
-    for (int g = ga; g < gb; ++g) {
-      // lane `part` of an element's 16 takes columns b = part and part + 16 of every PSF row: four independent accumulators
-      // (even / odd rows x the two columns) and no index division -- the first version walked q = part, part + 16, ... with
-      // one accumulator and q / ks per tap
-      double ac0 = 0.0, ac1 = 0.0, ac2 = 0.0, ac3 = 0.0;
-      const double* kp = spsf + part;
-      const double* tp0 = tile + (4 * (g - ga) + 2 * c) * TW + 4 * el + 2 * c - part;
-      // (fully unrolling this loop over the 25 PSF rows was measured slower: 5.8 -> 6.6 us per gather at rank 0, 12.9 -> 19.8
-      // at rank 32 -- the kernel is already at the limit of the instruction cache)
-      int a = 0;
-      for (; a + 1 < G.ks; a += 2) {
-        if (one) { ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0); ac1 = fma(kp[(a + 1) * FH_R64_SRP], tp0[-(a + 1) * TW], ac1); }
-        if (two) { ac2 = fma(kp[a * FH_R64_SRP + 16], tp0[-a * TW - 16], ac2); ac3 = fma(kp[(a + 1) * FH_R64_SRP + 16], tp0[-(a + 1) * TW - 16], ac3); }
+    // All groups of the run at once: lane `part` of an element's 16 takes columns b = part and part + 16 of every PSF row and
+    // feeds the row's two weights to the (up to 6) vertically adjacent elements it serves -- 2 + 2 n loads for 2 n FMAs.  Group
+    // by group it was 2 loads per FMA (0.9 us per group); earlier still one accumulator and q / ks per tap.  Measured inside
+    // (clock64, CTA 0, 5 groups): staging + barrier 0.8 us, this loop 4.5 us, reduction 0.6 us -- the loop runs at the pace of
+    // the shared-memory pipe: 8 warps x 12 loads x 2 wavefronts (two elements per warp span 160 bytes) per PSF row.
+    const int n = gb - ga;
+    double s0[6], s1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { s0[i] = 0.0; s1[i] = 0.0; }
+    const double* kp = spsf + part;
+    const double* tp0 = tile + (2 * c) * TW + 4 * el + 2 * c - part;
+    for (int a = 0; a < G.ks; ++a) {
+      const double k0 = one ? kp[a * FH_R64_SRP] : 0.0;
+      const double k1 = two ? kp[a * FH_R64_SRP + 16] : 0.0;
+      const double* tr = tp0 - a * TW;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < n) {
+          if (one) s0[i] = fma(k0, tr[4 * i * TW], s0[i]);
+          if (two) s1[i] = fma(k1, tr[4 * i * TW - 16], s1[i]);
+        }
       }
-      if (a < G.ks) {
-        if (one) ac0 = fma(kp[a * FH_R64_SRP], tp0[-a * TW], ac0);
-        if (two) ac2 = fma(kp[a * FH_R64_SRP + 16], tp0[-a * TW - 16], ac2);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i < n) {
+        double acc = s0[i] + s1[i];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (part == 0) qy[16 * (ga - g0 + i) + el] = acc;
       }
-      double acc = (ac0 + ac1) + (ac2 + ac3);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (part == 0) qy[16 * (g - g0) + el] = acc;
     }
   }
   __syncthreads();
