@@ -543,6 +543,33 @@ __device__ __forceinline__ void fh_r64_sr_stage_psf(double* spsf, const FhR64Gen
     spsf[i] = (a < G.ks && b < G.ks) ? (double)G.psf[a * G.ks + b] : 0.0;
   }
 }
+// The full rounds of the A^T gather for a strip whose first row is 0 (PAR = 0) or 2 (PAR = 1) modulo 4 (strips start at
+// multiples of 6; the PSF centre is a multiple of 4).  In round u row e of the strip multiplies PSF row A0[e] + 4 u with
+// measurement row YR[e] + u (relative to the first staged one): rows of the strip that share a PSF row or a measurement row
+// share the LOADS -- 7 x (3 + 4) or 7 x (2 + 4) per round instead of 7 x 12; the gather runs at the pace of the shared-memory
+// pipe.  The tables are compile-time, so the sharing is plain common-subexpression elimination.
+template <int PAR>
+__device__ __forceinline__ void fh_r64_sr_at_core(const double* spsf, const double* ys, const int (&qt)[7], int b0, int ks,
+                                                  double (&acc)[FH_RES_ROWS]) {
+  constexpr int A0[2][FH_RES_ROWS] = {{0, 3, 2, 1, 0, 3}, {2, 1, 0, 3, 2, 1}};
+  constexpr int YR[2][FH_RES_ROWS] = {{0, 1, 1, 1, 1, 2}, {1, 1, 1, 2, 2, 2}};
+  const int nfull = ks >> 2;                               // rounds in which every row's tap row A0 + 4 u exists (A0 <= 3)
+  for (int u = 0; u < nfull; ++u) {
+    const double* yu = ys + (size_t)u * 64;
+    const double* ku = spsf + (size_t)(4 * u) * FH_R64_SRP + b0;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      double yv[3], kv[4];
+#pragma unroll
+      for (int g = PAR; g < 3; ++g) yv[g] = yu[g * 64 + qt[t]];
+      if (PAR) yv[0] = 0.0;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) kv[h] = ku[h * FH_R64_SRP + 4 * t];        // taps beyond ks are zero
+#pragma unroll
+      for (int e = 0; e < FH_RES_ROWS; ++e) acc[e] = fma(kv[A0[PAR][e]], yv[YR[PAR][e]], acc[e]);
+    }
+  }
+}
 // mode 4, A^T: out rows = k (*)^T (zero insertion of the published 64 x 64 measurement plane `pl` of ysrc)   (utils_sisr.py:44-52)
 //   x[i][j] = sum over taps with (i + a - c) % 4 == 0 and (j + b - c) % 4 == 0 of k[a][b] y[((i + a - c) & 255) / 4][((j + b - c) & 255) / 4]
 __device__ __forceinline__ void fh_r64_sr_gather_at(const double* ysrc, double* out_rows, unsigned char* gbuf, const FhR64Gen& G,
@@ -577,37 +604,26 @@ __device__ __forceinline__ void fh_r64_sr_gather_at(const double* ysrc, double* 
 #pragma unroll
   for (int t = 0; t < 7; ++t) qt[t] = ((j + b0 + 4 * t - c) >> 2) & 63;
   // All 6 rows of the strip at once: 6 independent accumulator chains (the first version walked the rows one after another
-  // with ONE accumulator -- 49 dependent DFMAs per output, 294 per thread, at the latency of the FP64 pipe: 20 us of a 45 us
-  // iteration).  Row e takes the taps a = a0[e] + 4 u; per output the order of the sum is unchanged (a ascending, t
-  // ascending), so the results are bit-identical.  Rows beyond nrows (the last strip of a plane) are computed on whatever
-  // the staging area holds and never stored.
-  int a0[FH_RES_ROWS];
-  const double* yb[FH_RES_ROWS];
+  // with ONE accumulator -- 49 dependent DFMAs per output, 294 per thread, every one behind its own two shared-memory loads:
+  // 20 us of a 45 us iteration).  Row e takes the tap rows a = a0[e] + 4 u; per output the order of the sum is unchanged
+  // (a ascending, t ascending), so the results are bit-identical.  Rows beyond nrows (the last strip of a plane) are computed
+  // on whatever the staging area holds and never stored.
   double acc[FH_RES_ROWS];
 #pragma unroll
-  for (int e = 0; e < FH_RES_ROWS; ++e) {
-    const int i = row0 + e;
-    a0[e] = (4 - ((i - c) & 3)) & 3;
-    yb[e] = ys + (size_t)(((i + a0[e] - c) >> 2) - Ilo) * 64;              // + 64 per round: a grows by 4
-    acc[e] = 0.0;
-  }
-  const int nfull = G.ks >> 2;                                             // rounds in which every row's tap row a0 + 4 u exists (a0 <= 3)
-  for (int u = 0; u < nfull; ++u) {
+  for (int e = 0; e < FH_RES_ROWS; ++e) acc[e] = 0.0;
+  if ((row0 >> 1) & 1) fh_r64_sr_at_core<1>(spsf, ys, qt, b0, G.ks, acc);
+  else fh_r64_sr_at_core<0>(spsf, ys, qt, b0, G.ks, acc);
+  {
+    const int nfull = G.ks >> 2;
 #pragma unroll
     for (int e = 0; e < FH_RES_ROWS; ++e) {
-      const double* yr = yb[e] + u * 64;
-      const double* kr = spsf + (a0[e] + 4 * u) * FH_R64_SRP + b0;
+      const int a0e = (4 - ((row0 + e - c) & 3)) & 3;
+      for (int a = a0e + 4 * nfull; a < G.ks; a += 4) {
+        const double* yr = ys + (size_t)(((row0 + e + a - c) >> 2) - Ilo) * 64;
+        const double* kr = spsf + a * FH_R64_SRP + b0;
 #pragma unroll
-      for (int t = 0; t < 7; ++t) acc[e] = fma(kr[4 * t], yr[qt[t]], acc[e]);   // taps beyond ks are zero
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < FH_RES_ROWS; ++e) {
-    for (int a = a0[e] + 4 * nfull; a < G.ks; a += 4) {
-      const double* yr = ys + (size_t)(((row0 + e + a - c) >> 2) - Ilo) * 64;
-      const double* kr = spsf + a * FH_R64_SRP + b0;
-#pragma unroll
-      for (int t = 0; t < 7; ++t) acc[e] = fma(kr[4 * t], yr[qt[t]], acc[e]);
+        for (int t = 0; t < 7; ++t) acc[e] = fma(kr[4 * t], yr[qt[t]], acc[e]);
+      }
     }
   }
 #pragma unroll
