@@ -503,9 +503,9 @@ __device__ __forceinline__ void fh_r64_gather_conv(const double* src, double* ou
       // Six taps per round with a compile-time rotation of the window: before tap k slot j holds the input row congruent
       // to j (mod 6) among rows k .. k+5, so output e reads slot (e + k) % 6 and the dead slot k % 6 takes row k + 6.
       for (int k0 = 0; k0 < r.z; k0 += FH_RES_ROWS) {
-        // (measured: neither skipping the 125 zero-weight taps of the motion PSF's 342 padded ones nor loading the weights
-        // as 16-byte pairs changes the 12.5 us of a gather: it is bound by the latency of its short dependent runs -- 16
-        // runs of 1..5 rounds, descriptor -> pointers -> window -> rounds -- at 8 warps per SM, not by instruction counts)
+        // (measured, 12.5 us per gather at rank 0: skipping the 125 zero-weight taps of the motion PSF's 342 padded ones or
+        // loading the weights as 16-byte pairs changes nothing; two runs in flight per thread with separate accumulators
+        // -- twice the loads in flight per round -- is SLOWER: 13.3 us, 64.6 -> 72.7 us per iteration at rank 56)
 #pragma unroll
         for (int kk = 0; kk < FH_RES_ROWS; ++kk) {
           const double wv = w[k0 + kk];
